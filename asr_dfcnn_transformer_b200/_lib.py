@@ -1,0 +1,95 @@
+"""ctypes binding of libasrk.so (include/asrk.h).
+
+There is deliberately no fallback: if the CUDA library is missing or fails to
+load, every product entry point raises.  ``torch`` is used only as the carrier of
+device memory and streams.
+"""
+import ctypes
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libasrk.so")
+
+OK = 0
+E_BADARG, E_SHAPE, E_ALIGN, E_WORKSPACE, E_CUDA = -1, -2, -3, -4, -5
+ROW_OK, ROW_INFEASIBLE, ROW_NOT_ENOUGH_TIME, ROW_BAD_LENGTH = 0, 1, 2, 3
+SPEC_FBANK, SPEC_ASRT, SPEC_FBANK_RAW = 0, 1, 2
+DTYPE_I16, DTYPE_F32 = 0, 1
+LABELS_BY_LENGTH, LABELS_DROP_ZEROS = 0, 1
+
+# every symbol include/asrk.h declares: (restype, argtypes)
+_vp, _i, _ll, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t
+SIGNATURES = {
+    "asrk_version": (_i, []),
+    "asrk_error_string": (ctypes.c_char_p, [_i]),
+    "asrk_spectrogram_workspace_bytes": (_sz, [_i, _ll]),
+    "asrk_spectrogram_run": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _sz,
+                                  _vp]),
+    "asrk_snr2k_run": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "asrk_ctc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "asrk_ctc_loss_grad_run": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp,
+                                    _ll, _ll, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "asrk_ctc_decode_workspace_bytes": (_sz, [_i, _i]),
+    "asrk_ctc_greedy_decode_run": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp,
+                                        _sz, _vp]),
+}
+
+
+class AsrkError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = "asrk status %d" % code
+        try:
+            msg = lib().asrk_error_string(code).decode()
+        except Exception:
+            pass
+        super().__init__("%s: %s (%d)" % (where, msg, code))
+
+
+_lib = None
+
+
+def lib():
+    """Load libasrk.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            "libasrk.so is not built (%s). Run `python -m asr_dfcnn_transformer_b200._build`; "
+            "there is no CPU fallback." % LIB_PATH)
+    try:
+        import torch  # noqa: F401  (loads libcudart.so.12 so the library resolves it)
+    except Exception:
+        pass
+    handle = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)   # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def check(code, where):
+    if code != OK:
+        raise AsrkError(code, where)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("asr_dfcnn_transformer_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+    return torch
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)

@@ -1,0 +1,183 @@
+// Straight-line fp64 DFT codelets used by the spectrogram kernel.
+//
+// The 400-point real transform of one windowed frame (util/wav_util.py:70-75 in
+// the reference: fft(data_line * w), bins 0..199 kept) is computed as a
+// 200-point complex transform of z[m] = x[2m] + i x[2m+1] followed by the
+// real-input split.  200 = 20 x 10 (Cooley-Tukey), and both factors are
+// themselves done twiddle-free with the Good-Thomas prime-factor map
+// (20 = 4 x 5, 10 = 2 x 5).  Everything here is register-resident and fully
+// unrolled; indices are compile-time constants.
+//
+// The header compiles for the host as well (tests/test_fft_codelets.py builds a
+// tiny g++ harness around it) so the index maps are checked on the CPU.
+#pragma once
+
+#if defined(__CUDACC__)
+#define ASRK_HD __host__ __device__ __forceinline__
+#else
+#define ASRK_HD inline
+#endif
+
+namespace asrk {
+
+struct cplx {
+    double x, y;
+};
+
+ASRK_HD cplx cadd(cplx a, cplx b) { return cplx{a.x + b.x, a.y + b.y}; }
+ASRK_HD cplx csub(cplx a, cplx b) { return cplx{a.x - b.x, a.y - b.y}; }
+ASRK_HD cplx cmul(cplx a, cplx b) {
+    return cplx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+
+// cos(2 pi/5), cos(4 pi/5), sin(2 pi/5), sin(4 pi/5)
+#define ASRK_C1 0.30901699437494742410
+#define ASRK_C2 -0.80901699437494742410
+#define ASRK_S1 0.95105651629515357212
+#define ASRK_S2 0.58778525229247312917
+
+// forward 5-point DFT (kernel exp(-2 pi i nk/5)), in place.
+ASRK_HD void dft5(cplx& a0, cplx& a1, cplx& a2, cplx& a3, cplx& a4) {
+    cplx t1 = cadd(a1, a4), t2 = cadd(a2, a3);
+    cplx t3 = csub(a1, a4), t4 = csub(a2, a3);
+    cplx m1{a0.x + ASRK_C1 * t1.x + ASRK_C2 * t2.x, a0.y + ASRK_C1 * t1.y + ASRK_C2 * t2.y};
+    cplx m2{a0.x + ASRK_C2 * t1.x + ASRK_C1 * t2.x, a0.y + ASRK_C2 * t1.y + ASRK_C1 * t2.y};
+    cplx s1{ASRK_S1 * t3.x + ASRK_S2 * t4.x, ASRK_S1 * t3.y + ASRK_S2 * t4.y};
+    cplx s2{ASRK_S2 * t3.x - ASRK_S1 * t4.x, ASRK_S2 * t3.y - ASRK_S1 * t4.y};
+    a0 = cplx{a0.x + t1.x + t2.x, a0.y + t1.y + t2.y};
+    a1 = cplx{m1.x + s1.y, m1.y - s1.x};   // m1 - i s1
+    a4 = cplx{m1.x - s1.y, m1.y + s1.x};   // m1 + i s1
+    a2 = cplx{m2.x + s2.y, m2.y - s2.x};
+    a3 = cplx{m2.x - s2.y, m2.y + s2.x};
+}
+
+// forward 4-point DFT, in place.
+ASRK_HD void dft4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+    cplx s02 = cadd(a0, a2), d02 = csub(a0, a2);
+    cplx s13 = cadd(a1, a3), d13 = csub(a1, a3);
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = cplx{d02.x + d13.y, d02.y - d13.x};   // d02 - i d13
+    a3 = cplx{d02.x - d13.y, d02.y + d13.x};   // d02 + i d13
+}
+
+ASRK_HD void dft2(cplx& a0, cplx& a1) {
+    cplx s = cadd(a0, a1), d = csub(a0, a1);
+    a0 = s;
+    a1 = d;
+}
+
+// 20-point forward DFT, in -> out (natural order both sides), prime-factor map
+//   n = (5 n1 + 4 n2) mod 20,  k = (5 k1 + 16 k2) mod 20,  n1,k1 < 4, n2,k2 < 5.
+ASRK_HD void dft20(const cplx (&in)[20], cplx (&out)[20]) {
+    cplx a[4][5];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+#pragma unroll
+        for (int n1 = 0; n1 < 4; ++n1) a[n1][n2] = in[(5 * n1 + 4 * n2) % 20];
+        dft4(a[0][n2], a[1][n2], a[2][n2], a[3][n2]);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        dft5(a[k1][0], a[k1][1], a[k1][2], a[k1][3], a[k1][4]);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) out[(5 * k1 + 16 * k2) % 20] = a[k1][k2];
+    }
+}
+
+// 10-point forward DFT: n = (5 n1 + 2 n2) mod 10, k = (5 k1 + 6 k2) mod 10.
+ASRK_HD void dft10(const cplx (&in)[10], cplx (&out)[10]) {
+    cplx a[2][5];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        a[0][n2] = in[(2 * n2) % 10];
+        a[1][n2] = in[(5 + 2 * n2) % 10];
+        dft2(a[0][n2], a[1][n2]);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 2; ++k1) {
+        dft5(a[k1][0], a[k1][1], a[k1][2], a[k1][3], a[k1][4]);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) out[(5 * k1 + 6 * k2) % 10] = a[k1][k2];
+    }
+}
+
+}  // namespace asrk
+
+// ---------------------------------------------------------------------------
+// 200-point complex FFT split in two "roles passes" (see spectrogram.cu):
+//   Z[k1 + 20 k2] = sum_{n2<10} W200^{n2 k1} ( sum_{n1<20} z[10 n1 + n2] W20^{n1 k1} ) W10^{n2 k2}
+// pass 1, role r = n2:  y[k1] = W200^{r k1} * DFT20_{n1}( z[10 n1 + r] )
+// pass 2, role j     :  DFT10 over n2 for k1 = j and k1 = 20 - j (role 0: k1 = 0
+//                       and 10) -- the two k1 rows that hold each other's mirror
+//                       bins, so the real-input split
+//   2 X[k]         = (A + B) + O,   A = Z[k], B = conj(Z[200-k]),
+//   2 conj(X[200-k]) = (A + B) - O, O = (-i W400^k) (A - B)
+//                       runs on registers of one thread.
+// ---------------------------------------------------------------------------
+namespace asrk {
+
+// tw[k1] = W200^{r k1}
+ASRK_HD void fft200_pass1(const cplx (&z)[20], const cplx* tw, cplx (&y)[20]) {
+    dft20(z, y);
+#pragma unroll
+    for (int k1 = 1; k1 < 20; ++k1) y[k1] = cmul(y[k1], tw[k1]);
+}
+
+// |X|^2 * 4 for the bin pair (k, 200-k)
+ASRK_HD void split_pair(cplx A, cplx Zm, cplx P, double& pk, double& pm) {
+    cplx B{Zm.x, -Zm.y};
+    cplx E = cadd(A, B), D = csub(A, B);
+    cplx O = cmul(P, D);
+    double ex = E.x + O.x, ey = E.y + O.y;
+    double fx = E.x - O.x, fy = E.y - O.y;
+    pk = ex * ex + ey * ey;
+    pm = fx * fx + fy * fy;
+}
+
+// LoadY(k1, n2) -> cplx ; P[k] = -i W400^k = (-sin(2 pi k/400), -cos(2 pi k/400));
+// Emit(k, four_times_power) is called exactly once for every bin k in 0..199
+// owned by role j (20 bins per role).
+template <class LoadY, class Emit>
+ASRK_HD void fft200_pass2(int j, const LoadY& loadY, const cplx* P, const Emit& emit) {
+    const int k1a = (j == 0) ? 0 : j;
+    const int k1b = (j == 0) ? 10 : 20 - j;
+    cplx in[10], za[10], zb[10];
+#pragma unroll
+    for (int n2 = 0; n2 < 10; ++n2) in[n2] = loadY(k1a, n2);
+    dft10(in, za);   // za[k2] = Z[k1a + 20 k2]
+#pragma unroll
+    for (int n2 = 0; n2 < 10; ++n2) in[n2] = loadY(k1b, n2);
+    dft10(in, zb);   // zb[k2] = Z[k1b + 20 k2]
+    if (j != 0) {
+#pragma unroll
+        for (int k2 = 0; k2 < 10; ++k2) {
+            const int k = j + 20 * k2;
+            double pk, pm;
+            split_pair(za[k2], zb[9 - k2], P[k], pk, pm);
+            emit(k, pk);
+            emit(200 - k, pm);
+        }
+    } else {
+        // row k1 = 0: bins 20 k2, mirror 20 (10 - k2); k2 = 0 and 5 are their own mirror
+#pragma unroll
+        for (int k2 = 0; k2 <= 5; ++k2) {
+            const int k = 20 * k2;
+            double pk, pm;
+            split_pair(za[k2], za[(10 - k2) % 10], P[k], pk, pm);
+            emit(k, pk);
+            if (k2 != 0 && k2 != 5) emit(200 - k, pm);
+        }
+        // row k1 = 10: bins 10 + 20 k2, mirror 10 + 20 (9 - k2)
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) {
+            const int k = 10 + 20 * k2;
+            double pk, pm;
+            split_pair(zb[k2], zb[9 - k2], P[k], pk, pm);
+            emit(k, pk);
+            emit(200 - k, pm);
+        }
+    }
+}
+
+}  // namespace asrk

@@ -1,0 +1,675 @@
+// Parts 2 and 3 of the hot path: CTC loss forward-backward with the gradient
+// w.r.t. the logits, and greedy CTC decode.
+//
+// Reference call sites: K.ctc_batch_cost (lm_and_am/model/cnn_ctc.py:149-152),
+// tf.nn.ctc_loss_v2 (lm_and_am/model/acoustic_model2.py:79-80),
+// tf.nn.ctc_greedy_decoder (acoustic_model2.py:69, consumed at lm_and_am/test.py:
+// 48-52), util/utils.py:57-66 decode_ctc.  The arithmetic is TensorFlow's
+// CTCLossOp / CTCGreedyDecoderOp (third-party, restated in oracle/ctc_ref.py).
+//
+// Four launches per call (DESIGN.md "CTC kernels"):
+//   prep    : one thread per utterance -- effective label list (by length / drop
+//             zeros), feasibility, chains of repeated labels.
+//   rows    : one WARP per (t,b) row -- the 5.7 KB row is read once with 16-byte
+//             streaming loads into registers: max, first arg-max (greedy decode),
+//             log-sum-exp, and the gather of the few log-probabilities the lattice
+//             needs (blank + labels).  HBM-bound.
+//   lattice : one CTA per utterance -- log-space alpha / beta over the
+//             label-extended lattice, one (blank,label) state pair per thread so a
+//             step needs ONE neighbour value; periodic exact max-renormalisation
+//             keeps fp32 accurate for T in the thousands.  Latency-bound, tiny.
+//   grad    : one WARP per row -- softmax from the (L2-resident) row and the
+//             stored log-sum-exp, minus the lattice occupancies of blank and
+//             labels, written once with 16-byte stores; zero rows for t >= len.
+//             HBM-bound.  Repeated labels are summed along precomputed chains in
+//             a fixed order (no atomics): results are bit-reproducible.
+#include <math.h>
+
+#include "asrk_common.cuh"
+
+namespace asrk {
+namespace ctc {
+
+constexpr int kRowWarps = 8;                 // warps per CTA in the row kernels
+constexpr int kRenorm = 8;                   // lattice renormalisation period (steps)
+constexpr float kNegInf = -INFINITY;
+
+struct Params {
+    const float* logits;
+    long long stride_t, stride_b;
+    int T, B, V;
+    const int* labels;
+    int label_stride;
+    const int* label_len;
+    const int* input_len;
+    int blank;
+    int label_mode;
+    const float* grad_scale;
+    float* loss;
+    float* grad;
+    long long gstride_t, gstride_b;
+    int* row_status;
+    int* tokens;
+    int token_stride;
+    int* token_len;
+    float* neg_sum_logits;
+    int merge_repeated;
+    // workspace
+    int* eff_labels;     // [B][Ls]
+    int* eff_len;        // [B]
+    int* chain_next;     // [B][Ls]  next position with the same label, -1 at the end
+    int* chain_first;    // [B][Ls]  1 if no earlier position has the same label
+    float* lse;          // [B][T]
+    float* rowmax;       // [B][T]
+    int* argmax;         // [B][T]
+    float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (log-softmax)
+    float* occ;          // [B][T][2 Ls+1] alpha (scaled) then occupancy, lattice order
+    double* coff;        // [B][T]        alpha offsets
+    double* logp;        // [B]
+    int Ls;              // label_stride
+};
+
+struct WsLayout {
+    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, coff, logp, total;
+};
+
+static WsLayout ws_layout(int T, int B, int Ls) {
+    WsLayout l;
+    size_t o = 0;
+    const size_t BT = (size_t)B * (size_t)T;
+    l.eff_labels = o;  o = align_up(o + sizeof(int) * (size_t)B * Ls, 256);
+    l.eff_len = o;     o = align_up(o + sizeof(int) * (size_t)B, 256);
+    l.chain_next = o;  o = align_up(o + sizeof(int) * (size_t)B * Ls, 256);
+    l.chain_first = o; o = align_up(o + sizeof(int) * (size_t)B * Ls, 256);
+    l.lse = o;         o = align_up(o + sizeof(float) * BT, 256);
+    l.rowmax = o;      o = align_up(o + sizeof(float) * BT, 256);
+    l.argmax = o;      o = align_up(o + sizeof(int) * BT, 256);
+    l.lpl = o;         o = align_up(o + sizeof(float) * BT * (size_t)(Ls + 1), 256);
+    l.occ = o;         o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
+    l.coff = o;        o = align_up(o + sizeof(double) * BT, 256);
+    l.logp = o;        o = align_up(o + sizeof(double) * (size_t)B, 256);
+    l.total = o;
+    return l;
+}
+
+// ---------------------------------------------------------------------------
+// prep
+// ---------------------------------------------------------------------------
+__global__ void prep_kernel(Params p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int* lab = p.labels + (size_t)b * p.label_stride;
+    int* eff = p.eff_labels + (size_t)b * p.Ls;
+    int* nxt = p.chain_next + (size_t)b * p.Ls;
+    int* fst = p.chain_first + (size_t)b * p.Ls;
+    int status = ASRK_ROW_OK;
+    int L = 0;
+    if (p.label_mode == ASRK_LABELS_BY_LENGTH) {
+        L = p.label_len[b];
+        if (L < 0 || L > p.label_stride) { status = ASRK_ROW_BAD_LENGTH; L = 0; }
+        for (int j = 0; j < L; ++j) eff[j] = lab[j];
+    } else {
+        // tf.contrib.layers.dense_to_sparse: every 0 entry is dropped (acoustic_model2.py:71)
+        for (int j = 0; j < p.label_stride; ++j)
+            if (lab[j] != 0) eff[L++] = lab[j];
+    }
+    const int tl = p.input_len[b];
+    if (tl < 1 || tl > p.T) status = ASRK_ROW_BAD_LENGTH;
+    int repeats = 0;
+    for (int j = 0; j < L; ++j) {
+        const int c = eff[j];
+        if (c < 0 || c >= p.V) { status = ASRK_ROW_BAD_LENGTH; eff[j] = 0; }
+        if (j > 0 && eff[j] == eff[j - 1]) ++repeats;
+    }
+    if (status == ASRK_ROW_OK && tl < L + repeats) status = ASRK_ROW_NOT_ENOUGH_TIME;
+    // chains of equal labels (O(L^2), L is at most a few hundred)
+    for (int j = 0; j < L; ++j) {
+        int n = -1;
+        for (int k = j + 1; k < L; ++k)
+            if (eff[k] == eff[j]) { n = k; break; }
+        nxt[j] = n;
+        int first = 1;
+        for (int k = 0; k < j; ++k)
+            if (eff[k] == eff[j]) { first = 0; break; }
+        fst[j] = first;
+    }
+    p.eff_len[b] = (status == ASRK_ROW_BAD_LENGTH) ? 0 : L;
+    p.row_status[b] = status;
+}
+
+// ---------------------------------------------------------------------------
+// rows: per-row max / argmax / log-sum-exp and gather of the lattice log-probs
+// ---------------------------------------------------------------------------
+template <int NV4>
+struct RowRegs {
+    float4 v[NV4];
+};
+
+// load one row (V floats, V % 4 == 0, 16-byte aligned) into registers; missing
+// tail elements are -inf
+template <int NV4>
+__device__ __forceinline__ void load_row(const float* row, int V4, int lane, RowRegs<NV4>& r) {
+    const float4* x4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+        const int i = lane + 32 * k;
+        if (i < V4) r.v[k] = __ldg(x4 + i);
+        else r.v[k] = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+    }
+}
+
+// first maximum over the row: strict '>' scan order == lowest index among equals
+template <int NV4>
+__device__ __forceinline__ void row_argmax(const RowRegs<NV4>& r, int lane, float& m, int& am) {
+    m = kNegInf;
+    am = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+        const int base = 4 * (lane + 32 * k);
+        // NaN never wins a strict '>' comparison
+        if (r.v[k].x > m) { m = r.v[k].x; am = base; }
+        if (r.v[k].y > m) { m = r.v[k].y; am = base + 1; }
+        if (r.v[k].z > m) { m = r.v[k].z; am = base + 2; }
+        if (r.v[k].w > m) { m = r.v[k].w; am = base + 3; }
+    }
+    // per-lane candidates are in increasing index order inside the lane only, so the
+    // cross-lane reduction must compare (value desc, index asc)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+    }
+    if (am == 0x7fffffff) am = 0;   // all -inf / NaN row: TF's scan leaves index 0
+}
+
+template <int NV4>
+__device__ __forceinline__ float row_sumexp(const RowRegs<NV4>& r, float m) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+        s += __expf(r.v[k].x - m);
+        s += __expf(r.v[k].y - m);
+        s += __expf(r.v[k].z - m);
+        s += __expf(r.v[k].w - m);
+    }
+    return warp_sum(s);
+}
+
+// generic (unaligned / V % 4 != 0 / very large V) row pass: two sweeps
+__device__ __forceinline__ void row_stats_generic(const float* row, int V, int lane, float& m, int& am,
+                                                  float& s) {
+    m = kNegInf;
+    am = 0x7fffffff;
+    for (int i = lane; i < V; i += 32) {
+        const float x = row[i];
+        if (x > m) { m = x; am = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+    }
+    if (am == 0x7fffffff) am = 0;
+    s = 0.f;
+    for (int i = lane; i < V; i += 32) s += __expf(row[i] - m);
+    s = warp_sum(s);
+}
+
+template <int NV4, bool WANT_LSE>
+__global__ void __launch_bounds__(kRowWarps * 32) rows_kernel(Params p) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= (long long)p.T * p.B) return;
+    const int t = (int)(row / p.B), b = (int)(row % p.B);
+    int tl = p.input_len[b];
+    if (tl > p.T) tl = p.T;
+    if (t >= tl) return;
+    const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
+    float m, s = 0.f;
+    int am;
+    if constexpr (NV4 > 0) {
+        RowRegs<NV4> r;
+        load_row(x, p.V >> 2, lane, r);
+        row_argmax(r, lane, m, am);
+        if (WANT_LSE) s = row_sumexp(r, m);
+    } else {
+        row_stats_generic(x, p.V, lane, m, am, s);
+    }
+    const size_t bt = (size_t)b * p.T + t;
+    if (lane == 0) {
+        p.rowmax[bt] = m;
+        p.argmax[bt] = am;
+    }
+    if (WANT_LSE) {
+        const float lse = m + __logf(s);
+        if (lane == 0) p.lse[bt] = lse;
+        const int L = p.eff_len[b];
+        const int* eff = p.eff_labels + (size_t)b * p.Ls;
+        float* dst = p.lpl + bt * (size_t)(p.Ls + 1);
+        for (int j = lane; j <= L; j += 32) {
+            const int c = (j == 0) ? p.blank : eff[j - 1];
+            dst[j] = x[c] - lse;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// lattice
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float lse2(float a, float b) {
+    const float m = fmaxf(a, b);
+    if (m == kNegInf) return kNegInf;
+    return m + __logf(__expf(a - m) + __expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+    const float m = fmaxf(fmaxf(a, b), c);
+    if (m == kNegInf) return kNegInf;
+    return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+// block-wide max over all threads (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ float block_max(float v, float* red) {
+    v = warp_max(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();            // red[] free
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    float r = (lane < nw) ? red[lane] : kNegInf;
+    return warp_max(r);
+}
+
+// One CTA per utterance; thread i owns the state pair
+//   alpha sweep: (blank 2i, label 2i+1)     beta sweep: (label 2i-1, blank 2i)
+// so that each step needs exactly one neighbour value (the previous / next
+// label state), exchanged through a double-buffered shared array.
+__global__ void lattice_kernel(Params p) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.x;
+    const int i = threadIdx.x;
+    const int P = blockDim.x;
+    float* xch = sm;                 // [2][P]
+    float* red = sm + 2 * P;         // [32]
+    const int status = p.row_status[b];
+    const int L = p.eff_len[b];
+    const int T = p.input_len[b];
+    if (status == ASRK_ROW_BAD_LENGTH) {
+        if (i == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = (double)kNegInf; }
+        return;
+    }
+    const int S = p.Ls + 1;
+    const int U = 2 * p.Ls + 1;
+    const float* lpl = p.lpl + (size_t)b * p.T * S;
+    float* occ = p.occ + (size_t)b * p.T * U;
+    double* coff = p.coff + (size_t)b * p.T;
+    const int* eff = p.eff_labels + (size_t)b * p.Ls;
+
+    const int lab_i = (i < L) ? eff[i] : -1;            // label index i     (state 2i+1)
+    const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;   // label index i-1 (state 2i-1)
+    // alpha: label state 2i+1 may be entered from 2i-1 when the labels differ
+    const bool skip_a = (i >= 1 && i < L && lab_i != lab_im1);
+    // beta: label state 2i-1 may step to 2i+1 when the labels differ
+    const bool skip_b = (i >= 1 && i < L && lab_i != lab_im1);
+    const bool has_blank = (i <= L);
+    const bool has_lab_a = (i < L);            // alpha pair's label state exists
+    const bool has_lab_b = (i >= 1 && i <= L); // beta pair's label state exists
+
+    // ------------------------------ alpha ------------------------------
+    float a_b = kNegInf, a_l = kNegInf;
+    if (i == 0) {
+        a_b = lpl[0];
+        if (L >= 1) a_l = lpl[1];
+    }
+    double C = 0.0;
+    if (has_blank) occ[2 * i] = a_b;
+    if (has_lab_a) occ[2 * i + 1] = a_l;
+    if (i == 0) coff[0] = 0.0;
+    for (int t = 1; t < T; ++t) {
+        float* xb = xch + (t & 1) * P;
+        xb[i] = a_l;
+        const float lb = lpl[(size_t)t * S];
+        const float ll = has_lab_a ? lpl[(size_t)t * S + 1 + i] : kNegInf;
+        __syncthreads();
+        const float p1 = (i >= 1) ? xb[i - 1] : kNegInf;
+        const float nb = lb + lse2(a_b, p1);
+        const float nl = ll + lse3(a_l, a_b, skip_a ? p1 : kNegInf);
+        a_b = has_blank ? nb : kNegInf;
+        a_l = has_lab_a ? nl : kNegInf;
+        if ((t % kRenorm) == 0) {
+            const float m = block_max(fmaxf(a_b, a_l), red);
+            if (m > kNegInf) {
+                a_b -= m;
+                a_l -= m;
+                C += (double)m;
+            }
+        }
+        float* o = occ + (size_t)t * U;
+        if (has_blank) o[2 * i] = a_b;
+        if (has_lab_a) o[2 * i + 1] = a_l;
+        if (i == 0) coff[t] = C;
+    }
+    // log p = LSE(alpha_{T-1}(2L), alpha_{T-1}(2L-1)) + C
+    __syncthreads();
+    if (i == L) red[0] = a_b;
+    if (i == L - 1) red[1] = a_l;
+    if (L == 0 && i == 0) red[1] = kNegInf;
+    __syncthreads();
+    const float fin = lse2(red[0], red[1]);
+    const double logp = (fin == kNegInf) ? (double)kNegInf : (double)fin + C;
+    if (i == 0) {
+        p.logp[b] = logp;
+        p.loss[b] = (float)(-logp);
+        if (fin == kNegInf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
+    }
+    if (p.grad == nullptr || fin == kNegInf) return;   // uniform over the CTA
+    __syncthreads();
+
+    // ------------------------------ beta -------------------------------
+    // beta excludes y_t; e(u) = beta_{t+1}(u) + log y_{t+1}(l'_u)
+    float b_l = kNegInf, b_b = kNegInf;
+    if (i == L) {
+        b_b = 0.f;
+        if (L >= 1) b_l = 0.f;
+    }
+    double Dn = 0.0;
+    {
+        const int t = T - 1;
+        float* o = occ + (size_t)t * U;
+        const float off = (float)(coff[t] + Dn - logp);
+        if (has_blank) o[2 * i] = __expf(o[2 * i] + b_b + off);
+        if (has_lab_b) o[2 * i - 1] = __expf(o[2 * i - 1] + b_l + off);
+    }
+    for (int t = T - 2; t >= 0; --t) {
+        const float lb = lpl[(size_t)(t + 1) * S];
+        const float ll = has_lab_b ? lpl[(size_t)(t + 1) * S + i] : kNegInf;   // label index i-1 -> slot i
+        const float e_b = b_b + lb;
+        const float e_l = b_l + ll;
+        float* xb = xch + (t & 1) * P;
+        xb[i] = e_l;
+        __syncthreads();
+        const float n1 = (i + 1 < P) ? xb[i + 1] : kNegInf;   // e of label state 2i+1
+        const float nbb = lse2(e_b, n1);
+        const float nbl = lse3(e_l, e_b, skip_b ? n1 : kNegInf);
+        b_b = has_blank ? nbb : kNegInf;
+        b_l = has_lab_b ? nbl : kNegInf;
+        if ((t % kRenorm) == 0) {
+            const float m = block_max(fmaxf(b_b, b_l), red);
+            if (m > kNegInf) {
+                b_b -= m;
+                b_l -= m;
+                Dn += (double)m;
+            }
+        }
+        float* o = occ + (size_t)t * U;
+        const float off = (float)(coff[t] + Dn - logp);
+        if (has_blank) o[2 * i] = __expf(o[2 * i] + b_b + off);
+        if (has_lab_b) o[2 * i - 1] = __expf(o[2 * i - 1] + b_l + off);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// grad
+// ---------------------------------------------------------------------------
+template <int NV4>
+__global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= (long long)p.T * p.B) return;
+    const int t = (int)(row / p.B), b = (int)(row % p.B);
+    float* g = p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b;
+    const int tl = p.input_len[b];
+    const int status = p.row_status[b];
+    const int V = p.V;
+    if (t >= tl || status == ASRK_ROW_BAD_LENGTH) {
+        if constexpr (NV4 > 0) {
+            float4* g4 = reinterpret_cast<float4*>(g);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = lane; i < (V >> 2); i += 32) stg_stream(g4 + i, z);
+        } else {
+            for (int i = lane; i < V; i += 32) g[i] = 0.f;
+        }
+        return;
+    }
+    const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
+    const size_t bt = (size_t)b * p.T + t;
+    const float lse = p.lse[bt];
+    const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
+    if constexpr (NV4 > 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* g4 = reinterpret_cast<float4*>(g);
+        const int V4 = V >> 2;
+        float4 v[(NV4 > 0 ? NV4 : 1)];
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+            const int i = lane + 32 * k;
+            if (i < V4) v[k] = ldg_stream(x4 + i);
+        }
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+            const int i = lane + 32 * k;
+            if (i < V4) {
+                float4 y;
+                y.x = __expf(v[k].x - lse) * scale;
+                y.y = __expf(v[k].y - lse) * scale;
+                y.z = __expf(v[k].z - lse) * scale;
+                y.w = __expf(v[k].w - lse) * scale;
+                stg_stream(g4 + i, y);
+            }
+        }
+    } else {
+        for (int i = lane; i < V; i += 32) g[i] = __expf(x[i] - lse) * scale;
+    }
+    if (status != ASRK_ROW_OK) return;   // TF: no valid path -> dy = y
+    __syncwarp();
+    // subtract the lattice occupancies: blank = sum over even states; every distinct
+    // label = sum over its chain of positions (fixed order)
+    const int L = p.eff_len[b];
+    const int U = 2 * p.Ls + 1;
+    const float* occ = p.occ + bt * (size_t)U;
+    const float* lpl = p.lpl + bt * (size_t)(p.Ls + 1);
+    const int* eff = p.eff_labels + (size_t)b * p.Ls;
+    const int* nxt = p.chain_next + (size_t)b * p.Ls;
+    const int* fst = p.chain_first + (size_t)b * p.Ls;
+    float ob = 0.f;
+    for (int j = lane; j <= L; j += 32) ob += occ[2 * j];
+    ob = warp_sum(ob);
+    for (int j = lane; j < L; j += 32) {
+        if (fst[j]) {
+            float o = 0.f;
+            for (int k = j; k >= 0; k = nxt[k]) o += occ[2 * k + 1];
+            const int c = eff[j];
+            // a label equal to the blank index is folded into the blank entry below
+            if (c != p.blank) g[c] = (__expf(lpl[1 + j]) - o) * scale;
+        }
+    }
+    // labels that coincide with the blank index (pathological but legal input)
+    float extra = 0.f;
+    for (int j = lane; j < L; j += 32)
+        if (eff[j] == p.blank) extra += occ[2 * j + 1];
+    extra = warp_sum(extra);
+    if (lane == 0) g[p.blank] = (__expf(lpl[0]) - (ob + extra)) * scale;
+}
+
+// ---------------------------------------------------------------------------
+// greedy decode: collapse repeats / drop blanks with a warp ballot + prefix count
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) collapse_kernel(Params p) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= p.B) return;
+    int tl = p.input_len[b];
+    if (tl < 0) tl = 0;
+    if (tl > p.T) tl = p.T;
+    const int* am = p.argmax + (size_t)b * p.T;
+    const float* mx = p.rowmax + (size_t)b * p.T;
+    int* out = p.tokens + (size_t)b * p.token_stride;
+    int count = 0;
+    int carry_prev = -1;           // class of the last frame of the previous chunk
+    double nsl = 0.0;
+    for (int base = 0; base < tl; base += 32) {
+        const int t = base + lane;
+        const bool in = t < tl;
+        const int c = in ? am[t] : -1;
+        int prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0) prev = carry_prev;
+        const bool keep = in && c != p.blank && !(p.merge_repeated && c == prev);
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        if (keep && count + rank < p.token_stride) out[count + rank] = c;
+        count += __popc(mask);
+        carry_prev = __shfl_sync(0xffffffffu, c, 31);
+        if (in) nsl += (double)mx[t];
+    }
+    nsl = warp_sum(nsl);
+    if (lane == 0) {
+        p.token_len[b] = count < p.token_stride ? count : p.token_stride;
+        if (p.neg_sum_logits) p.neg_sum_logits[b] = (float)(-nsl);
+    }
+}
+
+static int pick_nv4(const Params& p, const void* a, long long st, long long sb, const void* g,
+                    long long gt, long long gb) {
+    // vector path: V % 4 == 0, 16-byte aligned bases and strides, V <= 2048
+    if (p.V % 4 != 0 || p.V > 2048) return 0;
+    if ((reinterpret_cast<uintptr_t>(a) & 15) || (st % 4) || (sb % 4)) return 0;
+    if (g && ((reinterpret_cast<uintptr_t>(g) & 15) || (gt % 4) || (gb % 4))) return 0;
+    const int v4 = p.V / 4;
+    if (v4 <= 32 * 4) return 4;
+    if (v4 <= 32 * 8) return 8;
+    if (v4 <= 32 * 12) return 12;
+    return 16;
+}
+
+template <bool WANT_LSE>
+static void launch_rows(const Params& p, int nv4, cudaStream_t stream) {
+    const long long rows = (long long)p.T * p.B;
+    const unsigned grid = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+    switch (nv4) {
+        case 4: rows_kernel<4, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 8: rows_kernel<8, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 12: rows_kernel<12, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 16: rows_kernel<16, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        default: rows_kernel<0, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+    }
+}
+
+static void launch_grad(const Params& p, int nv4, cudaStream_t stream) {
+    const long long rows = (long long)p.T * p.B;
+    const unsigned grid = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+    switch (nv4) {
+        case 4: grad_kernel<4><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 8: grad_kernel<8><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 12: grad_kernel<12><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 16: grad_kernel<16><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        default: grad_kernel<0><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+    }
+}
+
+}  // namespace ctc
+}  // namespace asrk
+
+using namespace asrk;
+using namespace asrk::ctc;
+
+extern "C" size_t asrk_ctc_workspace_bytes(int T, int B, int label_stride) {
+    if (T <= 0 || B <= 0 || label_stride < 0) return 0;
+    return ws_layout(T, B, label_stride < 1 ? 1 : label_stride).total;
+}
+
+extern "C" size_t asrk_ctc_decode_workspace_bytes(int T, int B) {
+    if (T <= 0 || B <= 0) return 0;
+    return ws_layout(T, B, 1).total;
+}
+
+static void bind_workspace(Params& p, void* workspace, const WsLayout& l) {
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    p.eff_labels = reinterpret_cast<int*>(ws + l.eff_labels);
+    p.eff_len = reinterpret_cast<int*>(ws + l.eff_len);
+    p.chain_next = reinterpret_cast<int*>(ws + l.chain_next);
+    p.chain_first = reinterpret_cast<int*>(ws + l.chain_first);
+    p.lse = reinterpret_cast<float*>(ws + l.lse);
+    p.rowmax = reinterpret_cast<float*>(ws + l.rowmax);
+    p.argmax = reinterpret_cast<int*>(ws + l.argmax);
+    p.lpl = reinterpret_cast<float*>(ws + l.lpl);
+    p.occ = reinterpret_cast<float*>(ws + l.occ);
+    p.coff = reinterpret_cast<double*>(ws + l.coff);
+    p.logp = reinterpret_cast<double*>(ws + l.logp);
+}
+
+extern "C" int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long stride_b,
+                                      int T, int B, int V, const int* labels, int label_stride,
+                                      const int* label_len, const int* input_len, int blank,
+                                      int label_mode, const float* grad_scale, float* loss, float* grad,
+                                      long long gstride_t, long long gstride_b, int* row_status,
+                                      int* tokens, int token_stride, int* token_len,
+                                      float* neg_sum_logits, void* workspace, size_t workspace_bytes,
+                                      asrk_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (T < 0 || B < 0 || V < 1 || label_stride < 0) return ASRK_E_BADARG;
+    if (B == 0 || T == 0) return ASRK_OK;
+    if (!logits || !labels || !input_len || !loss || !row_status || !workspace) return ASRK_E_BADARG;
+    if (label_mode != ASRK_LABELS_BY_LENGTH && label_mode != ASRK_LABELS_DROP_ZEROS) return ASRK_E_BADARG;
+    if (label_mode == ASRK_LABELS_BY_LENGTH && !label_len) return ASRK_E_BADARG;
+    if (blank < 0 || blank >= V) return ASRK_E_BADARG;
+    if (tokens && (!token_len || token_stride < 1)) return ASRK_E_BADARG;
+    if (label_stride + 1 > 1024) return ASRK_E_SHAPE;   // one state pair per thread
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return ASRK_E_WORKSPACE;
+    const int Ls = label_stride < 1 ? 1 : label_stride;
+    const WsLayout l = ws_layout(T, B, Ls);
+    if (workspace_bytes < l.total) return ASRK_E_WORKSPACE;
+
+    Params p{};
+    p.logits = logits; p.stride_t = stride_t; p.stride_b = stride_b;
+    p.T = T; p.B = B; p.V = V;
+    p.labels = labels; p.label_stride = label_stride;
+    p.label_len = label_len; p.input_len = input_len;
+    p.blank = blank; p.label_mode = label_mode;
+    p.grad_scale = grad_scale; p.loss = loss;
+    p.grad = grad; p.gstride_t = gstride_t; p.gstride_b = gstride_b;
+    p.row_status = row_status;
+    p.tokens = tokens; p.token_stride = token_stride; p.token_len = token_len;
+    p.neg_sum_logits = neg_sum_logits; p.merge_repeated = 1;
+    p.Ls = Ls;
+    bind_workspace(p, workspace, l);
+
+    const int nv4 = pick_nv4(p, logits, stride_t, stride_b, grad, gstride_t, gstride_b);
+    prep_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p);
+    launch_rows<true>(p, nv4, stream);
+    int P = ((label_stride + 1) + 31) / 32 * 32;
+    lattice_kernel<<<B, P, sizeof(float) * (2 * P + 32), stream>>>(p);
+    if (grad) launch_grad(p, nv4, stream);
+    if (tokens) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
+    return launch_status();
+}
+
+extern "C" int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long long stride_b,
+                                          int T, int B, int V, const int* input_len, int blank,
+                                          int merge_repeated, int* tokens, int token_stride,
+                                          int* token_len, float* neg_sum_logits, void* workspace,
+                                          size_t workspace_bytes, asrk_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (T < 0 || B < 0 || V < 1) return ASRK_E_BADARG;
+    if (B == 0) return ASRK_OK;
+    if (!logits || !input_len || !tokens || !token_len || !workspace) return ASRK_E_BADARG;
+    if (token_stride < 1) return ASRK_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return ASRK_E_WORKSPACE;
+    const int Teff = T < 1 ? 1 : T;
+    const WsLayout l = ws_layout(Teff, B, 1);
+    if (workspace_bytes < l.total) return ASRK_E_WORKSPACE;
+    Params p{};
+    p.logits = logits; p.stride_t = stride_t; p.stride_b = stride_b;
+    p.T = T; p.B = B; p.V = V;
+    p.input_len = input_len; p.blank = blank;
+    p.tokens = tokens; p.token_stride = token_stride; p.token_len = token_len;
+    p.neg_sum_logits = neg_sum_logits; p.merge_repeated = merge_repeated ? 1 : 0;
+    p.Ls = 1;
+    bind_workspace(p, workspace, l);
+    if (T > 0) {
+        const int nv4 = pick_nv4(p, logits, stride_t, stride_b, nullptr, 0, 0);
+        launch_rows<false>(p, nv4, stream);
+    }
+    collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
+    return launch_status();
+}

@@ -1,0 +1,239 @@
+"""CTC loss / gradient and greedy decode: host side of asrk_ctc_*.
+
+Mirrors the call surface the reference's models use (names, argument meaning,
+error behaviour):
+  * ``ctc_batch_cost(y_true, y_pred, input_length, label_length)`` -- Keras
+    ``K.ctc_batch_cost`` as called through ``ctc_lambda``
+    (lm_and_am/model/cnn_ctc.py:149-152): softmax input ``[B,T,V]``, blank =
+    V-1, ``log(y_pred + 1e-7)``, labels masked by ``label_length``, ``[B,1]``.
+  * ``ctc_loss_v2(labels, logits, label_length, logit_length, blank_index)`` --
+    ``tf.nn.ctc_loss_v2`` as called at lm_and_am/model/acoustic_model2.py:79-80
+    (time-major logits ``[T,B,V]``).  ``labels`` may be dense ``[B,L]`` (masked by
+    label_length) or a ``SparseLabels`` made by ``dense_to_sparse`` (which drops
+    every 0, acoustic_model2.py:71).
+  * ``ctc_greedy_decoder(inputs, sequence_length)`` -- ``tf.nn.ctc_greedy_decoder``
+    (acoustic_model2.py:69); ``decode_ctc(num_result, input_length)`` --
+    util/utils.py:57-66.
+Both losses are differentiable (``torch.autograd.Function``): the gradient w.r.t.
+the logits is produced by the same kernel pass as the loss.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib
+from .features import workspace
+
+SparseTensorValue = namedtuple("SparseTensorValue", "indices values dense_shape")
+SparseLabels = namedtuple("SparseLabels", "dense")   # result of dense_to_sparse: zeros are dropped
+CtcResult = namedtuple("CtcResult", "loss grad row_status tokens token_len neg_sum_logits")
+
+
+class InvalidArgumentError(ValueError):
+    """What TensorFlow raises from CTCLossOp ("Not enough time for target
+    transition sequence"), aborting ``sess.run`` (lm_and_am/train.py:58-69)."""
+
+
+def _strides(t, layout):
+    # element strides of (time, batch); V must be contiguous
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise ValueError("logits must be a 3-D tensor with a contiguous last dimension")
+    if layout == "tbv":
+        return t.shape[0], t.shape[1], t.shape[2], t.stride(0), t.stride(1)
+    if layout == "btv":
+        return t.shape[1], t.shape[0], t.shape[2], t.stride(1), t.stride(0)
+    raise ValueError("layout must be 'tbv' or 'btv'")
+
+
+def _i32(x, dev, torch):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.int32).contiguous().view(-1)
+    return torch.as_tensor(np.asarray(x).reshape(-1).astype(np.int32)).to(dev)
+
+
+def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="by_length",
+                  layout="tbv", grad_scale=None, want_grad=True, decode=False, grad_out=None,
+                  stream=None):
+    """Raw op: one fused pass.  logits float32 CUDA tensor ``[T,B,V]`` ('tbv') or
+    ``[B,T,V]`` ('btv'); labels int32 ``[B,Lmax]``.  Returns CtcResult of device
+    tensors (no synchronisation, statuses are NOT checked here)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    if logits.dtype != torch.float32 or not logits.is_cuda:
+        raise TypeError("logits must be a float32 CUDA tensor")
+    dev = logits.device
+    T, B, V, st, sb = _strides(logits, layout)
+    if blank is None:
+        blank = V - 1
+    labels = labels.to(device=dev, dtype=torch.int32) if isinstance(labels, torch.Tensor) else \
+        torch.as_tensor(np.asarray(labels).astype(np.int32)).to(dev)
+    labels = labels.reshape(B, -1).contiguous()
+    Ls = labels.shape[1]
+    input_len = _i32(input_len, dev, torch)
+    label_len = _i32(label_len, dev, torch) if label_len is not None else None
+    mode = _lib.LABELS_BY_LENGTH if label_mode == "by_length" else _lib.LABELS_DROP_ZEROS
+    loss = torch.empty(B, dtype=torch.float32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    grad = None
+    gt = gb = 0
+    if want_grad:
+        grad = grad_out if grad_out is not None else torch.empty_like(logits)
+        _, _, _, gt, gb = _strides(grad, layout)
+    tokens = tlen = nsl = None
+    if decode:
+        tokens = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
+        tlen = torch.empty(B, dtype=torch.int32, device=dev)
+        nsl = torch.empty(B, dtype=torch.float32, device=dev)
+    if grad_scale is not None:
+        grad_scale = grad_scale.to(device=dev, dtype=torch.float32).contiguous()
+    nbytes = L.asrk_ctc_workspace_bytes(T, B, Ls)
+    ws = workspace(nbytes, dev, "ctc")
+    rc = L.asrk_ctc_loss_grad_run(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(labels), Ls,
+                                  _lib.ptr(label_len), _lib.ptr(input_len), int(blank), mode,
+                                  _lib.ptr(grad_scale), _lib.ptr(loss), _lib.ptr(grad), gt, gb,
+                                  _lib.ptr(status), _lib.ptr(tokens), max(T, 1), _lib.ptr(tlen),
+                                  _lib.ptr(nsl), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(stream))
+    _lib.check(rc, "asrk_ctc_loss_grad_run")
+    return CtcResult(loss, grad, status, tokens, tlen, nsl)
+
+
+def _raise_on_status(status):
+    st = status.cpu().numpy()
+    bad = np.nonzero(st == _lib.ROW_NOT_ENOUGH_TIME)[0]
+    if len(bad):
+        raise InvalidArgumentError("Not enough time for target transition sequence "
+                                   "(required: label length + repeats) in batch rows %s" % bad.tolist())
+    bad = np.nonzero(st == _lib.ROW_BAD_LENGTH)[0]
+    if len(bad):
+        raise InvalidArgumentError("sequence_length / label_length / label value out of range in "
+                                   "batch rows %s" % bad.tolist())
+
+
+def _make_fn():
+    torch = _lib.require_cuda()
+
+    class _CTCLoss(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, logits, labels, label_len, input_len, blank, label_mode, layout, check):
+            need = logits.requires_grad
+            r = ctc_loss_grad(logits.detach(), labels, label_len, input_len, blank, label_mode,
+                              layout, want_grad=need)
+            if check:
+                _raise_on_status(r.row_status)
+            ctx.layout = layout
+            if need:
+                ctx.save_for_backward(r.grad)
+            return r.loss
+
+        @staticmethod
+        def backward(ctx, go):
+            (g,) = ctx.saved_tensors
+            if ctx.layout == "tbv":
+                gi = g * go.view(1, -1, 1)
+            else:
+                gi = g * go.view(-1, 1, 1)
+            return gi, None, None, None, None, None, None, None
+
+    return _CTCLoss
+
+
+_fn_cache = []
+
+
+def _fn():
+    if not _fn_cache:
+        _fn_cache.append(_make_fn())
+    return _fn_cache[0]
+
+
+def dense_to_sparse(target):
+    """tf.contrib.layers.dense_to_sparse (acoustic_model2.py:71): every entry
+    equal to 0 is dropped, including a genuine label id 0."""
+    return SparseLabels(target)
+
+
+def ctc_loss_v2(labels, logits, label_length, logit_length, logits_time_major=True, blank_index=None,
+                check=True):
+    """tf.nn.ctc_loss_v2 (acoustic_model2.py:79-80).  Returns loss ``[B]``."""
+    layout = "tbv" if logits_time_major else "btv"
+    if isinstance(labels, SparseLabels):
+        return _fn().apply(logits, labels.dense, None, logit_length, blank_index, "drop_zeros", layout, check)
+    return _fn().apply(logits, labels, label_length, logit_length, blank_index, "by_length", layout, check)
+
+
+def ctc_batch_cost(y_true, y_pred, input_length, label_length, check=True):
+    """Keras K.ctc_batch_cost (cnn_ctc.py:149-152): ``y_pred`` softmax output
+    ``[B,T,V]``; returns ``[B,1]``."""
+    torch = _lib.require_cuda()
+    x = torch.log(y_pred + 1e-7)     # keras: log(transpose(y_pred) + epsilon); the transpose is a stride swap
+    loss = _fn().apply(x, y_true, label_length, input_length, None, "by_length", "btv", check)
+    return loss.unsqueeze(1)
+
+
+def greedy_decode(logits, input_len, blank=None, merge_repeated=True, layout="tbv", stream=None):
+    """Raw op.  Returns (tokens int32 [B,T], token_len int32 [B], neg_sum_logits
+    float32 [B]) as device tensors; only ``tokens[b, :token_len[b]]`` is defined."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    if logits.dtype != torch.float32 or not logits.is_cuda:
+        raise TypeError("logits must be a float32 CUDA tensor")
+    dev = logits.device
+    T, B, V, st, sb = _strides(logits, layout)
+    if blank is None:
+        blank = V - 1
+    input_len = _i32(input_len, dev, torch)
+    tokens = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
+    tlen = torch.empty(B, dtype=torch.int32, device=dev)
+    nsl = torch.empty(B, dtype=torch.float32, device=dev)
+    nbytes = L.asrk_ctc_decode_workspace_bytes(max(T, 1), B)
+    ws = workspace(nbytes, dev, "ctc")
+    rc = L.asrk_ctc_greedy_decode_run(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(input_len), int(blank),
+                                      1 if merge_repeated else 0, _lib.ptr(tokens), max(T, 1),
+                                      _lib.ptr(tlen), _lib.ptr(nsl), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr(stream))
+    _lib.check(rc, "asrk_ctc_greedy_decode_run")
+    return tokens, tlen, nsl
+
+
+def tokens_to_lists(tokens, token_len):
+    tk = tokens.cpu().numpy()
+    tl = token_len.cpu().numpy()
+    return [tk[b, : tl[b]].astype(np.int64).tolist() for b in range(tk.shape[0])]
+
+
+def ctc_greedy_decoder(inputs, sequence_length, merge_repeated=True):
+    """tf.nn.ctc_greedy_decoder (acoustic_model2.py:69): inputs ``[T,B,V]``.
+    Returns ``([SparseTensorValue], neg_sum_logits[B,1])`` like ``sess.run`` of
+    the TF op gives."""
+    tokens, tlen, nsl = greedy_decode(inputs, sequence_length, None, merge_repeated, "tbv")
+    seqs = tokens_to_lists(tokens, tlen)
+    idx = [(b, j) for b, s in enumerate(seqs) for j in range(len(s))]
+    vals = [v for s in seqs for v in s]
+    width = max([len(s) for s in seqs] + [0])
+    sp = SparseTensorValue(np.asarray(idx, dtype=np.int64).reshape(-1, 2),
+                           np.asarray(vals, dtype=np.int64),
+                           np.asarray([len(seqs), width], dtype=np.int64))
+    return [sp], nsl.cpu().numpy().reshape(-1, 1)
+
+
+def sparse_tensor_to_dense(sp, default_value=0):
+    """tf.sparse_tensor_to_dense (lm_and_am/test.py:51 pads with 0)."""
+    out = np.full(tuple(int(v) for v in sp.dense_shape), default_value, dtype=np.int64)
+    if len(sp.values):
+        out[sp.indices[:, 0], sp.indices[:, 1]] = sp.values
+    return out
+
+
+def decode_ctc(num_result, input_length):
+    """util/utils.py:57-66: greedy decode of one utterance ``[1,T,V]`` (Keras
+    ``K.ctc_decode(greedy=True)``); returns the 1-D id array of row 0."""
+    torch = _lib.require_cuda()
+    x = num_result if isinstance(num_result, torch.Tensor) else torch.as_tensor(np.asarray(num_result, dtype=np.float32))
+    x = x[:, :, :].to("cuda", dtype=torch.float32)
+    in_len = np.zeros((1), dtype=np.int32)
+    in_len[0] = input_length
+    # K.ctc_decode takes log(transpose(y_pred) + epsilon); the arg-max is unchanged
+    # by the monotone map, but ties created by the float32 log are not, so apply it
+    xl = torch.log(x + 1e-7)
+    tokens, tlen, _ = greedy_decode(xl, in_len, None, True, "btv")
+    return np.asarray(tokens_to_lists(tokens, tlen)[0], dtype=np.int64)

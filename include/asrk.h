@@ -1,0 +1,175 @@
+/* asrk.h -- C ABI of the B200-native acoustic-model hot path.
+ *
+ * Drop-in boundary for the three parts of the reference's data-parallel path
+ * (786440445/ASR_DFCNN_Transformer).  The reference has no FFI of its own: the
+ * path sits behind plain Python callables.  Each entry
+ * point below names the reference callable it replaces; INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller;
+ *     the library allocates nothing persistent.  Scratch memory is caller
+ *     provided and sized by the matching *_workspace_bytes() query; it must be
+ *     256-byte aligned and is overwritten by every call.
+ *   - all work is enqueued on the cudaStream_t argument; no call synchronises.
+ *   - every function returns an int status: ASRK_OK or a negative ASRK_E_* code.
+ *     Nothing throws, nothing exits.  Per-utterance data problems (infeasible
+ *     CTC rows) are reported through a device int32 row_status array so the host
+ *     can raise / drop the row exactly as the reference's callers do.
+ *   - re-entrant; no global mutable state.
+ */
+#ifndef ASRK_H_
+#define ASRK_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* CUDA stream handle, passed as an opaque pointer (cudaStream_t). */
+typedef void* asrk_stream_t;
+
+#define ASRK_OK 0
+#define ASRK_E_BADARG (-1)    /* null pointer / negative size / unknown enum            */
+#define ASRK_E_SHAPE (-2)     /* a size outside what the kernels support                */
+#define ASRK_E_ALIGN (-3)     /* pointer or stride not aligned as documented            */
+#define ASRK_E_WORKSPACE (-4) /* workspace too small or misaligned                      */
+#define ASRK_E_CUDA (-5)      /* a CUDA runtime call / kernel launch failed             */
+
+/* row_status values written by asrk_ctc_loss_grad_run */
+#define ASRK_ROW_OK 0
+#define ASRK_ROW_INFEASIBLE 1   /* no valid alignment: loss=+inf, grad=softmax (TF semantics) */
+#define ASRK_ROW_NOT_ENOUGH_TIME 2 /* input_len < L + #repeats: TF raises InvalidArgument      */
+#define ASRK_ROW_BAD_LENGTH 3   /* input_len < 1 or > T, label_len < 0 or > label_stride,
+                                   or a label outside [0,V)                             */
+
+int asrk_version(void);
+const char* asrk_error_string(int code);
+
+/* ------------------------------------------------------------------------
+ * Part 1: spectrogram features (+ optional fused noise mix)
+ *   replaces  util/wav_util.py:49-79   compute_fbank            (ASRK_SPEC_FBANK)
+ *             util/wav_util.py:82-112  compute_fbank_from_asrt  (ASRK_SPEC_ASRT)
+ *             util/noise.py:48-52,108  SNR2K + "signal + K*noise" (noise != NULL)
+ *
+ * A ragged batch of B mono 16 kHz utterances.  Utterance b owns the
+ * sample_counts[b] samples starting at sample_offsets[b] of `samples` (and of
+ * `noise`).  For the 16-byte vector path every sample_offsets[b] should be a
+ * multiple of 8 (int16) / 4 (float32) samples (pad between utterances); other
+ * offsets work through a slower scalar path.  The number of frames of utterance b is frame_offsets[b+1] -
+ * frame_offsets[b]; it is decided BY THE HOST with the reference's Python float
+ * expression  int(N/fs*1000 - 25)//10 + 1  (wav_util.py:61; asrt: no "+1",
+ * :96) and must satisfy 160*(n-1)+400 <= N.  Frame i covers samples
+ * [160 i, 160 i + 400) (wav_util.py:67-69), is multiplied by the symmetric
+ * Hamming window of :51-52, transformed (400-point DFT, fp64 internally), and
+ * bins 0..199 of log(|X| * mag + 1) are produced (mag = 1, asrt: 1/N).
+ * ASRK_SPEC_FBANK then z-scores every bin over the frames of the utterance
+ * (sklearn.preprocessing.scale semantics, wav_util.py:79).
+ *
+ * Output row r of utterance b, frame i is  out + (out_row_offsets[b] + i)*200
+ * floats (out_row_offsets == NULL: frame_offsets is used, i.e. a ragged
+ * [total_frames, 200] matrix; pass b*1600 for the loader's zero-padded
+ * [B,1600,200,1] layout of lm_and_am/data_loader.py:107,146).
+ *
+ * Noise mix (sample_dtype float32 only): when noise != NULL every sample is
+ * replaced on the fly by  fl32(signal + fl32(K_b * noise))  (noise.py:108) with
+ * K_b = gain[b] if gain != NULL, else computed on the device from snr_db[b]
+ * with the float32 arithmetic of noise.py:48-52 (numpy pairwise summation).
+ * ------------------------------------------------------------------------ */
+#define ASRK_SPEC_FBANK 0       /* compute_fbank: log-magnitude + per-utterance z-score */
+#define ASRK_SPEC_ASRT 1        /* compute_fbank_from_asrt: |X|/N, no z-score           */
+#define ASRK_SPEC_FBANK_RAW 2   /* compute_fbank before the z-score of wav_util.py:79   */
+
+#define ASRK_DTYPE_I16 0
+#define ASRK_DTYPE_F32 1
+
+size_t asrk_spectrogram_workspace_bytes(int batch, long long total_frames);
+
+int asrk_spectrogram_run(const void* samples,               /* device, int16 or float32 [total_samples] */
+                         int sample_dtype,                  /* ASRK_DTYPE_*                              */
+                         const float* noise,                /* device float32 [total_samples] or NULL    */
+                         const float* gain,                 /* device float32 [B] or NULL                */
+                         const int* snr_db,                 /* device int32 [B] or NULL                  */
+                         const long long* sample_offsets,   /* device int64 [B]  first sample            */
+                         const long long* sample_counts,    /* device int64 [B]  number of samples       */
+                         const long long* frame_offsets,    /* device int64 [B+1]                        */
+                         const long long* out_row_offsets,  /* device int64 [B] or NULL                  */
+                         int batch,
+                         long long total_frames,            /* = frame_offsets[B] (host copy)            */
+                         int mode,                          /* ASRK_SPEC_*                               */
+                         float* out,                        /* device float32, rows of 200               */
+                         void* workspace, size_t workspace_bytes, asrk_stream_t stream);
+
+/* Mix gains only (noise.py:48-52 SNR2K on the device, float32 numpy semantics):
+ * gain_out[b] = fl32(sqrt(es/en)) * fl32(10^(-dB/20)).  Utterances longer than
+ * 2^20 samples get a NaN gain (pass explicit gains for those). */
+int asrk_snr2k_run(const float* signal, const float* noise, const long long* sample_offsets,
+                   const long long* sample_counts, const int* snr_db, int batch, float* gain_out,
+                   asrk_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Part 2: CTC loss forward-backward + gradient w.r.t. the logits
+ *   replaces  K.ctc_batch_cost via ctc_lambda, lm_and_am/model/cnn_ctc.py:149-152
+ *             tf.nn.ctc_loss_v2(..., blank_index=V-1),
+ *                                   lm_and_am/model/acoustic_model2.py:79-80
+ *   (TensorFlow CTCLossOp semantics: softmax over the logits inside the op,
+ *    ctc_merge_repeated=True, preprocess_collapse_repeated=False.)
+ *
+ * logits element (t,b,v) is logits[t*stride_t + b*stride_b + v] (V contiguous),
+ * so both the TF time-major [T,B,V] and the Keras batch-major [B,T,V] layouts
+ * are accepted; grad uses its own strides.  labels is int32 [B, label_stride].
+ * label_mode ASRK_LABELS_BY_LENGTH takes labels[b][0..label_len[b]) (Keras
+ * ctc_label_dense_to_sparse); ASRK_LABELS_DROP_ZEROS keeps the non-zero entries
+ * of the whole row (tf.contrib.layers.dense_to_sparse, acoustic_model2.py:71).
+ *   loss[b]   = -log p(labels_b | logits_b)
+ *   grad[t,b,v] = grad_scale[b] * (softmax(logits[t,b,:])[v] - occupancy[t,b,v])
+ *                 for t < input_len[b], and 0 for t >= input_len[b]
+ * grad == NULL computes the loss only.  When tokens != NULL the greedy decode of
+ * part 3 is produced from the same read of the logits (merge_repeated = 1).
+ * ------------------------------------------------------------------------ */
+#define ASRK_LABELS_BY_LENGTH 0
+#define ASRK_LABELS_DROP_ZEROS 1
+
+size_t asrk_ctc_workspace_bytes(int T, int B, int label_stride);
+
+int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long stride_b,
+                           int T, int B, int V,
+                           const int* labels, int label_stride, /* device int32 [B,label_stride] */
+                           const int* label_len,                /* device int32 [B]              */
+                           const int* input_len,                /* device int32 [B]              */
+                           int blank, int label_mode,
+                           const float* grad_scale,             /* device float32 [B] or NULL    */
+                           float* loss,                         /* device float32 [B]            */
+                           float* grad, long long gstride_t, long long gstride_b, /* or NULL     */
+                           int* row_status,                     /* device int32 [B]              */
+                           int* tokens, int token_stride,       /* device int32 [B,token_stride] or NULL */
+                           int* token_len,                      /* device int32 [B] (with tokens) */
+                           float* neg_sum_logits,               /* device float32 [B] or NULL     */
+                           void* workspace, size_t workspace_bytes, asrk_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Part 3: greedy CTC decode
+ *   replaces  tf.nn.ctc_greedy_decoder, lm_and_am/model/acoustic_model2.py:69
+ *             (consumed at lm_and_am/test.py:48-52) and
+ *             util/utils.py:57-66 decode_ctc (K.ctc_decode(greedy=True))
+ * Per frame t < input_len[b] the FIRST maximum over v is taken (strict '>'
+ * scan); it is emitted when != blank and (not merge_repeated or != previous
+ * frame's class); neg_sum_logits[b] = -sum_t max_v logits.  tokens row b holds
+ * token_len[b] ids; the rest of the row is left untouched (the host pads with
+ * 0, test.py:51, or -1, Keras).
+ * ------------------------------------------------------------------------ */
+size_t asrk_ctc_decode_workspace_bytes(int T, int B);
+
+int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long long stride_b,
+                               int T, int B, int V, const int* input_len, int blank,
+                               int merge_repeated,
+                               int* tokens, int token_stride, int* token_len,
+                               float* neg_sum_logits, /* device float32 [B] or NULL */
+                               void* workspace, size_t workspace_bytes, asrk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASRK_H_ */

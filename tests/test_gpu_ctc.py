@@ -1,0 +1,178 @@
+"""GPU parity: CTC loss / gradient and greedy decode vs the float64 oracle."""
+import numpy as np
+import pytest
+
+from oracle import ctc_ref, synth
+from tests.util import CTC_ATOL, CTC_RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(x, labels, ll, il, blank=None, label_mode="by_length", layout="tbv", decode=False):
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    xt = torch.as_tensor(x).cuda()
+    if layout == "btv":
+        xt = xt.permute(1, 0, 2).contiguous()
+    r = ctc.ctc_loss_grad(xt, labels, ll, il, blank, label_mode, layout, decode=decode)
+    g = r.grad
+    if layout == "btv":
+        g = g.permute(1, 0, 2)
+    return r, r.loss.cpu().numpy(), g.cpu().numpy(), r.row_status.cpu().numpy()
+
+
+def _check(x, labels, ll, il, blank, **kw):
+    r, loss, grad, status = _run(x, labels, ll, il, blank, **kw)
+    mode = kw.get("label_mode", "by_length")
+    rl, rg, ok = ctc_ref.ctc_loss_grad_batch(x, labels, ll, il, blank, label_mode=mode)
+    assert np.all(status[ok] == 0)
+    np.testing.assert_allclose(loss[ok], rl[ok], rtol=CTC_RTOL, atol=CTC_ATOL)
+    np.testing.assert_allclose(grad, rg, rtol=CTC_RTOL, atol=CTC_ATOL)
+    return r
+
+
+def test_small_cases_tbv_and_btv():
+    rng = np.random.default_rng(0)
+    x, labels, ll, il = synth.ctc_batch(rng, [20, 13, 7, 30, 1, 2], 52, 0, 9)
+    _check(x, labels, ll, il, 51)
+    _check(x, labels, ll, il, 51, layout="btv")
+
+
+def test_known_answers():
+    # T=1, L=0: loss = -log softmax(blank)
+    x = np.array([[[0.0, 1.0, 2.0, 3.0]]], dtype=np.float32)            # [T=1,B=1,V=4]
+    r, loss, grad, st = _run(x, np.zeros((1, 1), np.int32), [0], [1], 3)
+    lp = x[0, 0] - np.log(np.exp(x[0, 0]).sum())
+    assert abs(loss[0] + lp[3]) < 1e-5
+    y = np.exp(lp); y[3] -= 1.0
+    np.testing.assert_allclose(grad[0, 0], y, atol=1e-5)
+    # T=2, L=1 (label 0): paths "0b", "b0", "00"
+    x = np.zeros((2, 1, 3), dtype=np.float32)
+    r, loss, grad, st = _run(x, np.array([[0]], np.int32), [1], [2], 2)
+    assert abs(loss[0] + np.log(3.0 / 9.0)) < 1e-5
+    # repeated label needs T = L + repeats exactly: labels (1,1), T=3 -> single path "1 b 1"
+    x = np.zeros((3, 1, 3), dtype=np.float32)
+    r, loss, grad, st = _run(x, np.array([[1, 1]], np.int32), [2], [3], 2)
+    assert abs(loss[0] + 3 * np.log(1.0 / 3.0)) < 1e-5 and st[0] == 0
+    # not enough time: labels (1,1), T=2
+    r, loss, grad, st = _run(x[:2], np.array([[1, 1]], np.int32), [2], [2], 2)
+    assert st[0] == 2 and np.isinf(loss[0])
+    np.testing.assert_allclose(grad[:, 0], np.full((2, 3), 1.0 / 3.0), atol=1e-6)   # dy = y
+
+
+def test_label_zero_and_drop_zeros_mode():
+    rng = np.random.default_rng(1)
+    x, labels, ll, il = synth.ctc_batch(rng, [25, 25, 18], 40, 4, 8, lmax=12)
+    labels[0, 1] = 0      # a genuine label id 0
+    _check(x, labels, ll, il, 39)
+    _check(x, labels, ll, il, 39, label_mode="drop_zeros")
+
+
+def test_input_len_shorter_than_T_zero_grad_rows():
+    rng = np.random.default_rng(2)
+    x, labels, ll, il = synth.ctc_batch(rng, [9, 30, 17], 64, 2, 6)
+    r, loss, grad, st = _run(x, labels, ll, il, 63)
+    assert np.all(grad[9:, 0] == 0) and np.all(grad[17:, 2] == 0)
+    # sum_v grad = 0 on valid frames (softmax minus a distribution)
+    assert np.abs(grad[:9, 0].sum(-1)).max() < 1e-4
+
+
+def test_c1_shape_dict_vocab():
+    c = synth.config_c1()
+    _check(c["logits"], c["labels"], c["label_len"], c["input_len"], c["V"] - 1)
+
+
+def test_c2_shape_subset():
+    rng = np.random.default_rng(2000)
+    il = np.array([synth.t_ctc(synth.n_frames(int(n))) for n in synth.ragged_lengths(rng, 24, 3.0, 7.0)], np.int32)
+    x, labels, ll, il = synth.ctc_batch(rng, il, synth.VOCAB_DICT_TXT, 8, 24, lmax=64)
+    _check(x, labels, ll, il, synth.VOCAB_DICT_TXT - 1)
+
+
+def test_long_lattice_c3_shape_one_row():
+    rng = np.random.default_rng(3000)
+    x, labels, ll, il = synth.ctc_batch(rng, [1998, 1500], synth.VOCAB_DICT_TXT, 280, 320)
+    _check(x, labels, ll, il, synth.VOCAB_DICT_TXT - 1)
+
+
+def test_mixdict_vocab_and_unaligned_vocab():
+    rng = np.random.default_rng(4)
+    for V in (synth.VOCAB_MIXDICT, 1423, 37):
+        x, labels, ll, il = synth.ctc_batch(rng, [40, 33, 12], V, 3, 10)
+        _check(x, labels, ll, il, V - 1)
+
+
+def test_keras_ctc_batch_cost_and_autograd():
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    rng = np.random.default_rng(5)
+    x, labels, ll, il = synth.ctc_batch(rng, [30, 22, 16, 30], 60, 3, 9, lmax=16)
+    p = torch.softmax(torch.as_tensor(x).permute(1, 0, 2), -1).contiguous()      # [B,T,V]
+    pt = p.cuda().requires_grad_(True)
+    cost = ctc.ctc_batch_cost(torch.as_tensor(labels.astype(np.float32)), pt,
+                              torch.as_tensor(il.reshape(-1, 1).astype(np.int64)),
+                              torch.as_tensor(ll.reshape(-1, 1).astype(np.int64)))
+    assert tuple(cost.shape) == (4, 1)
+    cost.sum().backward()
+    rl, rgp = ctc_ref.keras_ctc_batch_cost(labels, p.numpy(), il, ll)
+    np.testing.assert_allclose(cost.detach().cpu().numpy(), rl, rtol=CTC_RTOL, atol=CTC_ATOL)
+    np.testing.assert_allclose(pt.grad.cpu().numpy(), rgp, rtol=2e-3, atol=1e-3)
+
+
+def test_ctc_loss_v2_raises_like_tf():
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    x = torch.zeros((2, 1, 3), device="cuda")
+    with pytest.raises(ctc.InvalidArgumentError):
+        ctc.ctc_loss_v2(torch.tensor([[1, 1]], dtype=torch.int32), x, torch.tensor([2]), torch.tensor([2]),
+                        blank_index=2)
+
+
+def test_greedy_decode_bit_exact():
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    rng = np.random.default_rng(6)
+    for V, scale in ((synth.VOCAB_DICT_TXT, 3.0), (50, 0.5), (7, 0.2)):
+        il = np.array([63, 1, 40, 88, 33, 64, 32, 31], np.int32)
+        x = synth.logits_tbv(rng, 88, len(il), V, scale)
+        # force ties, repeats and blanks
+        x[5:9, 0, :] = 0.0                 # all equal -> index 0 four times
+        x[10:13, 2, V - 1] = 50.0          # blanks
+        x[13:15, 2, 3] = 50.0              # repeat "3 3"
+        x[15, 2, V - 1] = 50.0
+        x[16, 2, 3] = 50.0                 # "3" again after a blank -> emitted twice
+        x = np.round(x * 4) / 4            # many exact ties
+        tokens, tlen, nsl = ctc.greedy_decode(torch.as_tensor(x).cuda(), il)
+        got = ctc.tokens_to_lists(tokens, tlen)
+        ref, rnsl = ctc_ref.greedy_decode(x, il)
+        assert got == ref
+        np.testing.assert_allclose(nsl.cpu().numpy(), rnsl, rtol=1e-5, atol=1e-4)
+        got2, _ = ctc_ref.greedy_decode(x, il, merge_repeated=False)
+        t2, l2, _ = ctc.greedy_decode(torch.as_tensor(x).cuda(), il, merge_repeated=False)
+        assert ctc.tokens_to_lists(t2, l2) == got2
+
+
+def test_fused_decode_matches_standalone():
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    rng = np.random.default_rng(8)
+    x, labels, ll, il = synth.ctc_batch(rng, [50, 41, 63, 9], 200, 3, 12)
+    r, *_ = _run(x, labels, ll, il, 199, decode=True)
+    ref, _ = ctc_ref.greedy_decode(x, il)
+    assert ctc.tokens_to_lists(r.tokens, r.token_len) == ref
+
+
+def test_tf_decoder_surface_and_decode_ctc():
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    rng = np.random.default_rng(9)
+    x = synth.logits_tbv(rng, 30, 2, 20, 1.0)
+    dec, nsl = ctc.ctc_greedy_decoder(torch.as_tensor(x).cuda(), np.array([30, 12], np.int32))
+    ref, _ = ctc_ref.greedy_decode(x, [30, 12])
+    dense = ctc.sparse_tensor_to_dense(dec[0], default_value=0)
+    assert np.array_equal(dense, ctc_ref.densify(ref, 0))
+    assert nsl.shape == (2, 1)
+    p = np.exp(x[:, :1]) / np.exp(x[:, :1]).sum(-1, keepdims=True)
+    ids = ctc.decode_ctc(np.transpose(p, (1, 0, 2)).astype(np.float32), 30)
+    ref1, _ = ctc_ref.greedy_decode(np.log(p.astype(np.float32) + np.float32(1e-7)), [30])
+    assert ids.tolist() == ref1[0]

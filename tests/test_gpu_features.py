@@ -1,0 +1,105 @@
+"""GPU parity: spectrogram kernels vs the oracle restatement and vs the golden
+vectors produced by the reference's own code (tools/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fbank_ref, synth
+from tests.util import FEATURE_TOL, feature_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(signals, mode, **kw):
+    from asr_dfcnn_transformer_b200 import features
+    fb = features.compute_features(signals, mode=mode, **kw)
+    return fb.features.cpu().numpy(), fb.frame_offsets
+
+
+@pytest.mark.parametrize("mode,key", [("fbank", "fbank"), ("asrt", "asrt")])
+def test_golden_vectors(golden_dir, mode, key):
+    files = sorted(glob.glob(os.path.join(golden_dir, "fbank_*.npz")))
+    assert files
+    sigs, refs = [], []
+    for f in files:
+        d = np.load(f)
+        sigs.append(d["pcm"])
+        refs.append(d[key])
+    out, fo = _gpu(sigs, mode)
+    for i, f in enumerate(files):
+        got = out[fo[i]:fo[i + 1]]
+        assert got.shape == refs[i].shape, (f, got.shape, refs[i].shape)
+        err = feature_err(got, refs[i])
+        assert err <= FEATURE_TOL, (os.path.basename(f), mode, err)
+
+
+def test_raw_vs_oracle_generators():
+    rng = np.random.default_rng(7)
+    sigs = [synth.g1_white(rng, 16000), synth.g2_voiced(rng, 40000), synth.g2_voiced(rng, 16080),
+            synth.g1_white(rng, 401), synth.g1_white(rng, 399), synth.g2_voiced(rng, 5173)]
+    sigs += list(synth.g3_edge_cases(rng).values())
+    out, fo = _gpu(sigs, "fbank_raw")
+    for i, s in enumerate(sigs):
+        ref = fbank_ref.compute_fbank_unnormalised(s)
+        got = out[fo[i]:fo[i + 1]]
+        assert got.shape == ref.shape
+        assert feature_err(got, ref) <= FEATURE_TOL, (i, feature_err(got, ref))
+
+
+def test_fbank_zscore_vs_oracle_ragged_batch():
+    rng = np.random.default_rng(11)
+    lens = synth.ragged_lengths(rng, 24, 0.5, 3.0)
+    sigs = [synth.g2_voiced(rng, int(n)) if i % 2 else synth.g1_white(rng, int(n)) for i, n in enumerate(lens)]
+    out, fo = _gpu(sigs, "fbank")
+    worst = 0.0
+    for i, s in enumerate(sigs):
+        ref = fbank_ref.compute_fbank(s)
+        worst = max(worst, feature_err(out[fo[i]:fo[i + 1]], ref))
+    assert worst <= FEATURE_TOL, worst
+
+
+def test_padded_loader_layout():
+    rng = np.random.default_rng(5)
+    sigs = [synth.g1_white(rng, 16000), synth.g1_white(rng, 9000)]
+    from asr_dfcnn_transformer_b200 import features
+    fb = features.compute_features(sigs, mode="fbank", padded_rows=1600)
+    out = fb.features.cpu().numpy()
+    assert out.shape == (2, 1600, 200)
+    for i, s in enumerate(sigs):
+        ref = fbank_ref.compute_fbank(s)
+        assert feature_err(out[i, :ref.shape[0]], ref) <= FEATURE_TOL
+        assert np.all(out[i, ref.shape[0]:] == 0)
+
+
+def test_noise_golden(golden_dir):
+    from asr_dfcnn_transformer_b200 import features, noise
+    files = sorted(glob.glob(os.path.join(golden_dir, "noise_case*.npz")))
+    assert files
+    for f in files:
+        d = np.load(f)
+        K = noise.SNR2K(d["signal"], d["noise"], int(d["snr_db"]))
+        assert K.dtype == np.float32
+        assert K == d["K"], (f, K, d["K"])            # bit-exact gain
+        mixed = noise.mix(d["signal"], d["noise"], int(d["snr_db"]))
+        assert np.array_equal(mixed, d["mixed"])       # bit-exact mixed signal
+        fb = features.compute_features([d["signal"]], noises=[d["noise"]], snr_db=[int(d["snr_db"])])
+        err = feature_err(fb.features.cpu().numpy(), d["fbank"])
+        assert err <= FEATURE_TOL, (f, err)
+
+
+def test_wav_file_surface(tmp_path):
+    import scipy.io.wavfile as wavfile
+    from asr_dfcnn_transformer_b200 import wav_util
+    rng = np.random.default_rng(3)
+    sig = synth.g2_voiced(rng, 16240)
+    p = str(tmp_path / "a.wav")
+    wavfile.write(p, 16000, sig)
+    got = wav_util.compute_fbank(p)
+    assert got.dtype == np.float64
+    assert feature_err(got, fbank_ref.compute_fbank(sig)) <= FEATURE_TOL
+    got2 = wav_util.compute_fbank_from_asrt(p)
+    assert feature_err(got2, fbank_ref.compute_fbank_from_asrt(sig)) <= FEATURE_TOL
+    wd, fr = wav_util.read_wav_data(p)
+    assert fr == 16000 and wd.shape == (1, 16240) and np.array_equal(wd[0], sig)
