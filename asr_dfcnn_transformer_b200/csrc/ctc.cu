@@ -258,15 +258,22 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_kernel(Params p) {
 // ---------------------------------------------------------------------------
 // lattice
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float lse2(float a, float b) {
-    const float m = fmaxf(a, b);
-    if (m == kNegInf) return kNegInf;
-    return m + __logf(__expf(a - m) + __expf(b - m));
+// log(e^a + e^b [+ e^c]) with the running values in double and the transcendentals
+// in fp32: the exp arguments are differences <= 0 and the log argument is in
+// [1,3], so the absolute error per step is ~3e-7 whatever the magnitude of the
+// running sums (which reach T*log V ~ 1e4 for T in the thousands) -- plain fp32
+// log-space would lose 1e-3 there.
+__device__ __forceinline__ double lse2(double a, double b) {
+    const double m = fmax(a, b);
+    if (m == (double)kNegInf) return m;
+    const float s = __expf((float)(a - m)) + __expf((float)(b - m));
+    return m + (double)__logf(s);
 }
-__device__ __forceinline__ float lse3(float a, float b, float c) {
-    const float m = fmaxf(fmaxf(a, b), c);
-    if (m == kNegInf) return kNegInf;
-    return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+__device__ __forceinline__ double lse3(double a, double b, double c) {
+    const double m = fmax(fmax(a, b), c);
+    if (m == (double)kNegInf) return m;
+    const float s = __expf((float)(a - m)) + __expf((float)(b - m)) + __expf((float)(c - m));
+    return m + (double)__logf(s);
 }
 
 // block-wide max over all threads (blockDim.x multiple of 32, <= 1024)
@@ -284,19 +291,23 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // One CTA per utterance; thread i owns the state pair
 //   alpha sweep: (blank 2i, label 2i+1)     beta sweep: (label 2i-1, blank 2i)
 // so that each step needs exactly one neighbour value (the previous / next
-// label state), exchanged through a double-buffered shared array.
+// label state), exchanged through a double-buffered shared array.  alpha is kept
+// for the backward sweep as float32 relative to an offset C_t that is refreshed
+// from the exact column maximum every kRenorm steps.
 __global__ void lattice_kernel(Params p) {
-    extern __shared__ float sm[];
+    extern __shared__ double smd[];
     const int b = blockIdx.x;
     const int i = threadIdx.x;
     const int P = blockDim.x;
-    float* xch = sm;                 // [2][P]
-    float* red = sm + 2 * P;         // [32]
+    double* xch = smd;                                   // [2][P]
+    float* red = reinterpret_cast<float*>(smd + 2 * P);  // [32]
+    double* fin2 = smd + 2 * P + 16;                     // [2]
     const int status = p.row_status[b];
     const int L = p.eff_len[b];
     const int T = p.input_len[b];
+    const double ninf = (double)kNegInf;
     if (status == ASRK_ROW_BAD_LENGTH) {
-        if (i == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = (double)kNegInf; }
+        if (i == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
         return;
     }
     const int S = p.Ls + 1;
@@ -306,106 +317,94 @@ __global__ void lattice_kernel(Params p) {
     double* coff = p.coff + (size_t)b * p.T;
     const int* eff = p.eff_labels + (size_t)b * p.Ls;
 
-    const int lab_i = (i < L) ? eff[i] : -1;            // label index i     (state 2i+1)
-    const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;   // label index i-1 (state 2i-1)
-    // alpha: label state 2i+1 may be entered from 2i-1 when the labels differ
-    const bool skip_a = (i >= 1 && i < L && lab_i != lab_im1);
-    // beta: label state 2i-1 may step to 2i+1 when the labels differ
-    const bool skip_b = (i >= 1 && i < L && lab_i != lab_im1);
+    const int lab_i = (i < L) ? eff[i] : -1;                     // label index i   (state 2i+1)
+    const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;    // label index i-1 (state 2i-1)
+    // the skip transition 2i-1 <-> 2i+1 exists when both labels exist and differ
+    const bool skip = (i >= 1 && i < L && lab_i != lab_im1);
     const bool has_blank = (i <= L);
-    const bool has_lab_a = (i < L);            // alpha pair's label state exists
-    const bool has_lab_b = (i >= 1 && i <= L); // beta pair's label state exists
+    const bool has_lab_a = (i < L);             // alpha pair's label state 2i+1 exists
+    const bool has_lab_b = (i >= 1 && i <= L);  // beta pair's label state 2i-1 exists
 
     // ------------------------------ alpha ------------------------------
-    float a_b = kNegInf, a_l = kNegInf;
+    double a_b = ninf, a_l = ninf;
     if (i == 0) {
-        a_b = lpl[0];
-        if (L >= 1) a_l = lpl[1];
+        a_b = (double)lpl[0];
+        if (L >= 1) a_l = (double)lpl[1];
     }
     double C = 0.0;
-    if (has_blank) occ[2 * i] = a_b;
-    if (has_lab_a) occ[2 * i + 1] = a_l;
-    if (i == 0) coff[0] = 0.0;
+    if (T >= 1) {
+        const float m = block_max((float)fmax(a_b, a_l), red);
+        if (m > kNegInf) C = (double)m;
+    }
+    if (has_blank) occ[2 * i] = (float)(a_b - C);
+    if (has_lab_a) occ[2 * i + 1] = (float)(a_l - C);
+    if (i == 0) coff[0] = C;
     for (int t = 1; t < T; ++t) {
-        float* xb = xch + (t & 1) * P;
+        double* xb = xch + (t & 1) * P;
         xb[i] = a_l;
-        const float lb = lpl[(size_t)t * S];
-        const float ll = has_lab_a ? lpl[(size_t)t * S + 1 + i] : kNegInf;
+        const double lb = (double)lpl[(size_t)t * S];
+        const double ll = has_lab_a ? (double)lpl[(size_t)t * S + 1 + i] : ninf;
         __syncthreads();
-        const float p1 = (i >= 1) ? xb[i - 1] : kNegInf;
-        const float nb = lb + lse2(a_b, p1);
-        const float nl = ll + lse3(a_l, a_b, skip_a ? p1 : kNegInf);
-        a_b = has_blank ? nb : kNegInf;
-        a_l = has_lab_a ? nl : kNegInf;
+        const double p1 = (i >= 1) ? xb[i - 1] : ninf;
+        const double nb = lb + lse2(a_b, p1);
+        const double nl = ll + lse3(a_l, a_b, skip ? p1 : ninf);
+        a_b = has_blank ? nb : ninf;
+        a_l = has_lab_a ? nl : ninf;
         if ((t % kRenorm) == 0) {
-            const float m = block_max(fmaxf(a_b, a_l), red);
-            if (m > kNegInf) {
-                a_b -= m;
-                a_l -= m;
-                C += (double)m;
-            }
+            const float m = block_max((float)(fmax(a_b, a_l) - C), red);
+            if (m > kNegInf) C += (double)m;
         }
         float* o = occ + (size_t)t * U;
-        if (has_blank) o[2 * i] = a_b;
-        if (has_lab_a) o[2 * i + 1] = a_l;
+        if (has_blank) o[2 * i] = (float)(a_b - C);
+        if (has_lab_a) o[2 * i + 1] = (float)(a_l - C);
         if (i == 0) coff[t] = C;
     }
-    // log p = LSE(alpha_{T-1}(2L), alpha_{T-1}(2L-1)) + C
+    // log p = LSE(alpha_{T-1}(2L), alpha_{T-1}(2L-1))
     __syncthreads();
-    if (i == L) red[0] = a_b;
-    if (i == L - 1) red[1] = a_l;
-    if (L == 0 && i == 0) red[1] = kNegInf;
+    if (i == L) fin2[0] = a_b;
+    if (i == L - 1) fin2[1] = a_l;
+    if (L == 0 && i == 0) fin2[1] = ninf;
     __syncthreads();
-    const float fin = lse2(red[0], red[1]);
-    const double logp = (fin == kNegInf) ? (double)kNegInf : (double)fin + C;
+    const double logp = lse2(fin2[0], fin2[1]);
     if (i == 0) {
         p.logp[b] = logp;
         p.loss[b] = (float)(-logp);
-        if (fin == kNegInf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
+        if (logp == ninf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
     }
-    if (p.grad == nullptr || fin == kNegInf) return;   // uniform over the CTA
+    if (p.grad == nullptr || logp == ninf) return;   // uniform over the CTA
     __syncthreads();
 
     // ------------------------------ beta -------------------------------
     // beta excludes y_t; e(u) = beta_{t+1}(u) + log y_{t+1}(l'_u)
-    float b_l = kNegInf, b_b = kNegInf;
+    double b_l = ninf, b_b = ninf;
     if (i == L) {
-        b_b = 0.f;
-        if (L >= 1) b_l = 0.f;
+        b_b = 0.0;
+        if (L >= 1) b_l = 0.0;
     }
-    double Dn = 0.0;
     {
         const int t = T - 1;
         float* o = occ + (size_t)t * U;
-        const float off = (float)(coff[t] + Dn - logp);
-        if (has_blank) o[2 * i] = __expf(o[2 * i] + b_b + off);
-        if (has_lab_b) o[2 * i - 1] = __expf(o[2 * i - 1] + b_l + off);
+        const double off = coff[t] - logp;
+        if (has_blank) o[2 * i] = __expf((float)((double)o[2 * i] + b_b + off));
+        if (has_lab_b) o[2 * i - 1] = __expf((float)((double)o[2 * i - 1] + b_l + off));
     }
     for (int t = T - 2; t >= 0; --t) {
-        const float lb = lpl[(size_t)(t + 1) * S];
-        const float ll = has_lab_b ? lpl[(size_t)(t + 1) * S + i] : kNegInf;   // label index i-1 -> slot i
-        const float e_b = b_b + lb;
-        const float e_l = b_l + ll;
-        float* xb = xch + (t & 1) * P;
+        const double lb = (double)lpl[(size_t)(t + 1) * S];
+        const double ll = has_lab_b ? (double)lpl[(size_t)(t + 1) * S + i] : ninf;   // label i-1 -> slot i
+        const double e_b = b_b + lb;
+        const double e_l = b_l + ll;
+        double* xb = xch + (t & 1) * P;
         xb[i] = e_l;
         __syncthreads();
-        const float n1 = (i + 1 < P) ? xb[i + 1] : kNegInf;   // e of label state 2i+1
-        const float nbb = lse2(e_b, n1);
-        const float nbl = lse3(e_l, e_b, skip_b ? n1 : kNegInf);
-        b_b = has_blank ? nbb : kNegInf;
-        b_l = has_lab_b ? nbl : kNegInf;
-        if ((t % kRenorm) == 0) {
-            const float m = block_max(fmaxf(b_b, b_l), red);
-            if (m > kNegInf) {
-                b_b -= m;
-                b_l -= m;
-                Dn += (double)m;
-            }
-        }
+        const double n1 = (i + 1 < P) ? xb[i + 1] : ninf;   // e of label state 2i+1
+        const double nbb = lse2(e_b, n1);
+        const double nbl = lse3(e_l, e_b, skip ? n1 : ninf);
+        b_b = has_blank ? nbb : ninf;
+        b_l = has_lab_b ? nbl : ninf;
         float* o = occ + (size_t)t * U;
-        const float off = (float)(coff[t] + Dn - logp);
-        if (has_blank) o[2 * i] = __expf(o[2 * i] + b_b + off);
-        if (has_lab_b) o[2 * i - 1] = __expf(o[2 * i - 1] + b_l + off);
+        const double off = coff[t] - logp;
+        if (has_blank) o[2 * i] = __expf((float)((double)o[2 * i] + b_b + off));
+        if (has_lab_b) o[2 * i - 1] = __expf((float)((double)o[2 * i - 1] + b_l + off));
     }
 }
 
@@ -638,7 +637,7 @@ extern "C" int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, l
     prep_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p);
     launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
-    lattice_kernel<<<B, P, sizeof(float) * (2 * P + 32), stream>>>(p);
+    lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p);
     if (grad) launch_grad(p, nv4, stream);
     if (tokens) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
     return launch_status();

@@ -380,6 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                 for (int k = hth; k < kBins; k += kHelperThreads) {
                     double s1 = 0.0, s2 = 0.0;
                     for (int c = c_lo; c <= c_hi; ++c) {
+                        // CTAs whose chunk is empty never flushed anything
+                        if ((long long)(c + 1) * n_tiles / G == (long long)c * n_tiles / G) continue;
                         const double* q = p.partials + (size_t)(c + acc_b) * 400;
                         s1 += __ldcg(q + k);
                         s2 += __ldcg(q + 200 + k);
