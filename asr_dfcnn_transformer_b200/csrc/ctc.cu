@@ -597,14 +597,14 @@ static void bind_workspace(Params& p, void* workspace, const WsLayout& l) {
     p.logp = reinterpret_cast<double*>(ws + l.logp);
 }
 
-extern "C" int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long stride_b,
-                                      int T, int B, int V, const int* labels, int label_stride,
-                                      const int* label_len, const int* input_len, int blank,
-                                      int label_mode, const float* grad_scale, float* loss, float* grad,
-                                      long long gstride_t, long long gstride_b, int* row_status,
-                                      int* tokens, int token_stride, int* token_len,
-                                      float* neg_sum_logits, void* workspace, size_t workspace_bytes,
-                                      asrk_stream_t stream_) {
+extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stride_t, long long stride_b,
+                                             int T, int B, int V, const int* labels, int label_stride,
+                                             const int* label_len, const int* input_len, int blank,
+                                             int label_mode, const float* grad_scale, float* loss,
+                                             float* grad, long long gstride_t, long long gstride_b,
+                                             int* row_status, int* tokens, int token_stride,
+                                             int* token_len, float* neg_sum_logits, void* workspace,
+                                             size_t workspace_bytes, asrk_stream_t stream_, int phases) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (T < 0 || B < 0 || V < 1 || label_stride < 0) return ASRK_E_BADARG;
     if (B == 0 || T == 0) return ASRK_OK;
@@ -634,13 +634,29 @@ extern "C" int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, l
     bind_workspace(p, workspace, l);
 
     const int nv4 = pick_nv4(p, logits, stride_t, stride_b, grad, gstride_t, gstride_b);
-    prep_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p);
-    launch_rows<true>(p, nv4, stream);
+    if (phases & ASRK_PHASE_CTC_PREP) prep_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p);
+    if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
-    lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p);
-    if (grad) launch_grad(p, nv4, stream);
-    if (tokens) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
+    if (phases & ASRK_PHASE_CTC_LATTICE)
+        lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p);
+    if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
+    if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
     return launch_status();
+}
+
+extern "C" int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long stride_b,
+                                      int T, int B, int V, const int* labels, int label_stride,
+                                      const int* label_len, const int* input_len, int blank,
+                                      int label_mode, const float* grad_scale, float* loss, float* grad,
+                                      long long gstride_t, long long gstride_b, int* row_status,
+                                      int* tokens, int token_stride, int* token_len,
+                                      float* neg_sum_logits, void* workspace, size_t workspace_bytes,
+                                      asrk_stream_t stream_) {
+    return asrk_ctc_loss_grad_run_phases(logits, stride_t, stride_b, T, B, V, labels, label_stride,
+                                         label_len, input_len, blank, label_mode, grad_scale, loss, grad,
+                                         gstride_t, gstride_b, row_status, tokens, token_stride,
+                                         token_len, neg_sum_logits, workspace, workspace_bytes, stream_,
+                                         ASRK_PHASE_ALL);
 }
 
 extern "C" int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long long stride_b,

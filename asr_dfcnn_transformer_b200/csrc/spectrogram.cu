@@ -511,13 +511,13 @@ extern "C" size_t asrk_spectrogram_workspace_bytes(int batch, long long total_fr
     return ws_layout(batch, total_frames, 1024).total;
 }
 
-extern "C" int asrk_spectrogram_run(const void* samples, int sample_dtype, const float* noise,
-                                    const float* gain, const int* snr_db,
-                                    const long long* sample_offsets, const long long* sample_counts,
-                                    const long long* frame_offsets, const long long* out_row_offsets,
-                                    int batch, long long total_frames,
-                                    int mode, float* out, void* workspace, size_t workspace_bytes,
-                                    asrk_stream_t stream_) {
+extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype, const float* noise,
+                                           const float* gain, const int* snr_db,
+                                           const long long* sample_offsets, const long long* sample_counts,
+                                           const long long* frame_offsets, const long long* out_row_offsets,
+                                           int batch, long long total_frames,
+                                           int mode, float* out, void* workspace, size_t workspace_bytes,
+                                           asrk_stream_t stream_, int phases) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (batch < 0 || total_frames < 0) return ASRK_E_BADARG;
     if (batch == 0) return ASRK_OK;
@@ -552,7 +552,9 @@ extern "C" int asrk_spectrogram_run(const void* samples, int sample_dtype, const
     p.partials = reinterpret_cast<double*>(ws + l.partials);
     p.tile_rec = reinterpret_cast<TileRec*>(ws + l.tile_rec);
 
-    if (noise && !gain) {
+    if (noise && !gain && !(phases & ASRK_PHASE_SPEC_SETUP)) {
+        p.gain = reinterpret_cast<float*>(ws + l.gains);   // computed by an earlier SETUP phase
+    } else if (noise && !gain) {
         // K from snr_db with the reference's float32 arithmetic (noise.cu)
         float* g = reinterpret_cast<float*>(ws + l.gains);
         const int st = asrk_snr2k_run(reinterpret_cast<const float*>(samples), noise, sample_offsets,
@@ -561,9 +563,11 @@ extern "C" int asrk_spectrogram_run(const void* samples, int sample_dtype, const
         p.gain = g;
     }
 
-    setup_kernel<<<1, 1024, 0, stream>>>(const_cast<double*>(p.tables), frame_offsets, batch,
-                                         p.tile_offsets, p.done);
-    if (sample_dtype == ASRK_DTYPE_F32) {
+    if (phases & ASRK_PHASE_SPEC_SETUP)
+        setup_kernel<<<1, 1024, 0, stream>>>(const_cast<double*>(p.tables), frame_offsets, batch,
+                                             p.tile_offsets, p.done);
+    if (!(phases & ASRK_PHASE_SPEC_MAIN)) {
+    } else if (sample_dtype == ASRK_DTYPE_F32) {
         const size_t smem = main_smem_bytes<true>();
         cudaFuncSetAttribute(spectrogram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         spectrogram_kernel<true><<<grid, kThreads, smem, stream>>>(p);
@@ -572,6 +576,19 @@ extern "C" int asrk_spectrogram_run(const void* samples, int sample_dtype, const
         cudaFuncSetAttribute(spectrogram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         spectrogram_kernel<false><<<grid, kThreads, smem, stream>>>(p);
     }
-    if (mode == ASRK_SPEC_FBANK) normalize_kernel<<<grid * 4, 256, 0, stream>>>(p);
+    if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE))
+        normalize_kernel<<<grid * 4, 256, 0, stream>>>(p);
     return launch_status();
+}
+
+extern "C" int asrk_spectrogram_run(const void* samples, int sample_dtype, const float* noise,
+                                    const float* gain, const int* snr_db,
+                                    const long long* sample_offsets, const long long* sample_counts,
+                                    const long long* frame_offsets, const long long* out_row_offsets,
+                                    int batch, long long total_frames,
+                                    int mode, float* out, void* workspace, size_t workspace_bytes,
+                                    asrk_stream_t stream_) {
+    return asrk_spectrogram_run_phases(samples, sample_dtype, noise, gain, snr_db, sample_offsets,
+                                       sample_counts, frame_offsets, out_row_offsets, batch, total_frames,
+                                       mode, out, workspace, workspace_bytes, stream_, ASRK_PHASE_ALL);
 }

@@ -53,7 +53,7 @@ def _i32(x, dev, torch):
 
 def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="by_length",
                   layout="tbv", grad_scale=None, want_grad=True, decode=False, grad_out=None,
-                  stream=None):
+                  stream=None, phases=_lib.PHASE_ALL, outputs=None):
     """Raw op: one fused pass.  logits float32 CUDA tensor ``[T,B,V]`` ('tbv') or
     ``[B,T,V]`` ('btv'); labels int32 ``[B,Lmax]``.  Returns CtcResult of device
     tensors (no synchronisation, statuses are NOT checked here)."""
@@ -72,8 +72,12 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
     input_len = _i32(input_len, dev, torch)
     label_len = _i32(label_len, dev, torch) if label_len is not None else None
     mode = _lib.LABELS_BY_LENGTH if label_mode == "by_length" else _lib.LABELS_DROP_ZEROS
-    loss = torch.empty(B, dtype=torch.float32, device=dev)
-    status = torch.empty(B, dtype=torch.int32, device=dev)
+    if outputs is not None:      # re-issue of a later phase on the same buffers
+        loss, grad_out, status, tokens_, tlen_, nsl_ = outputs
+    else:
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        tokens_ = tlen_ = nsl_ = None
     grad = None
     gt = gb = 0
     if want_grad:
@@ -81,18 +85,19 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
         _, _, _, gt, gb = _strides(grad, layout)
     tokens = tlen = nsl = None
     if decode:
-        tokens = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
-        tlen = torch.empty(B, dtype=torch.int32, device=dev)
-        nsl = torch.empty(B, dtype=torch.float32, device=dev)
+        tokens = tokens_ if tokens_ is not None else torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
+        tlen = tlen_ if tlen_ is not None else torch.empty(B, dtype=torch.int32, device=dev)
+        nsl = nsl_ if nsl_ is not None else torch.empty(B, dtype=torch.float32, device=dev)
     if grad_scale is not None:
         grad_scale = grad_scale.to(device=dev, dtype=torch.float32).contiguous()
     nbytes = L.asrk_ctc_workspace_bytes(T, B, Ls)
     ws = workspace(nbytes, dev, "ctc")
-    rc = L.asrk_ctc_loss_grad_run(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(labels), Ls,
-                                  _lib.ptr(label_len), _lib.ptr(input_len), int(blank), mode,
-                                  _lib.ptr(grad_scale), _lib.ptr(loss), _lib.ptr(grad), gt, gb,
-                                  _lib.ptr(status), _lib.ptr(tokens), max(T, 1), _lib.ptr(tlen),
-                                  _lib.ptr(nsl), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(stream))
+    rc = L.asrk_ctc_loss_grad_run_phases(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(labels), Ls,
+                                         _lib.ptr(label_len), _lib.ptr(input_len), int(blank), mode,
+                                         _lib.ptr(grad_scale), _lib.ptr(loss), _lib.ptr(grad), gt, gb,
+                                         _lib.ptr(status), _lib.ptr(tokens), max(T, 1), _lib.ptr(tlen),
+                                         _lib.ptr(nsl), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(stream),
+                                         int(phases))
     _lib.check(rc, "asrk_ctc_loss_grad_run")
     return CtcResult(loss, grad, status, tokens, tlen, nsl)
 

@@ -102,7 +102,7 @@ def pack_host(signals, fs=16000, mode="fbank", noises=None, pin=True):
 
 def spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
                        mode="fbank", noise=None, gain=None, snr_db=None, out=None,
-                       out_row_offsets=None, stream=None):
+                       out_row_offsets=None, stream=None, phases=_lib.PHASE_ALL):
     """Launch the kernels on device tensors that are already packed.
 
     samples: int16 / float32 [total]; sample_offsets, sample_counts: int64 [B];
@@ -121,11 +121,11 @@ def spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, ba
         out = torch.empty((max(total_frames, 1), N_BINS), dtype=torch.float32, device=dev)[:total_frames]
     nbytes = L.asrk_spectrogram_workspace_bytes(batch, total_frames)
     ws = workspace(nbytes, dev, "spec")
-    st = L.asrk_spectrogram_run(_lib.ptr(samples), dt, _lib.ptr(noise), _lib.ptr(gain), _lib.ptr(snr_db),
-                                _lib.ptr(sample_offsets), _lib.ptr(sample_counts),
-                                _lib.ptr(frame_offsets), _lib.ptr(out_row_offsets), batch,
-                                total_frames, MODES[mode], _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                                _lib.stream_ptr(stream))
+    st = L.asrk_spectrogram_run_phases(_lib.ptr(samples), dt, _lib.ptr(noise), _lib.ptr(gain),
+                                       _lib.ptr(snr_db), _lib.ptr(sample_offsets), _lib.ptr(sample_counts),
+                                       _lib.ptr(frame_offsets), _lib.ptr(out_row_offsets), batch,
+                                       total_frames, MODES[mode], _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr(stream), int(phases))
     _lib.check(st, "asrk_spectrogram_run")
     return out
 

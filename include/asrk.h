@@ -169,6 +169,40 @@ int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long lon
                                float* neg_sum_logits, /* device float32 [B] or NULL */
                                void* workspace, size_t workspace_bytes, asrk_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Measurement entry points: the same calls with a bit mask of the launches to
+ * enqueue, so that a harness can bracket every kernel with its own CUDA events
+ * on the launching stream.  ASRK_PHASE_ALL is what the plain entry points pass;
+ * phases of one call must be issued in order on one stream with the same
+ * arguments and workspace.
+ * ------------------------------------------------------------------------ */
+#define ASRK_PHASE_SPEC_SETUP 1      /* tables, tile map, (SNR2K gains)            */
+#define ASRK_PHASE_SPEC_MAIN 2       /* framing + window + FFT + log-magnitude     */
+#define ASRK_PHASE_SPEC_NORMALIZE 4  /* per-utterance z-score                      */
+#define ASRK_PHASE_CTC_PREP 1        /* label lists, feasibility, repeat chains    */
+#define ASRK_PHASE_CTC_ROWS 2        /* per-frame log-sum-exp / arg-max / gather   */
+#define ASRK_PHASE_CTC_LATTICE 4     /* alpha / beta recursion, loss               */
+#define ASRK_PHASE_CTC_GRAD 8        /* gradient rows                              */
+#define ASRK_PHASE_CTC_COLLAPSE 16   /* greedy collapse (when tokens != NULL)      */
+#define ASRK_PHASE_ALL 0x7fffffff
+
+int asrk_spectrogram_run_phases(const void* samples, int sample_dtype, const float* noise,
+                                const float* gain, const int* snr_db,
+                                const long long* sample_offsets, const long long* sample_counts,
+                                const long long* frame_offsets, const long long* out_row_offsets,
+                                int batch, long long total_frames, int mode, float* out,
+                                void* workspace, size_t workspace_bytes, asrk_stream_t stream,
+                                int phases);
+
+int asrk_ctc_loss_grad_run_phases(const float* logits, long long stride_t, long long stride_b,
+                                  int T, int B, int V, const int* labels, int label_stride,
+                                  const int* label_len, const int* input_len, int blank,
+                                  int label_mode, const float* grad_scale, float* loss, float* grad,
+                                  long long gstride_t, long long gstride_b, int* row_status,
+                                  int* tokens, int token_stride, int* token_len,
+                                  float* neg_sum_logits, void* workspace, size_t workspace_bytes,
+                                  asrk_stream_t stream, int phases);
+
 #ifdef __cplusplus
 }
 #endif

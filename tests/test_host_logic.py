@@ -1,0 +1,58 @@
+"""CPU: host-side packing / frame rules / error behaviour (no device needed)."""
+import numpy as np
+import pytest
+
+from oracle import synth
+
+
+def test_pack_host_alignment_and_offsets():
+    from asr_dfcnn_transformer_b200 import features
+    rng = np.random.default_rng(0)
+    sigs = [synth.g1_white(rng, n) for n in (16000, 401, 9999, 300)]
+    pk = features.pack_host(sigs, pin=False)
+    assert pk.sample_counts.tolist() == [16000, 401, 9999, 300]
+    assert all(o % 8 == 0 for o in pk.sample_offsets)         # 16-byte aligned int16 starts
+    assert pk.n_frames.tolist() == [98, 1, 60, 0]
+    assert pk.frame_offsets.tolist() == [0, 98, 99, 159, 159]
+    buf = pk.samples.numpy()
+    for s, o in zip(sigs, pk.sample_offsets):
+        assert np.array_equal(buf[o:o + len(s)], s)
+    f32 = [s.astype(np.float32) / 32768 for s in sigs[:2]]
+    pk = features.pack_host(f32, pin=False, noises=[np.zeros(16000, np.float32), np.ones(401, np.float32)])
+    assert all(o % 4 == 0 for o in pk.sample_offsets) and pk.noise is not None
+
+
+def test_pack_host_errors():
+    from asr_dfcnn_transformer_b200 import features
+    rng = np.random.default_rng(0)
+    with pytest.raises(ValueError):
+        features.pack_host([], pin=False)
+    with pytest.raises(ValueError):                       # short last frame, like the reference
+        features.pack_host([synth.g1_white(rng, 399)], pin=False)
+    with pytest.raises(ValueError):                       # 8 kHz audio: frame rule asks for too many frames
+        features.pack_host([synth.g1_white(rng, 8000)], fs=8000, pin=False)
+    with pytest.raises(ValueError):
+        features.pack_host([np.zeros((2, 100), np.int16)], pin=False)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from asr_dfcnn_transformer_b200 import ctc, features
+    with pytest.raises(RuntimeError):
+        features.compute_features([np.zeros(16000, np.int16)])
+    with pytest.raises(RuntimeError):
+        ctc.greedy_decode(torch.zeros(3, 1, 4), [3])
+
+
+def test_bench_workload_shapes():
+    import bench
+    hb = bench.make_batch(2000, batch=8)
+    assert len(hb["pcm"]) == 8 and hb["logits"].shape[1:] == (8, synth.VOCAB_DICT_TXT)
+    assert all(48000 <= len(p) <= 112000 for p in hb["pcm"])
+    assert (hb["label_len"] < hb["input_len"]).all()
+    feat, ctc_b = bench.algorithmic_bytes(hb)
+    n = sum(len(p) for p in hb["pcm"])
+    assert feat == 2 * n + 800 * int(hb["nfr"].sum())
+    assert ctc_b == 8 * synth.VOCAB_DICT_TXT * int(hb["input_len"].sum())

@@ -1,0 +1,21 @@
+"""Small driver for ncu: builds one C2 batch and runs a few steps of the hot path.
+    python tools/profile_step.py [steps] [batch]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import bench  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+decode = len(sys.argv) > 3 and sys.argv[3] == "decode"
+torch.cuda.set_device(0)
+dev = torch.device("cuda", 0)
+db = bench.DeviceBatch(bench.make_batch(2000, batch=batch), dev, torch)
+for _ in range(steps):
+    r = bench.run_step(db)
+torch.cuda.synchronize()
+print("loss sum", float(r.loss.sum()), "status max", int(r.row_status.max()))
