@@ -34,7 +34,7 @@ constexpr int kFftWarps = 10;
 constexpr int kHelperWarps = 4;
 constexpr int kFftThreads = kFftWarps * 32;          // 320
 constexpr int kHelperThreads = kHelperWarps * 32;    // 128
-constexpr int kThreads = kFftThreads + kHelperThreads;
+constexpr int kThreads = 16 * 32;                    // warps 12,13 are placeholders (see roles)
 constexpr int kTile = 32;                            // frames per tile (= lanes)
 constexpr int kHop = 160, kFrameLen = 400, kBins = 200;
 constexpr int kHopRows = 34;                         // 31*160+400 = 5360 samples -> 34 hops
@@ -42,7 +42,6 @@ constexpr int kOutStride = 201;                      // padded row of the |X|^2 
 constexpr int kHopWordsI16 = 81;                     // 80 words of int16 pairs + 1 pad (odd)
 constexpr int kHopWordsF32 = 162;                    // 160 words + 2 pad (81 * 2)
 constexpr int kTabDoubles = 1200;                    // window[400] | W200 table[200 cplx] | P[200 cplx]
-constexpr int kHelperBar = 1;
 
 struct TileRec {            // written by the main kernel, read by the normalise kernel
     int b;
@@ -95,7 +94,7 @@ static WsLayout ws_layout(int batch, long long total_frames, int grid) {
     l.done = o;          o = align_up(o + sizeof(int) * (size_t)batch, 256);
     l.gains = o;         o = align_up(o + sizeof(float) * (size_t)batch, 256);
     l.stats = o;         o = align_up(o + sizeof(double) * 400 * (size_t)batch, 256);
-    l.partials = o;      o = align_up(o + sizeof(double) * 400 * (size_t)(grid + batch + 1), 256);
+    l.partials = o;      o = align_up(o + sizeof(double) * 400 * kHelperWarps * (size_t)(grid + batch + 1), 256);
     l.tile_rec = o;
     size_t max_tiles = (size_t)(total_frames / kTile) + (size_t)batch + 1;
     o = align_up(o + sizeof(TileRec) * max_tiles, 256);
@@ -164,11 +163,6 @@ __device__ __forceinline__ double i16_to_f64(int v) {
     return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)v)) - 4503601774854144.0;
 }
 
-__device__ __forceinline__ float log_mag(float p4, float mag) {
-    // p4 = 4 |X|^2 ; log(|X| * mag + 1), natural log (wav_util.py:76,107,111)
-    const float m = sqrtf(p4) * (0.5f * mag);
-    return log1pf(m);
-}
 
 template <bool F32>
 __device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, uint32_t* dst, int hth) {
@@ -272,6 +266,77 @@ __device__ __forceinline__ int chunk_of(long long tile, long long n, long long G
 // ---------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------
+// Named barriers (id 0 is __syncthreads).  FULL/EMPTY pairs hand the three PCM
+// buffers and the two |X|^2 tiles between the FFT warps and the helper warps so
+// that neither side waits for the other unless it is a whole tile behind.
+enum : int {
+    kBarHelpers = 1,      // helper warps only
+    kBarExchA = 2,        // FFT warps only: pass 1 -> pass 2
+    kBarExchB = 3,        // FFT warps only: pass 2 -> next pass 1
+    kBarPcmFull = 4,      // +stage (4,5,6)
+    kBarPcmEmpty = 7,     // +stage (7,8,9)
+    kBarOutFull = 10,     // +slot (10,11)
+    kBarOutEmpty = 12,    // +slot (12,13)
+};
+constexpr int kPipeThreads = kFftThreads + kHelperThreads;   // threads on a FULL/EMPTY barrier
+
+__device__ __forceinline__ void bar_sync(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// log(|X| * mag + 1) from p4 = 4 |X|^2, natural log (wav_util.py:76,107,111), fp32:
+// v = 1 + m is split into 2^e * f exactly; lg2.approx on f in [1,2) has an absolute
+// error of 2^-22, so the result is good to ~1 ulp at any magnitude; for small m the
+// rounding of 1 + m is put back with the first-order term (m - (v - 1)) / v.
+__device__ __forceinline__ float log_mag(float p4, float half_mag) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p4));
+    const float m = r * half_mag;
+    const float v = 1.0f + m;
+    const int vi = __float_as_int(v);
+    const float e = (float)((vi >> 23) - 127);
+    const float f = __int_as_float((vi & 0x007fffff) | 0x3f800000);
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(f));
+    // ln2 = 0.693145751953125 (exact in 12 bits) + 1.42860682e-6
+    float y = fmaf(e, 0.693145751953125f, fmaf(l2, 0.69314718056f, e * 1.42860682e-6f));
+    // (called from divergent code: no warp votes here)
+    if (m < 0.5f) y += __fdividef(m - (v - 1.0f), v);
+    return y;
+}
+
+// Asynchronous staging of one PCM tile (no arithmetic on the way): LDGSTS copies of
+// one padded-layout word (int16 pair) / two words (float pair), zero-filled past
+// the end of the utterance.  Needs the utterance start to be 4- / 8-byte aligned.
+template <bool F32>
+__device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta& m, uint32_t* dst, int hth) {
+    const long long t0 = (long long)m.f0 * kHop;
+    if (!F32) {
+        const short* src = reinterpret_cast<const short*>(p.samples) + m.sbase;
+        constexpr int kWords = kHopRows * 80;
+        for (int w = hth; w < kWords; w += kHelperThreads) {
+            const long long us = t0 + 2LL * w;
+            long long rem = (m.nsamp - us) * 2;
+            const int nb = rem >= 4 ? 4 : (rem > 0 ? (int)rem : 0);
+            cp_async4(dst + (w / 80) * kHopWordsI16 + (w % 80), nb ? src + us : src, nb);
+        }
+    } else {
+        const float* src = reinterpret_cast<const float*>(p.samples) + m.sbase;
+        constexpr int kPairs = kHopRows * 80;
+        for (int w = hth; w < kPairs; w += kHelperThreads) {
+            const long long us = t0 + 2LL * w;
+            long long rem = (m.nsamp - us) * 4;
+            const int nb = rem >= 8 ? 8 : (rem > 0 ? (int)rem : 0);
+            cp_async8(reinterpret_cast<float*>(dst) + (w / 80) * kHopWordsF32 + 2 * (w % 80),
+                      nb ? src + us : src, nb);
+        }
+    }
+}
+
 template <bool F32>
 __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -279,8 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     double* tab = reinterpret_cast<double*>(smem_raw);                       // 1200 doubles
     cplx* exch = reinterpret_cast<cplx*>(tab + kTabDoubles);                  // [200][32]
     float* outt = reinterpret_cast<float*>(exch + 200 * kTile);               // [2][32*201]
-    uint32_t* pcm = reinterpret_cast<uint32_t*>(outt + 2 * kTile * kOutStride);  // [2][kPcmWords]
-    double* flushbuf = reinterpret_cast<double*>(pcm + 2 * kPcmWords + ((2 * kPcmWords) & 1));  // [4][400]
+    uint32_t* pcm = reinterpret_cast<uint32_t*>(outt + 2 * kTile * kOutStride);  // [3][kPcmWords]
     __shared__ Meta meta[4];
     __shared__ int s_flag;
 
@@ -291,20 +355,25 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     const int tile_begin = (int)((long long)blockIdx.x * n_tiles / G);
     const int tile_end = (int)((long long)(blockIdx.x + 1) * n_tiles / G);
     const int my_tiles = tile_end - tile_begin;
+    if (my_tiles <= 0) return;   // uniform per CTA
 
     for (int i = tid; i < kTabDoubles; i += kThreads) tab[i] = p.tables[i];
-    if (my_tiles <= 0) return;   // uniform per CTA
+    __syncthreads();
 
     const double* tabW = tab;
     const cplx* tabT = reinterpret_cast<const cplx*>(tab + 400);
     const cplx* tabP = reinterpret_cast<const cplx*>(tab + 800);
 
+    // warp roles: 0..9 FFT; 10,11,14,15 helpers (two on each of the sub-partitions
+    // that only hold two FFT warps); 12,13 only pad the warp numbering
     if (warp < kFftWarps) {
         // ------------------------------ FFT warps ------------------------------
         const int r = warp;
-        __syncthreads();   // S0
+        int st = 0;   // PCM stage = i % 3
         for (int i = 0; i < my_tiles; ++i) {
-            const uint32_t* pc = pcm + (i & 1) * kPcmWords;
+            const int s = i & 1;
+            const uint32_t* pc = pcm + st * kPcmWords;
+            bar_sync(kBarPcmFull + st, kPipeThreads);
             {
                 cplx z[20], y[20];
 #pragma unroll
@@ -325,53 +394,55 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                     const double2 w2 = *reinterpret_cast<const double2*>(tabW + 20 * n1 + 2 * r);
                     z[n1] = cplx{x0 * w2.x, x1 * w2.y};   // wav_util.py:71 data_line * w
                 }
+                if (i + 3 < my_tiles) bar_arrive(kBarPcmEmpty + st, kPipeThreads);
                 fft200_pass1(z, tabT + r * 20, y);
 #pragma unroll
                 for (int k1 = 0; k1 < 20; ++k1) exch[(k1 * 10 + r) * kTile + lane] = y[k1];
             }
-            __syncthreads();   // S1
+            bar_sync(kBarExchA, kFftThreads);
+            if (i >= 2) bar_sync(kBarOutEmpty + s, kPipeThreads);
             {
-                float* ot = outt + (i & 1) * (kTile * kOutStride) + lane * kOutStride;
+                float* ot = outt + s * (kTile * kOutStride) + lane * kOutStride;
                 auto loadY = [&](int k1, int n2) { return exch[(k1 * 10 + n2) * kTile + lane]; };
                 auto emit = [&](int k, double p4) { ot[k] = (float)p4; };
                 fft200_pass2(r, loadY, tabP, emit);
             }
-            __syncthreads();   // S2
+            bar_arrive(kBarOutFull + s, kPipeThreads);
+            bar_sync(kBarExchB, kFftThreads);
+            st = (st == 2) ? 0 : st + 1;
         }
-    } else {
+    } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
         // ----------------------------- helper warps ----------------------------
-        const int hth = tid - kFftThreads;
-        const int hw = hth >> 5;
+        const int hw = (warp < 12) ? warp - 10 : warp - 12;      // 0..3
+        const int hth = hw * 32 + lane;
+        const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
+        const bool mix = (p.noise != nullptr);
         double acc1[7], acc2[7];
 #pragma unroll
         for (int s = 0; s < 7; ++s) { acc1[s] = 0.0; acc2[s] = 0.0; }
-        const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
         int acc_b = -1;        // utterance the accumulators belong to
         int acc_tiles = 0;     // tiles accumulated since the last flush
         int acc_tiles_b = 0;   // total tiles of utterance acc_b
         long long acc_nfr = 0;
 
         auto flush = [&]() {
-            // combine the four helper warps in a fixed order, publish the partial
-            // column sums, and let the CTA that retires the utterance finalise it
-            double* fb = flushbuf + hw * 400;
+            // publish this warp's partial column sums; the CTA that retires the last
+            // tile of the utterance adds all partials in a fixed order (no atomics on
+            // data) and writes mean and 1/std
+            double* slot = p.partials + ((size_t)(blockIdx.x + acc_b) * kHelperWarps + hw) * 400;
 #pragma unroll
             for (int s = 0; s < 7; ++s) {
                 const int k = lane + 32 * s;
-                if (k < kBins) { fb[k] = acc1[s]; fb[200 + k] = acc2[s]; }
+                if (k < kBins) { slot[k] = acc1[s]; slot[200 + k] = acc2[s]; }
                 acc1[s] = 0.0; acc2[s] = 0.0;
             }
-            named_bar_sync(kHelperBar, kHelperThreads);
-            double* slot = p.partials + (size_t)(blockIdx.x + acc_b) * 400;
-            for (int k = hth; k < 400; k += kHelperThreads)
-                slot[k] = ((flushbuf[k] + flushbuf[400 + k]) + flushbuf[800 + k]) + flushbuf[1200 + k];
             __threadfence();
-            named_bar_sync(kHelperBar, kHelperThreads);
+            bar_sync(kBarHelpers, kHelperThreads);
             if (hth == 0) {
                 const int old = atomicAdd(p.done + acc_b, acc_tiles);
                 s_flag = (old + acc_tiles == acc_tiles_b);
             }
-            named_bar_sync(kHelperBar, kHelperThreads);
+            bar_sync(kBarHelpers, kHelperThreads);
             if (s_flag) {
                 __threadfence();
                 const long long t_lo = p.tile_offsets[acc_b];
@@ -382,9 +453,12 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                     for (int c = c_lo; c <= c_hi; ++c) {
                         // CTAs whose chunk is empty never flushed anything
                         if ((long long)(c + 1) * n_tiles / G == (long long)c * n_tiles / G) continue;
-                        const double* q = p.partials + (size_t)(c + acc_b) * 400;
-                        s1 += __ldcg(q + k);
-                        s2 += __ldcg(q + 200 + k);
+                        const double* q = p.partials + (size_t)(c + acc_b) * kHelperWarps * 400;
+#pragma unroll
+                        for (int h = 0; h < kHelperWarps; ++h) {
+                            s1 += __ldcg(q + h * 400 + k);
+                            s2 += __ldcg(q + h * 400 + 200 + k);
+                        }
                     }
                     // sklearn.preprocessing.scale (wav_util.py:79): mean, std (ddof=0),
                     // std < 10 eps -> 1
@@ -398,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                     p.stats[(size_t)acc_b * 400 + 200 + k] = 1.0 / sd;
                 }
             }
-            named_bar_sync(kHelperBar, kHelperThreads);
+            bar_sync(kBarHelpers, kHelperThreads);
             acc_tiles = 0;
         };
 
@@ -411,7 +485,8 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                 acc_nfr = m.nfr;
             }
             const float* ot = outt + (i & 1) * (kTile * kOutStride);
-#pragma unroll 1
+            const float half_mag = 0.5f * m.mag;
+#pragma unroll 2
             for (int ff = 0; ff < 8; ++ff) {
                 const int f = hw * 8 + ff;
                 if (f >= m.nf) break;
@@ -420,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                 for (int s = 0; s < 7; ++s) {
                     const int k = lane + 32 * s;
                     if (k < kBins) {
-                        const float y = log_mag(ot[f * kOutStride + k], m.mag);
+                        const float y = log_mag(ot[f * kOutStride + k], half_mag);
                         orow[k] = y;
                         if (want_stats) {
                             const double yd = (double)y;
@@ -433,30 +508,41 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
             acc_tiles += 1;
         };
 
-        if (hth == 0) {
-            fill_meta(p, tile_begin, -1, meta[0]);
-            TileRec rec{meta[0].b, meta[0].nf, meta[0].row0};
-            p.tile_rec[tile_begin] = rec;
-        }
-        named_bar_sync(kHelperBar, kHelperThreads);
-        load_pcm_tile<F32>(p, meta[0], pcm, hth);
-        __syncthreads();   // S0
-        for (int i = 0; i < my_tiles; ++i) {
-            if (i + 1 < my_tiles) {
+        // tile t (chunk-local): metadata, then start filling PCM stage t % 3.  The
+        // async path returns with the copies in flight (one commit group per tile).
+        auto issue = [&](int t) {
+            if (t < my_tiles) {
                 if (hth == 0) {
-                    Meta& mn = meta[(i + 1) & 3];
-                    fill_meta(p, tile_begin + i + 1, meta[i & 3].b, mn);
+                    Meta& mn = meta[t & 3];
+                    fill_meta(p, tile_begin + t, t == 0 ? -1 : meta[(t - 1) & 3].b, mn);
                     TileRec rec{mn.b, mn.nf, mn.row0};
-                    p.tile_rec[tile_begin + i + 1] = rec;
+                    p.tile_rec[tile_begin + t] = rec;
                 }
-                named_bar_sync(kHelperBar, kHelperThreads);
-                load_pcm_tile<F32>(p, meta[(i + 1) & 3], pcm + ((i + 1) & 1) * kPcmWords, hth);
+                bar_sync(kBarHelpers, kHelperThreads);
+                if (t >= 3) bar_sync(kBarPcmEmpty + (t % 3), kPipeThreads);
+                const Meta& m = meta[t & 3];
+                uint32_t* dst = pcm + (t % 3) * kPcmWords;
+                const bool aligned = ((m.sbase * (F32 ? 4 : 2)) & (F32 ? 7 : 3)) == 0;
+                if (!mix && aligned) issue_pcm_tile_async<F32>(p, m, dst, hth);
+                else load_pcm_tile<F32>(p, m, dst, hth);
             }
-            __syncthreads();   // S1
-            if (i >= 1) epilogue(i - 1);
-            __syncthreads();   // S2
+            cp_async_commit();
+        };
+
+        issue(0);
+        issue(1);
+        cp_async_wait<1>();
+        bar_arrive(kBarPcmFull + 0, kPipeThreads);
+        for (int i = 0; i < my_tiles; ++i) {
+            issue(i + 2);
+            if (i + 1 < my_tiles) {
+                cp_async_wait<1>();          // everything but the newest group: tile i+1 has landed
+                bar_arrive(kBarPcmFull + ((i + 1) % 3), kPipeThreads);
+            }
+            bar_sync(kBarOutFull + (i & 1), kPipeThreads);
+            epilogue(i);
+            if (i + 2 < my_tiles) bar_arrive(kBarOutEmpty + (i & 1), kPipeThreads);
         }
-        epilogue(my_tiles - 1);
         if (want_stats) flush();
     }
 }
@@ -495,8 +581,7 @@ template <bool F32>
 static size_t main_smem_bytes() {
     const size_t pcm_words = (size_t)kHopRows * (F32 ? kHopWordsF32 : kHopWordsI16);
     size_t b = sizeof(double) * kTabDoubles + sizeof(cplx) * 200 * kTile +
-               sizeof(float) * 2 * kTile * kOutStride + sizeof(uint32_t) * (2 * pcm_words + 1) +
-               sizeof(double) * 4 * 400;
+               sizeof(float) * 2 * kTile * kOutStride + sizeof(uint32_t) * (3 * pcm_words);
     return b + 16;
 }
 
@@ -508,7 +593,7 @@ using namespace asrk::spec;
 
 extern "C" size_t asrk_spectrogram_workspace_bytes(int batch, long long total_frames) {
     if (batch < 0 || total_frames < 0) return 0;
-    return ws_layout(batch, total_frames, 1024).total;
+    return ws_layout(batch, total_frames, 256).total;
 }
 
 extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype, const float* noise,
@@ -529,8 +614,8 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
     if (noise && !gain && !snr_db) return ASRK_E_BADARG;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return ASRK_E_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return ASRK_E_ALIGN;
-    const int grid = sm_count();
-    const WsLayout l = ws_layout(batch, total_frames, 1024);
+    const int grid = sm_count() > 256 ? 256 : sm_count();
+    const WsLayout l = ws_layout(batch, total_frames, 256);
     if (workspace_bytes < l.total) return ASRK_E_WORKSPACE;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
 
