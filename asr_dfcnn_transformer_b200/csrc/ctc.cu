@@ -64,13 +64,14 @@ struct Params {
     int* argmax;         // [B][T]
     float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (log-softmax)
     float* occ;          // [B][T][2 Ls+1] alpha (scaled) then occupancy, lattice order
+    float* beta;         // [B][T][2 Ls+1] beta (small-lattice kernel only)
     double* coff;        // [B][T]        alpha offsets
     double* logp;        // [B]
     int Ls;              // label_stride
 };
 
 struct WsLayout {
-    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, coff, logp, total;
+    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, beta, coff, logp, total;
 };
 
 static WsLayout ws_layout(int T, int B, int Ls) {
@@ -86,6 +87,7 @@ static WsLayout ws_layout(int T, int B, int Ls) {
     l.argmax = o;      o = align_up(o + sizeof(int) * BT, 256);
     l.lpl = o;         o = align_up(o + sizeof(float) * BT * (size_t)(Ls + 1), 256);
     l.occ = o;         o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
+    l.beta = o;        o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
     l.coff = o;        o = align_up(o + sizeof(double) * BT, 256);
     l.logp = o;        o = align_up(o + sizeof(double) * (size_t)B, 256);
     l.total = o;
@@ -95,46 +97,80 @@ static WsLayout ws_layout(int T, int B, int Ls) {
 // ---------------------------------------------------------------------------
 // prep
 // ---------------------------------------------------------------------------
-__global__ void prep_kernel(Params p) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.B) return;
+// One CTA per utterance, one thread per label slot.
+__global__ void __launch_bounds__(1024) prep_kernel(Params p) {
+    extern __shared__ int sh[];            // [Ls] effective labels, then [33] scan scratch
+    const int b = blockIdx.x;
+    const int j = threadIdx.x;
+    const int Ls = p.label_stride;
+    int* seff = sh;
+    int* scr = sh + (Ls > 0 ? Ls : 1);
+    __shared__ int s_status;
     const int* lab = p.labels + (size_t)b * p.label_stride;
     int* eff = p.eff_labels + (size_t)b * p.Ls;
     int* nxt = p.chain_next + (size_t)b * p.Ls;
     int* fst = p.chain_first + (size_t)b * p.Ls;
-    int status = ASRK_ROW_OK;
-    int L = 0;
-    if (p.label_mode == ASRK_LABELS_BY_LENGTH) {
-        L = p.label_len[b];
-        if (L < 0 || L > p.label_stride) { status = ASRK_ROW_BAD_LENGTH; L = 0; }
-        for (int j = 0; j < L; ++j) eff[j] = lab[j];
-    } else {
-        // tf.contrib.layers.dense_to_sparse: every 0 entry is dropped (acoustic_model2.py:71)
-        for (int j = 0; j < p.label_stride; ++j)
-            if (lab[j] != 0) eff[L++] = lab[j];
-    }
     const int tl = p.input_len[b];
-    if (tl < 1 || tl > p.T) status = ASRK_ROW_BAD_LENGTH;
-    int repeats = 0;
-    for (int j = 0; j < L; ++j) {
-        const int c = eff[j];
-        if (c < 0 || c >= p.V) { status = ASRK_ROW_BAD_LENGTH; eff[j] = 0; }
-        if (j > 0 && eff[j] == eff[j - 1]) ++repeats;
+    if (j == 0) s_status = (tl < 1 || tl > p.T) ? ASRK_ROW_BAD_LENGTH : ASRK_ROW_OK;
+    int Lby = 0;
+    if (p.label_mode == ASRK_LABELS_BY_LENGTH) {
+        Lby = p.label_len[b];
+        if (Lby < 0 || Lby > Ls) Lby = -1;
     }
-    if (status == ASRK_ROW_OK && tl < L + repeats) status = ASRK_ROW_NOT_ENOUGH_TIME;
-    // chains of equal labels (O(L^2), L is at most a few hundred)
-    for (int j = 0; j < L; ++j) {
+    __syncthreads();
+    if (Lby < 0) {
+        if (j == 0) { p.eff_len[b] = 0; p.row_status[b] = ASRK_ROW_BAD_LENGTH; }
+        return;
+    }
+    // keep flag: by length (Keras) or every non-zero entry (dense_to_sparse, acoustic_model2.py:71)
+    const int v = (j < Ls) ? lab[j] : 0;
+    const int keep = (j < Ls) && ((p.label_mode == ASRK_LABELS_BY_LENGTH) ? (j < Lby) : (v != 0));
+    // block-wide exclusive scan of keep
+    const int lane = j & 31, warp = j >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) scr[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        int c = (lane < (int)(blockDim.x >> 5)) ? scr[lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        scr[lane] = incl - c;
+        if (lane == 31) scr[32] = incl;
+    }
+    __syncthreads();
+    const int L = scr[32];
+    if (keep) {
+        int c = v;
+        if (c < 0 || c >= p.V) { atomicExch(&s_status, ASRK_ROW_BAD_LENGTH); c = 0; }
+        seff[scr[warp] + within] = c;
+    }
+    __syncthreads();
+    int rep = 0;
+    if (j < L) {
+        const int c = seff[j];
+        eff[j] = c;
+        rep = (j > 0 && seff[j - 1] == c) ? 1 : 0;
         int n = -1;
         for (int k = j + 1; k < L; ++k)
-            if (eff[k] == eff[j]) { n = k; break; }
+            if (seff[k] == c) { n = k; break; }
         nxt[j] = n;
         int first = 1;
         for (int k = 0; k < j; ++k)
-            if (eff[k] == eff[j]) { first = 0; break; }
+            if (seff[k] == c) { first = 0; break; }
         fst[j] = first;
     }
-    p.eff_len[b] = (status == ASRK_ROW_BAD_LENGTH) ? 0 : L;
-    p.row_status[b] = status;
+    const int repeats = __syncthreads_count(rep);
+    if (j == 0) {
+        int status = s_status;
+        if (status == ASRK_ROW_OK && tl < L + repeats) status = ASRK_ROW_NOT_ENOUGH_TIME;
+        p.eff_len[b] = (status == ASRK_ROW_BAD_LENGTH) ? 0 : L;
+        p.row_status[b] = status;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -288,6 +324,121 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     return warp_max(r);
 }
 
+// Utterances whose lattice fits one warp (L <= 31 labels -> 32 state pairs) and whose
+// gathered log-probabilities fit the shared-memory budget take the warp-level kernel.
+constexpr int kSmallSmemFloats = 16 * 1024;   // 64 KB of lpl per CTA
+__host__ __device__ __forceinline__ bool small_lattice(int L, int T) {
+    return L <= 31 && (long long)T * (L + 1) <= kSmallSmemFloats;
+}
+
+// Warp-per-direction lattice: warp 0 runs alpha, warp 1 runs beta AT THE SAME TIME
+// (they only meet in the occupancies), lane i owns one state pair, the neighbour
+// value moves by one warp shuffle per step, and the gathered log-probabilities of
+// the whole utterance sit in shared memory.  No block barrier inside the recursion.
+// A final pass over all (t,u) by the whole CTA turns alpha + beta - log p into
+// occupancies.
+__global__ void __launch_bounds__(128) lattice_small_kernel(Params p) {
+    extern __shared__ float slp[];             // [T][L+1]
+    __shared__ double s_fin[2];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int status = p.row_status[b];
+    const int L = p.eff_len[b];
+    const int T = p.input_len[b];
+    const double ninf = (double)kNegInf;
+    if (status == ASRK_ROW_BAD_LENGTH) {
+        if (tid == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
+        return;
+    }
+    if (!small_lattice(L, T)) return;          // handled by lattice_kernel
+    const int S = p.Ls + 1;
+    const int U = 2 * p.Ls + 1;
+    const int W = L + 1;                        // shared row width
+    const float* lpl = p.lpl + (size_t)b * p.T * S;
+    float* alpha = p.occ + (size_t)b * p.T * U;
+    float* beta = p.beta + (size_t)b * p.T * U;
+    const int* eff = p.eff_labels + (size_t)b * p.Ls;
+    for (int idx = tid; idx < T * W; idx += blockDim.x) slp[idx] = lpl[(size_t)(idx / W) * S + (idx % W)];
+    __syncthreads();
+
+    const int i = lane;
+    const int lab_i = (i < L) ? eff[i] : -1;
+    const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
+    const bool skip = (i >= 1 && i < L && lab_i != lab_im1);
+    const bool has_blank = (i <= L);
+    if (warp == 0) {
+        // alpha: pair (blank 2i, label 2i+1)
+        const bool has_lab = (i < L);
+        double a_b = ninf, a_l = ninf;
+        if (i == 0) {
+            a_b = (double)slp[0];
+            if (L >= 1) a_l = (double)slp[1];
+        }
+        if (has_blank) alpha[2 * i] = (float)a_b;
+        if (has_lab) alpha[2 * i + 1] = (float)a_l;
+        for (int t = 1; t < T; ++t) {
+            const double lb = (double)slp[t * W];
+            const double ll = has_lab ? (double)slp[t * W + 1 + i] : ninf;
+            double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+            if (i == 0) p1 = ninf;
+            const double nb = lb + lse2(a_b, p1);
+            const double nl = ll + lse3(a_l, a_b, skip ? p1 : ninf);
+            a_b = has_blank ? nb : ninf;
+            a_l = has_lab ? nl : ninf;
+            float* o = alpha + (size_t)t * U;
+            if (has_blank) o[2 * i] = (float)a_b;
+            if (has_lab) o[2 * i + 1] = (float)a_l;
+        }
+        // log p = LSE(alpha_{T-1}(2L), alpha_{T-1}(2L-1))
+        const double fb = __shfl_sync(0xffffffffu, a_b, L);
+        const double fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : ninf;
+        if (lane == 0) s_fin[0] = lse2(fb, fl);
+    } else if (warp == 1 && p.grad != nullptr) {
+        // beta: pair (label 2i-1, blank 2i); excludes y_t
+        const bool has_lab = (i >= 1 && i <= L);
+        double b_l = ninf, b_b = ninf;
+        if (i == L) {
+            b_b = 0.0;
+            if (L >= 1) b_l = 0.0;
+        }
+        {
+            float* o = beta + (size_t)(T - 1) * U;
+            if (has_blank) o[2 * i] = (float)b_b;
+            if (has_lab) o[2 * i - 1] = (float)b_l;
+        }
+        for (int t = T - 2; t >= 0; --t) {
+            const double lb = (double)slp[(t + 1) * W];
+            const double ll = has_lab ? (double)slp[(t + 1) * W + i] : ninf;
+            const double e_b = b_b + lb;
+            const double e_l = b_l + ll;
+            double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+            if (i == 31) n1 = ninf;
+            const double nbb = lse2(e_b, n1);
+            const double nbl = lse3(e_l, e_b, skip ? n1 : ninf);
+            b_b = has_blank ? nbb : ninf;
+            b_l = has_lab ? nbl : ninf;
+            float* o = beta + (size_t)t * U;
+            if (has_blank) o[2 * i] = (float)b_b;
+            if (has_lab) o[2 * i - 1] = (float)b_l;
+        }
+    }
+    __syncthreads();
+    const double logp = s_fin[0];
+    if (tid == 0) {
+        p.logp[b] = logp;
+        p.loss[b] = (float)(-logp);
+        if (logp == ninf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
+    }
+    if (p.grad == nullptr || logp == ninf) return;
+    // occupancies: exp(alpha + beta - log p), every (t,u) independently
+    const int Ub = 2 * L + 1;
+    for (int idx = tid; idx < T * Ub; idx += blockDim.x) {
+        const size_t off = (size_t)(idx / Ub) * U + (idx % Ub);
+        alpha[off] = __expf((float)((double)alpha[off] + (double)beta[off] - logp));
+    }
+}
+
 // One CTA per utterance; thread i owns the state pair
 //   alpha sweep: (blank 2i, label 2i+1)     beta sweep: (label 2i-1, blank 2i)
 // so that each step needs exactly one neighbour value (the previous / next
@@ -310,6 +461,7 @@ __global__ void lattice_kernel(Params p) {
         if (i == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
         return;
     }
+    if (small_lattice(L, T)) return;          // handled by lattice_small_kernel
     const int S = p.Ls + 1;
     const int U = 2 * p.Ls + 1;
     const float* lpl = p.lpl + (size_t)b * p.T * S;
@@ -593,6 +745,7 @@ static void bind_workspace(Params& p, void* workspace, const WsLayout& l) {
     p.argmax = reinterpret_cast<int*>(ws + l.argmax);
     p.lpl = reinterpret_cast<float*>(ws + l.lpl);
     p.occ = reinterpret_cast<float*>(ws + l.occ);
+    p.beta = reinterpret_cast<float*>(ws + l.beta);
     p.coff = reinterpret_cast<double*>(ws + l.coff);
     p.logp = reinterpret_cast<double*>(ws + l.logp);
 }
@@ -634,11 +787,19 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     bind_workspace(p, workspace, l);
 
     const int nv4 = pick_nv4(p, logits, stride_t, stride_b, grad, gstride_t, gstride_b);
-    if (phases & ASRK_PHASE_CTC_PREP) prep_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p);
+    if (phases & ASRK_PHASE_CTC_PREP) {
+        const int pt = ((label_stride > 0 ? label_stride : 1) + 31) / 32 * 32;
+        prep_kernel<<<B, pt, sizeof(int) * (Ls + 40), stream>>>(p);
+    }
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
-    if (phases & ASRK_PHASE_CTC_LATTICE)
+    if (phases & ASRK_PHASE_CTC_LATTICE) {
+        // both kernels see every utterance; each takes the ones that fit it
+        cudaFuncSetAttribute(lattice_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(float) * kSmallSmemFloats));
+        lattice_small_kernel<<<B, 128, sizeof(float) * kSmallSmemFloats, stream>>>(p);
         lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p);
+    }
     if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
     if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
     return launch_status();

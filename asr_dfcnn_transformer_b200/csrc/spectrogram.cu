@@ -39,8 +39,12 @@ constexpr int kTile = 32;                            // frames per tile (= lanes
 constexpr int kHop = 160, kFrameLen = 400, kBins = 200;
 constexpr int kHopRows = 34;                         // 31*160+400 = 5360 samples -> 34 hops
 constexpr int kOutStride = 201;                      // padded row of the |X|^2 tile
-constexpr int kHopWordsI16 = 81;                     // 80 words of int16 pairs + 1 pad (odd)
-constexpr int kHopWordsF32 = 162;                    // 160 words + 2 pad (81 * 2)
+// hop rows stay 16-byte aligned (for 16-byte async copies) and are padded by 16
+// bytes: lane f reads word 84 f + c -> 8 distinct banks, a 4-way conflict on the
+// 20 sample loads of a thread per tile (the rest of its ~110 shared accesses are
+// conflict-free), instead of the 16-way conflict of the unpadded layout.
+constexpr int kHopWordsI16 = 84;                     // 80 words of int16 pairs + 4 pad
+constexpr int kHopWordsF32 = 164;                    // 160 words + 4 pad
 constexpr int kTabDoubles = 1200;                    // window[400] | W200 table[200 cplx] | P[200 cplx]
 
 struct TileRec {            // written by the main kernel, read by the normalise kernel
@@ -309,31 +313,24 @@ __device__ __forceinline__ float log_mag(float p4, float half_mag) {
     return y;
 }
 
-// Asynchronous staging of one PCM tile (no arithmetic on the way): LDGSTS copies of
-// one padded-layout word (int16 pair) / two words (float pair), zero-filled past
-// the end of the utterance.  Needs the utterance start to be 4- / 8-byte aligned.
+// Asynchronous staging of one PCM tile (no arithmetic on the way): 16-byte LDGSTS
+// copies into the padded hop rows, zero-filled past the end of the utterance.
+// Needs the utterance start to be 16-byte aligned.
 template <bool F32>
 __device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta& m, uint32_t* dst, int hth) {
     const long long t0 = (long long)m.f0 * kHop;
-    if (!F32) {
-        const short* src = reinterpret_cast<const short*>(p.samples) + m.sbase;
-        constexpr int kWords = kHopRows * 80;
-        for (int w = hth; w < kWords; w += kHelperThreads) {
-            const long long us = t0 + 2LL * w;
-            long long rem = (m.nsamp - us) * 2;
-            const int nb = rem >= 4 ? 4 : (rem > 0 ? (int)rem : 0);
-            cp_async4(dst + (w / 80) * kHopWordsI16 + (w % 80), nb ? src + us : src, nb);
-        }
-    } else {
-        const float* src = reinterpret_cast<const float*>(p.samples) + m.sbase;
-        constexpr int kPairs = kHopRows * 80;
-        for (int w = hth; w < kPairs; w += kHelperThreads) {
-            const long long us = t0 + 2LL * w;
-            long long rem = (m.nsamp - us) * 4;
-            const int nb = rem >= 8 ? 8 : (rem > 0 ? (int)rem : 0);
-            cp_async8(reinterpret_cast<float*>(dst) + (w / 80) * kHopWordsF32 + 2 * (w % 80),
-                      nb ? src + us : src, nb);
-        }
+    constexpr int kPerChunk = F32 ? 4 : 8;             // samples per 16 bytes
+    constexpr int kChunksPerHop = kHop / kPerChunk;    // 40 / 20
+    constexpr int kChunks = kHopRows * kChunksPerHop;
+    constexpr int kBytes = F32 ? 4 : 2;
+    constexpr int kRowWords = F32 ? kHopWordsF32 : kHopWordsI16;
+    const char* src = reinterpret_cast<const char*>(p.samples) + m.sbase * kBytes;
+    for (int c = hth; c < kChunks; c += kHelperThreads) {
+        const long long us = t0 + (long long)c * kPerChunk;
+        const long long rem = (m.nsamp - us) * kBytes;
+        const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+        cp_async16(dst + (c / kChunksPerHop) * kRowWords + (c % kChunksPerHop) * 4,
+                   nb ? src + us * kBytes : src, nb);
     }
 }
 
@@ -403,8 +400,9 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
             if (i >= 2) bar_sync(kBarOutEmpty + s, kPipeThreads);
             {
                 float* ot = outt + s * (kTile * kOutStride) + lane * kOutStride;
+                const float half_mag = 0.5f * meta[i & 3].mag;
                 auto loadY = [&](int k1, int n2) { return exch[(k1 * 10 + n2) * kTile + lane]; };
-                auto emit = [&](int k, double p4) { ot[k] = (float)p4; };
+                auto emit = [&](int k, double p4) { ot[k] = log_mag((float)p4, half_mag); };
                 fft200_pass2(r, loadY, tabP, emit);
             }
             bar_arrive(kBarOutFull + s, kPipeThreads);
@@ -485,7 +483,6 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                 acc_nfr = m.nfr;
             }
             const float* ot = outt + (i & 1) * (kTile * kOutStride);
-            const float half_mag = 0.5f * m.mag;
 #pragma unroll 2
             for (int ff = 0; ff < 8; ++ff) {
                 const int f = hw * 8 + ff;
@@ -495,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                 for (int s = 0; s < 7; ++s) {
                     const int k = lane + 32 * s;
                     if (k < kBins) {
-                        const float y = log_mag(ot[f * kOutStride + k], half_mag);
+                        const float y = ot[f * kOutStride + k];
                         orow[k] = y;
                         if (want_stats) {
                             const double yd = (double)y;
@@ -522,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                 if (t >= 3) bar_sync(kBarPcmEmpty + (t % 3), kPipeThreads);
                 const Meta& m = meta[t & 3];
                 uint32_t* dst = pcm + (t % 3) * kPcmWords;
-                const bool aligned = ((m.sbase * (F32 ? 4 : 2)) & (F32 ? 7 : 3)) == 0;
+                const bool aligned = (((reinterpret_cast<uintptr_t>(p.samples) + m.sbase * (F32 ? 4 : 2)) & 15) == 0);
                 if (!mix && aligned) issue_pcm_tile_async<F32>(p, m, dst, hth);
                 else load_pcm_tile<F32>(p, m, dst, hth);
             }

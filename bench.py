@@ -439,7 +439,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
-            "gpu_launches": 7 * args.steps,
+            "gpu_launches": 8 * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line))
