@@ -16,9 +16,10 @@ ROW_OK, ROW_INFEASIBLE, ROW_NOT_ENOUGH_TIME, ROW_BAD_LENGTH = 0, 1, 2, 3
 SPEC_FBANK, SPEC_ASRT, SPEC_FBANK_RAW = 0, 1, 2
 DTYPE_I16, DTYPE_F32 = 0, 1
 LABELS_BY_LENGTH, LABELS_DROP_ZEROS = 0, 1
-PHASE_ALL = 0x7fffffff
+PHASE_ALL = 0xffff
 PHASE_SPEC_SETUP, PHASE_SPEC_MAIN, PHASE_SPEC_NORMALIZE = 1, 2, 4
 PHASE_CTC_PREP, PHASE_CTC_ROWS, PHASE_CTC_LATTICE, PHASE_CTC_GRAD, PHASE_CTC_COLLAPSE = 1, 2, 4, 8, 16
+PHASE_CTC_FUSED = 32
 
 # every symbol include/asrk.h declares: (restype, argtypes)
 _vp, _i, _ll, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t

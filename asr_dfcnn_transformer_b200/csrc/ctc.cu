@@ -68,7 +68,16 @@ struct Params {
     double* coff;        // [B][T]        alpha offsets
     double* logp;        // [B]
     int Ls;              // label_stride
+    int fused;           // 1: utterances with a small lattice are done by fused_small_kernel
 };
+
+// Utterances whose lattice fits one warp (L <= 31 labels -> 32 state pairs) and whose
+// per-frame scalars + gathered log-probabilities + alpha + beta fit the shared-memory
+// budget take the fused CTA-per-utterance kernel.
+constexpr int kSmallSmemFloats = 16 * 1024;   // 64 KB per CTA
+__host__ __device__ __forceinline__ bool small_lattice(int L, int T) {
+    return L <= 31 && (long long)T * (5 * L + 6) <= kSmallSmemFloats;
+}
 
 struct WsLayout {
     size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, beta, coff, logp, total;
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_kernel(Params p) {
     int tl = p.input_len[b];
     if (tl > p.T) tl = p.T;
     if (t >= tl) return;
+    if (WANT_LSE && p.fused && small_lattice(p.eff_len[b], tl)) return;   // fused_small_kernel
     const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
     float m, s = 0.f;
     int am;
@@ -324,22 +334,25 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     return warp_max(r);
 }
 
-// Utterances whose lattice fits one warp (L <= 31 labels -> 32 state pairs) and whose
-// gathered log-probabilities fit the shared-memory budget take the warp-level kernel.
-constexpr int kSmallSmemFloats = 16 * 1024;   // 64 KB of lpl per CTA
-__host__ __device__ __forceinline__ bool small_lattice(int L, int T) {
-    return L <= 31 && (long long)T * (L + 1) <= kSmallSmemFloats;
-}
-
-// Warp-per-direction lattice: warp 0 runs alpha, warp 1 runs beta AT THE SAME TIME
-// (they only meet in the occupancies), lane i owns one state pair, the neighbour
-// value moves by one warp shuffle per step, and the gathered log-probabilities of
-// the whole utterance sit in shared memory.  No block barrier inside the recursion.
-// A final pass over all (t,u) by the whole CTA turns alpha + beta - log p into
-// occupancies.
-__global__ void __launch_bounds__(128) lattice_small_kernel(Params p) {
-    extern __shared__ float slp[];             // [T][L+1]
-    __shared__ double s_fin[2];
+// ---------------------------------------------------------------------------
+// fused CTA-per-utterance kernel (small lattices: the AISHELL-shaped case)
+// ---------------------------------------------------------------------------
+// One CTA owns one utterance from the first read of its logits to the last write of
+// its gradient:
+//   A  every warp streams rows (one 5.7 KB row per warp, held in registers):
+//      max / first arg-max / log-sum-exp, and the few log-probabilities the lattice
+//      needs go to shared memory;
+//   B  warp 0 runs alpha and warp 1 runs beta AT THE SAME TIME (lane = state pair,
+//      one shuffle per step, no block barrier inside the recursion) while warp 2
+//      collapses the arg-max path into the greedy decode;
+//   C  every warp streams the rows again (L2 hits: the CTA read them microseconds
+//      ago) and writes softmax minus occupancy once, 16 bytes per lane.
+// The logits cross HBM once in and the gradient once out; alpha, beta and the
+// gathered log-probabilities never leave shared memory.
+template <int NV4>
+__global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
+    extern __shared__ float sm[];
+    __shared__ double s_fin;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -349,19 +362,46 @@ __global__ void __launch_bounds__(128) lattice_small_kernel(Params p) {
     const double ninf = (double)kNegInf;
     if (status == ASRK_ROW_BAD_LENGTH) {
         if (tid == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
+        if (p.tokens && tid == 0) { p.token_len[b] = 0; if (p.neg_sum_logits) p.neg_sum_logits[b] = 0.f; }
+        if (p.grad) {   // keep the gradient defined: zeros
+            for (int t = warp; t < p.T; t += kRowWarps) {
+                float4* g4 = reinterpret_cast<float4*>(p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b);
+                for (int i = lane; i < (p.V >> 2); i += 32) stg_stream(g4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        }
         return;
     }
-    if (!small_lattice(L, T)) return;          // handled by lattice_kernel
-    const int S = p.Ls + 1;
-    const int U = 2 * p.Ls + 1;
-    const int W = L + 1;                        // shared row width
-    const float* lpl = p.lpl + (size_t)b * p.T * S;
-    float* alpha = p.occ + (size_t)b * p.T * U;
-    float* beta = p.beta + (size_t)b * p.T * U;
+    if (!small_lattice(L, T)) return;          // generic path
+    const int W = L + 1;                        // row width of the gathered log-probs
+    const int Ub = 2 * L + 1;                   // lattice states
+    float* slse = sm;                           // [T]
+    float* smax = slse + T;                     // [T]
+    int* samax = reinterpret_cast<int*>(smax + T);   // [T]
+    float* slp = smax + 2 * T;                  // [T][W]
+    float* sal = slp + T * W;                   // [T][Ub]
+    float* sbe = sal + T * Ub;                  // [T][Ub]
     const int* eff = p.eff_labels + (size_t)b * p.Ls;
-    for (int idx = tid; idx < T * W; idx += blockDim.x) slp[idx] = lpl[(size_t)(idx / W) * S + (idx % W)];
+    const int V4 = p.V >> 2;
+
+    // ---- A: row statistics + gather -----------------------------------------
+    for (int t = warp; t < T; t += kRowWarps) {
+        const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
+        RowRegs<NV4> r;
+        load_row(x, V4, lane, r);
+        float m;
+        int am;
+        row_argmax(r, lane, m, am);
+        const float ssum = row_sumexp(r, m);
+        const float lse = m + __logf(ssum);
+        if (lane == 0) { slse[t] = lse; smax[t] = m; samax[t] = am; }
+        for (int j = lane; j < W; j += 32) {
+            const int c = (j == 0) ? p.blank : eff[j - 1];
+            slp[t * W + j] = x[c] - lse;
+        }
+    }
     __syncthreads();
 
+    // ---- B: alpha || beta || greedy collapse ----------------------------------
     const int i = lane;
     const int lab_i = (i < L) ? eff[i] : -1;
     const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
@@ -375,8 +415,8 @@ __global__ void __launch_bounds__(128) lattice_small_kernel(Params p) {
             a_b = (double)slp[0];
             if (L >= 1) a_l = (double)slp[1];
         }
-        if (has_blank) alpha[2 * i] = (float)a_b;
-        if (has_lab) alpha[2 * i + 1] = (float)a_l;
+        if (has_blank) sal[2 * i] = (float)a_b;
+        if (has_lab) sal[2 * i + 1] = (float)a_l;
         for (int t = 1; t < T; ++t) {
             const double lb = (double)slp[t * W];
             const double ll = has_lab ? (double)slp[t * W + 1 + i] : ninf;
@@ -386,56 +426,131 @@ __global__ void __launch_bounds__(128) lattice_small_kernel(Params p) {
             const double nl = ll + lse3(a_l, a_b, skip ? p1 : ninf);
             a_b = has_blank ? nb : ninf;
             a_l = has_lab ? nl : ninf;
-            float* o = alpha + (size_t)t * U;
+            float* o = sal + t * Ub;
             if (has_blank) o[2 * i] = (float)a_b;
             if (has_lab) o[2 * i + 1] = (float)a_l;
         }
         // log p = LSE(alpha_{T-1}(2L), alpha_{T-1}(2L-1))
         const double fb = __shfl_sync(0xffffffffu, a_b, L);
         const double fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : ninf;
-        if (lane == 0) s_fin[0] = lse2(fb, fl);
-    } else if (warp == 1 && p.grad != nullptr) {
-        // beta: pair (label 2i-1, blank 2i); excludes y_t
-        const bool has_lab = (i >= 1 && i <= L);
-        double b_l = ninf, b_b = ninf;
-        if (i == L) {
-            b_b = 0.0;
-            if (L >= 1) b_l = 0.0;
+        if (lane == 0) s_fin = lse2(fb, fl);
+    } else if (warp == 1) {
+        if (p.grad != nullptr) {
+            // beta: pair (label 2i-1, blank 2i); excludes y_t
+            const bool has_lab = (i >= 1 && i <= L);
+            double b_l = ninf, b_b = ninf;
+            if (i == L) {
+                b_b = 0.0;
+                if (L >= 1) b_l = 0.0;
+            }
+            {
+                float* o = sbe + (T - 1) * Ub;
+                if (has_blank) o[2 * i] = (float)b_b;
+                if (has_lab) o[2 * i - 1] = (float)b_l;
+            }
+            for (int t = T - 2; t >= 0; --t) {
+                const double lb = (double)slp[(t + 1) * W];
+                const double ll = has_lab ? (double)slp[(t + 1) * W + i] : ninf;
+                const double e_b = b_b + lb;
+                const double e_l = b_l + ll;
+                double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+                if (i == 31) n1 = ninf;
+                const double nbb = lse2(e_b, n1);
+                const double nbl = lse3(e_l, e_b, skip ? n1 : ninf);
+                b_b = has_blank ? nbb : ninf;
+                b_l = has_lab ? nbl : ninf;
+                float* o = sbe + t * Ub;
+                if (has_blank) o[2 * i] = (float)b_b;
+                if (has_lab) o[2 * i - 1] = (float)b_l;
+            }
         }
-        {
-            float* o = beta + (size_t)(T - 1) * U;
-            if (has_blank) o[2 * i] = (float)b_b;
-            if (has_lab) o[2 * i - 1] = (float)b_l;
+    } else if (warp == 2 && p.tokens != nullptr) {
+        // greedy decode of this utterance: ballot + prefix count over 32-frame chunks
+        int* out = p.tokens + (size_t)b * p.token_stride;
+        int count = 0, carry_prev = -1;
+        double nsl = 0.0;
+        for (int base = 0; base < T; base += 32) {
+            const int t = base + lane;
+            const bool in = t < T;
+            const int c = in ? samax[t] : -1;
+            int prev = __shfl_up_sync(0xffffffffu, c, 1);
+            if (lane == 0) prev = carry_prev;
+            const bool keep = in && c != p.blank && !(p.merge_repeated && c == prev);
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            const int rank = __popc(mask & ((1u << lane) - 1u));
+            if (keep && count + rank < p.token_stride) out[count + rank] = c;
+            count += __popc(mask);
+            carry_prev = __shfl_sync(0xffffffffu, c, 31);
+            if (in) nsl += (double)smax[t];
         }
-        for (int t = T - 2; t >= 0; --t) {
-            const double lb = (double)slp[(t + 1) * W];
-            const double ll = has_lab ? (double)slp[(t + 1) * W + i] : ninf;
-            const double e_b = b_b + lb;
-            const double e_l = b_l + ll;
-            double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
-            if (i == 31) n1 = ninf;
-            const double nbb = lse2(e_b, n1);
-            const double nbl = lse3(e_l, e_b, skip ? n1 : ninf);
-            b_b = has_blank ? nbb : ninf;
-            b_l = has_lab ? nbl : ninf;
-            float* o = beta + (size_t)t * U;
-            if (has_blank) o[2 * i] = (float)b_b;
-            if (has_lab) o[2 * i - 1] = (float)b_l;
+        nsl = warp_sum(nsl);
+        if (lane == 0) {
+            p.token_len[b] = count < p.token_stride ? count : p.token_stride;
+            if (p.neg_sum_logits) p.neg_sum_logits[b] = (float)(-nsl);
         }
     }
     __syncthreads();
-    const double logp = s_fin[0];
+    const double logp = s_fin;
     if (tid == 0) {
         p.logp[b] = logp;
         p.loss[b] = (float)(-logp);
         if (logp == ninf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
     }
-    if (p.grad == nullptr || logp == ninf) return;
-    // occupancies: exp(alpha + beta - log p), every (t,u) independently
-    const int Ub = 2 * L + 1;
-    for (int idx = tid; idx < T * Ub; idx += blockDim.x) {
-        const size_t off = (size_t)(idx / Ub) * U + (idx % Ub);
-        alpha[off] = __expf((float)((double)alpha[off] + (double)beta[off] - logp));
+    if (p.grad == nullptr) return;
+
+    // ---- C: gradient rows -----------------------------------------------------
+    const bool fix = (logp != ninf) && (status == ASRK_ROW_OK);   // TF: no valid path -> dy = y
+    const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
+    const int* nxt = p.chain_next + (size_t)b * p.Ls;
+    const int* fst = p.chain_first + (size_t)b * p.Ls;
+    for (int t = warp; t < p.T; t += kRowWarps) {
+        float* g = p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b;
+        float4* g4 = reinterpret_cast<float4*>(g);
+        if (t >= T) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = lane; k < V4; k += 32) stg_stream(g4 + k, z);
+            continue;
+        }
+        const float4* x4 = reinterpret_cast<const float4*>(p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b);
+        const float lse = slse[t];
+        float4 v[NV4];
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < V4) v[k] = ldg_stream(x4 + idx);
+        }
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < V4) {
+                float4 y;
+                y.x = __expf(v[k].x - lse) * scale;
+                y.y = __expf(v[k].y - lse) * scale;
+                y.z = __expf(v[k].z - lse) * scale;
+                y.w = __expf(v[k].w - lse) * scale;
+                stg_stream(g4 + idx, y);
+            }
+        }
+        if (!fix) continue;
+        __syncwarp();
+        const float* al = sal + t * Ub;
+        const float* be = sbe + t * Ub;
+        float ob = 0.f;
+        for (int j = lane; j <= L; j += 32)
+            ob += __expf((float)((double)al[2 * j] + (double)be[2 * j] - logp));
+        float extra = 0.f;
+        for (int j = lane; j < L; j += 32) {
+            const int c = eff[j];
+            if (c == p.blank) extra += __expf((float)((double)al[2 * j + 1] + (double)be[2 * j + 1] - logp));
+            if (fst[j] && c != p.blank) {
+                float o = 0.f;
+                for (int k = j; k >= 0; k = nxt[k])
+                    o += __expf((float)((double)al[2 * k + 1] + (double)be[2 * k + 1] - logp));
+                g[c] = (__expf(slp[t * W + 1 + j]) - o) * scale;
+            }
+        }
+        ob = warp_sum(ob + extra);
+        if (lane == 0) g[p.blank] = (__expf(slp[t * W]) - ob) * scale;
     }
 }
 
@@ -461,7 +576,7 @@ __global__ void lattice_kernel(Params p) {
         if (i == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
         return;
     }
-    if (small_lattice(L, T)) return;          // handled by lattice_small_kernel
+    if (p.fused && small_lattice(L, T)) return;   // handled by fused_small_kernel
     const int S = p.Ls + 1;
     const int U = 2 * p.Ls + 1;
     const float* lpl = p.lpl + (size_t)b * p.T * S;
@@ -573,6 +688,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
     const int tl = p.input_len[b];
     const int status = p.row_status[b];
     const int V = p.V;
+    if (p.fused && (status == ASRK_ROW_BAD_LENGTH || small_lattice(p.eff_len[b], tl))) return;
     if (t >= tl || status == ASRK_ROW_BAD_LENGTH) {
         if constexpr (NV4 > 0) {
             float4* g4 = reinterpret_cast<float4*>(g);
@@ -653,6 +769,7 @@ __global__ void __launch_bounds__(128) collapse_kernel(Params p) {
     int tl = p.input_len[b];
     if (tl < 0) tl = 0;
     if (tl > p.T) tl = p.T;
+    if (p.fused && (p.row_status[b] == ASRK_ROW_BAD_LENGTH || small_lattice(p.eff_len[b], tl))) return;
     const int* am = p.argmax + (size_t)b * p.T;
     const float* mx = p.rowmax + (size_t)b * p.T;
     int* out = p.tokens + (size_t)b * p.token_stride;
@@ -703,6 +820,23 @@ static void launch_rows(const Params& p, int nv4, cudaStream_t stream) {
         case 12: rows_kernel<12, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
         case 16: rows_kernel<16, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
         default: rows_kernel<0, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+    }
+}
+
+static void launch_fused(const Params& p, int nv4, cudaStream_t stream) {
+    const size_t smem = sizeof(float) * kSmallSmemFloats;
+    switch (nv4) {
+#define ASRK_FUSED_CASE(N)                                                                              \
+    case N:                                                                                             \
+        cudaFuncSetAttribute(fused_small_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        fused_small_kernel<N><<<p.B, kRowWarps * 32, smem, stream>>>(p);                                 \
+        break;
+        ASRK_FUSED_CASE(4)
+        ASRK_FUSED_CASE(8)
+        ASRK_FUSED_CASE(12)
+        ASRK_FUSED_CASE(16)
+#undef ASRK_FUSED_CASE
+        default: break;
     }
 }
 
@@ -787,19 +921,18 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     bind_workspace(p, workspace, l);
 
     const int nv4 = pick_nv4(p, logits, stride_t, stride_b, grad, gstride_t, gstride_b);
+    p.fused = (nv4 > 0) ? 1 : 0;
     if (phases & ASRK_PHASE_CTC_PREP) {
         const int pt = ((label_stride > 0 ? label_stride : 1) + 31) / 32 * 32;
         prep_kernel<<<B, pt, sizeof(int) * (Ls + 40), stream>>>(p);
     }
+    // utterances with a small lattice: one fused CTA each; the row-parallel kernels
+    // below skip them and handle the long ones
+    if (p.fused && (phases & ASRK_PHASE_CTC_FUSED)) launch_fused(p, nv4, stream);
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
-    if (phases & ASRK_PHASE_CTC_LATTICE) {
-        // both kernels see every utterance; each takes the ones that fit it
-        cudaFuncSetAttribute(lattice_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(float) * kSmallSmemFloats));
-        lattice_small_kernel<<<B, 128, sizeof(float) * kSmallSmemFloats, stream>>>(p);
+    if (phases & ASRK_PHASE_CTC_LATTICE)
         lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p);
-    }
     if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
     if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
     return launch_status();

@@ -34,7 +34,7 @@ constexpr int kFftWarps = 10;
 constexpr int kHelperWarps = 4;
 constexpr int kFftThreads = kFftWarps * 32;          // 320
 constexpr int kHelperThreads = kHelperWarps * 32;    // 128
-constexpr int kThreads = 16 * 32;                    // warps 12,13 are placeholders (see roles)
+constexpr int kThreads = kFftThreads + kHelperThreads;
 constexpr int kTile = 32;                            // frames per tile (= lanes)
 constexpr int kHop = 160, kFrameLen = 400, kBins = 200;
 constexpr int kHopRows = 34;                         // 31*160+400 = 5360 samples -> 34 hops
@@ -361,8 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     const cplx* tabT = reinterpret_cast<const cplx*>(tab + 400);
     const cplx* tabP = reinterpret_cast<const cplx*>(tab + 800);
 
-    // warp roles: 0..9 FFT; 10,11,14,15 helpers (two on each of the sub-partitions
-    // that only hold two FFT warps); 12,13 only pad the warp numbering
+    // warp roles: 0..9 FFT (one residue of the 20 x 10 split each); 10..13 helpers
     if (warp < kFftWarps) {
         // ------------------------------ FFT warps ------------------------------
         const int r = warp;
@@ -409,9 +408,9 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
             bar_sync(kBarExchB, kFftThreads);
             st = (st == 2) ? 0 : st + 1;
         }
-    } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
+    } else {
         // ----------------------------- helper warps ----------------------------
-        const int hw = (warp < 12) ? warp - 10 : warp - 12;      // 0..3
+        const int hw = warp - kFftWarps;                          // 0..3
         const int hth = hw * 32 + lane;
         const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
         const bool mix = (p.noise != nullptr);
@@ -611,7 +610,9 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
     if (noise && !gain && !snr_db) return ASRK_E_BADARG;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return ASRK_E_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return ASRK_E_ALIGN;
-    const int grid = sm_count() > 256 ? 256 : sm_count();
+    int grid = sm_count() > 256 ? 256 : sm_count();
+    const int cta_limit = (phases >> 16) & 0x7fff;
+    if (cta_limit > 0 && cta_limit < grid) grid = cta_limit;
     const WsLayout l = ws_layout(batch, total_frames, 256);
     if (workspace_bytes < l.total) return ASRK_E_WORKSPACE;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
@@ -659,7 +660,7 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         spectrogram_kernel<false><<<grid, kThreads, smem, stream>>>(p);
     }
     if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE))
-        normalize_kernel<<<grid * 4, 256, 0, stream>>>(p);
+        normalize_kernel<<<sm_count() * 4, 256, 0, stream>>>(p);
     return launch_status();
 }
 

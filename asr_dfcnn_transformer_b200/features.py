@@ -102,7 +102,7 @@ def pack_host(signals, fs=16000, mode="fbank", noises=None, pin=True):
 
 def spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
                        mode="fbank", noise=None, gain=None, snr_db=None, out=None,
-                       out_row_offsets=None, stream=None, phases=_lib.PHASE_ALL):
+                       out_row_offsets=None, stream=None, phases=_lib.PHASE_ALL, cta_limit=0):
     """Launch the kernels on device tensors that are already packed.
 
     samples: int16 / float32 [total]; sample_offsets, sample_counts: int64 [B];
@@ -125,7 +125,7 @@ def spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, ba
                                        _lib.ptr(snr_db), _lib.ptr(sample_offsets), _lib.ptr(sample_counts),
                                        _lib.ptr(frame_offsets), _lib.ptr(out_row_offsets), batch,
                                        total_frames, MODES[mode], _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                                       _lib.stream_ptr(stream), int(phases))
+                                       _lib.stream_ptr(stream), int(phases) | (int(cta_limit) << 16))
     _lib.check(st, "asrk_spectrogram_run")
     return out
 

@@ -184,7 +184,12 @@ int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long lon
 #define ASRK_PHASE_CTC_LATTICE 4     /* alpha / beta recursion, loss               */
 #define ASRK_PHASE_CTC_GRAD 8        /* gradient rows                              */
 #define ASRK_PHASE_CTC_COLLAPSE 16   /* greedy collapse (when tokens != NULL)      */
-#define ASRK_PHASE_ALL 0x7fffffff
+#define ASRK_PHASE_CTC_FUSED 32      /* fused CTA-per-utterance kernel (small lattices) */
+#define ASRK_PHASE_ALL 0xffff
+/* asrk_spectrogram_run_phases only: bits 16..30 of `phases` cap the number of CTAs
+ * of the persistent spectrogram kernel (0 = one per SM), so that a caller running
+ * the CTC kernels on a second stream can leave SMs free for them. */
+#define ASRK_SPEC_CTA_LIMIT(n) ((int)(n) << 16)
 
 int asrk_spectrogram_run_phases(const void* samples, int sample_dtype, const float* noise,
                                 const float* gain, const int* snr_db,
