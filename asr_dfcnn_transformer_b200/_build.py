@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libasrk.so")
 SOURCES = ["asrk_api.cu", "spectrogram.cu", "noise.cu", "ctc.cu"]
 HEADERS = ["asrk_common.cuh", "asrk_fft.cuh", os.path.join("..", "..", "include", "asrk.h")]
-NVCC_FLAGS = [
+NVCC_FLAGS = (os.environ.get("ASRK_EXTRA_NVCC", "").split()) + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -8,26 +8,29 @@
 //     amplified by the z-score) is not reachable with fp32 butterflies on
 //     high-dynamic-range audio, so the 400-point transform runs in fp64 -- B200
 //     has a half-rate fp64 pipe (64 lanes/SM/clk), which is the bound of this
-//     kernel; everything after |X|^2 (sqrt, log, statistics, z-score) is fp32.
-//   * ONE persistent kernel, one CTA per SM, every warp an independent pipeline
-//     (no block barrier inside the transform).  A warp owns a tile of 3
-//     consecutive frames: LANE = (frame slot g, role r), ten lanes per frame.  The
-//     400-point real DFT is a 200-point complex DFT (20 x 10 Cooley-Tukey, both
-//     factors twiddle-free prime-factor codelets) + the real-input split:
-//       pass 1  lane r : DFT20 of the residue class r, times W200^(r k1)
-//       -- exchange through the warp's private shared buffer (__syncwarp only) --
-//       pass 2  lane j : DFT10 of rows j and 20-j, split, log(|X|+1) -> out tile
-//     then the 3 x 800-byte rows leave with 16-byte stores while the per-bin sums
-//     for the z-score are accumulated (fp32, shifted by the first row so that no
-//     cancellation happens).  The PCM of the next tile arrives with cp.async
-//     (16-byte LDGSTS, zero-filled past the end of the utterance) while the
-//     current one is transformed.
-//   * work is handed out in blocks of (warps x 3 tiles) consecutive frames of one
-//     utterance through an atomic counter, in utterance order, so utterances
-//     complete progressively; the per-block column sums are combined in a fixed
-//     order (fp64, no float atomics) and the CTA that retires the LAST block of an
-//     utterance z-scores it in place while its rows are still in L2 -- there is no
-//     second kernel and no second trip to HBM.
+//     kernel (register-resident codelets reach > 90 % of it, tools/ubench);
+//     everything after |X|^2 (sqrt, log, z-score) is fp32.
+//   * ONE persistent kernel, one CTA per SM.  A tile is 32 consecutive frames of
+//     one utterance: LANE = FRAME, WARP = ROLE.  The 400-point real DFT is a
+//     200-point complex DFT (20 x 10 Cooley-Tukey, both factors twiddle-free
+//     prime-factor codelets) + the real-input split; ten "FFT warps" each own one
+//     of the ten residues, so window values and twiddles are warp-uniform and come
+//     from the constant bank (no load/store-unit traffic), the PCM tile is staged
+//     in padded shared memory by cp.async, and the only exchange between the two
+//     passes is one conflict-free 100 KB fp64 buffer.
+//   * four "helper warps" run concurrently: they claim tiles from an atomic counter
+//     (in utterance order), stage the PCM two tiles ahead (mixing in K*noise on the
+//     fly in noise mode), and move finished 32 x 200 log-magnitude tiles to global
+//     memory with coalesced stores.  FULL/EMPTY named barriers decouple the two
+//     groups by up to a tile.
+//   * z-score: the helpers accumulate the per-bin column sums of every tile while
+//     they copy it out (fp32, shifted by the tile's first row so that nothing
+//     cancels), combine them per tile in fp64 in a fixed order (reproducible, no float
+//     atomics), and the CTA that retires the LAST tile of an utterance turns the tile
+//     partials into mean and 1/std.  A second, purely streaming kernel with the whole
+//     chip's memory parallelism normalises in place (the rows are largely still in
+//     L2).  [An in-kernel z-score by the retiring CTA was measured: one CTA's 448
+//     threads cannot keep enough L2 requests in flight -- 40 us per utterance.]
 #include <math.h>
 
 #include "asrk_common.cuh"
@@ -36,35 +39,43 @@
 namespace asrk {
 namespace spec {
 
+constexpr int kFftWarps = 10;
+constexpr int kHelperWarps = 4;
+constexpr int kFftThreads = kFftWarps * 32;          // 320
+constexpr int kHelperThreads = kHelperWarps * 32;    // 128
+constexpr int kThreads = kFftThreads + kHelperThreads;
+constexpr int kTile = 32;                            // frames per tile (= lanes)
 constexpr int kHop = 160, kFrameLen = 400, kBins = 200;
-constexpr int kTileFrames = 3;                         // frames per warp tile
-constexpr int kTilesPerWarp = 3;                       // tiles per warp in a full block
-constexpr int kTileSamples = (kTileFrames - 1) * kHop + kFrameLen;   // 720
-constexpr int kRowStride = 11;                         // exchange: cplx per k1 row   } conflict-free
-constexpr int kSlotStride = 222;                       // exchange: cplx per frame    } (tools: bank model)
-constexpr int kExchCplx = kTileFrames * kSlotStride;   // 666 cplx = 10656 B per warp
-constexpr int kOutStride = 204;                        // floats per row of the out tile (aliases the exchange)
-constexpr int kTabDoubles = 1200;                      // window[400] | tw[k1][r] | P[k]
-constexpr int kMaxBatch = 2047;                        // utterances per launch (block prefix in smem)
-// int16 staging: 26 pad words after every hop (80 words of sample pairs), so that the
-// three frame slots of a warp read banks 10 g + r (conflict-free); physical word of
-// logical word W is W + 26 (W / 80)
-constexpr int kHopPadWords = 26;
+constexpr int kHopRows = 34;                         // 31*160+400 = 5360 samples -> 34 hops
+constexpr int kOutStride = 201;                      // padded row of the out tile
+// hop rows stay 16-byte aligned (for 16-byte async copies) and are padded by 16
+// bytes: lane f reads word 84 f + c -> 8 distinct banks, a 4-way conflict on the
+// 20 sample loads of a thread per tile (its only other shared accesses are the
+// conflict-free exchange), instead of the 16-way conflict of the unpadded layout.
+constexpr int kHopWordsI16 = 84;                     // 80 words of int16 pairs + 4 pad
+constexpr int kHopWordsF32 = 164;                    // 160 words + 4 pad
+constexpr int kTabDoubles = 1200;                    // window[400] | tw[r][k1] | P[k]
+constexpr int kMaxBatch = 2047;                      // utterances per launch (tile prefix in smem)
+constexpr int kRing = 8;                             // tile metadata ring
 
-__device__ const double g_tables[kTabDoubles] = {
+__device__ const double g_tab[kTabDoubles] = {
 #include "asrk_tables.inc"
 };
 
-enum : int { kInI16 = 0, kInF32 = 1, kInMix = 2 };
-
-template <int IN>
-struct InTraits;
-template <>
-struct InTraits<kInI16> { static constexpr int kPcmBytes = (kTileSamples / 2 + 4 * 26) * 4, kWarps = 16; };
-template <>
-struct InTraits<kInF32> { static constexpr int kPcmBytes = kTileSamples * 4, kWarps = 15; };
-template <>
-struct InTraits<kInMix> { static constexpr int kPcmBytes = kTileSamples * 8, kWarps = 12; };
+struct Meta {               // one tile, written by helper thread 0
+    int valid;
+    int b;
+    int f0;
+    int nf;
+    int ntiles_b;            // tiles of utterance b
+    int tile;                // global tile index (row of the partial sums)
+    long long sbase;         // first sample of the utterance in the ragged buffer
+    long long nsamp;         // samples of the utterance
+    long long row0;          // output row of frame 0 of the utterance
+    long long nfr;           // frames of the utterance
+    float half_mag;
+    float gain;
+};
 
 struct Params {
     const void* samples;
@@ -78,20 +89,24 @@ struct Params {
     int mode;
     float* out;
     // workspace
-    int* counters;           // [0] next block, [1 + b] retired blocks of utterance b (zeroed per launch)
+    int* counters;           // [0] next tile, [1 + b] retired tiles of utterance b (zeroed per launch)
+    double2* partials;       // [tiles][200]: per-tile column sums (sum y, sum y^2)
+    float* stats;            // [B][3][200]: mean (hi, lo), 1/std
 };
 
 struct WsLayout {
-    size_t counters, gains, total;
+    size_t counters, gains, stats, partials, total;
 };
-
-__host__ __device__ constexpr int frames_per_block(int warps) { return warps * kTilesPerWarp * kTileFrames; }
 
 static WsLayout ws_layout(int batch, long long total_frames) {
     WsLayout l;
     size_t o = 0;
     l.counters = o;  o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
     l.gains = o;     o = align_up(o + sizeof(float) * (size_t)batch, 256);
+    l.stats = o;     o = align_up(o + sizeof(float) * 3 * kBins * (size_t)batch, 256);
+    l.partials = o;
+    const size_t max_tiles = (size_t)(total_frames / kTile) + (size_t)batch + 1;
+    o = align_up(o + sizeof(double2) * kBins * max_tiles, 256);
     l.total = o;
     return l;
 }
@@ -121,135 +136,181 @@ __device__ __forceinline__ float log_mag(float p4, float half_mag) {
     return (e + l2) * 0.69314718056f;
 }
 
-struct Utt {               // per-block, warp-uniform
-    int b;
-    int nblk;              // blocks of the utterance
-    int f0;                // first frame of the block (utterance-local)
-    int nt;                // tiles in the block
-    long long nfr;         // frames of the utterance
-    long long sbase;       // first sample in the ragged buffer
-    long long nsamp;
-    long long row0;        // output row of frame 0 of the utterance
-    float half_mag;
-    float gain;
-    bool aligned;
-};
-
-// Start the copy of the PCM of one tile (frames f .. f+2) into the warp's staging
-// buffer.  Aligned utterances: 16-byte LDGSTS, zero-filled past the end; returns
-// with the copies in flight (one commit group).  Others: plain loads.
-template <int IN>
-__device__ __forceinline__ void stage_tile(const Params& p, const Utt& u, int f, unsigned char* pcm, int lane) {
-    const long long s0 = (long long)f * kHop;
-    constexpr int kBytes = (IN == kInI16) ? 2 : 4;
-    constexpr int kPerChunk = 16 / kBytes;
-    constexpr int kChunks = kTileSamples / kPerChunk;            // 90 / 180
-    if (u.aligned) {
-        const char* src = reinterpret_cast<const char*>(p.samples) + u.sbase * kBytes;
-        if (IN == kInI16) {
-            // 8-byte LDGSTS (4 samples) into the padded hop rows
+// Synchronous staging of one PCM tile (unaligned utterances, and the noise mix:
+// fl32(signal + fl32(K * noise)) is formed on the way in).
+template <bool F32>
+__device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, uint32_t* dst, int hth) {
+    const long long t0 = (long long)m.f0 * kHop;   // utterance-local first sample of the tile
+    if (!F32) {
+        const short* src = reinterpret_cast<const short*>(p.samples) + m.sbase;
+        constexpr int kChunks = kHopRows * 20;   // 16-byte chunks of 8 samples
+        for (int c = hth; c < kChunks; c += kHelperThreads) {
+            const long long us = t0 + (long long)c * 8;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            const short* g = src + us;
+            if (us + 8 <= m.nsamp && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+                const int4 v = __ldg(reinterpret_cast<const int4*>(g));
+                w0 = (uint32_t)v.x; w1 = (uint32_t)v.y; w2 = (uint32_t)v.z; w3 = (uint32_t)v.w;
+            } else {
+                uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int c = lane; c < kTileSamples / 4; c += 32) {
-                const long long us = s0 + (long long)c * 4;
-                const long long rem = (u.nsamp - us) * 2;
-                const int nb = rem >= 8 ? 8 : (rem > 0 ? (int)rem : 0);
-                cp_async8(pcm + 4 * (2 * c + kHopPadWords * (c / 40)), nb ? src + us * 2 : src, nb);
+                for (int e = 0; e < 8; ++e) {
+                    if (us + e < m.nsamp) {
+                        const uint32_t s = (uint16_t)g[e];
+                        w[e >> 1] |= s << (16 * (e & 1));
+                    }
+                }
+                w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
             }
-        } else {
-#pragma unroll
-            for (int c = lane; c < kChunks; c += 32) {
-                const long long us = s0 + (long long)c * kPerChunk;
-                const long long rem = (u.nsamp - us) * kBytes;
-                const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-                cp_async16(pcm + 16 * c, nb ? src + us * kBytes : src, nb);
-            }
-        }
-        if (IN == kInMix) {
-            const char* nz = reinterpret_cast<const char*>(p.noise) + u.sbase * 4;
-#pragma unroll
-            for (int c = lane; c < kChunks; c += 32) {
-                const long long us = s0 + (long long)c * 4;
-                const long long rem = (u.nsamp - us) * 4;
-                const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-                cp_async16(pcm + kTileSamples * 4 + 16 * c, nb ? nz + us * 4 : nz, nb);
-            }
+            uint32_t* d = dst + (c / 20) * kHopWordsI16 + (c % 20) * 4;
+            d[0] = w0; d[1] = w1; d[2] = w2; d[3] = w3;
         }
     } else {
-        if (IN == kInI16) {
-            const short* src = reinterpret_cast<const short*>(p.samples) + u.sbase;
-            short* d = reinterpret_cast<short*>(pcm);
-            for (int i = lane; i < kTileSamples; i += 32)
-                d[i + 2 * kHopPadWords * (i / kHop)] = (s0 + i < u.nsamp) ? src[s0 + i] : (short)0;
-        } else {
-            const float* src = reinterpret_cast<const float*>(p.samples) + u.sbase;
-            float* d = reinterpret_cast<float*>(pcm);
-            for (int i = lane; i < kTileSamples; i += 32) d[i] = (s0 + i < u.nsamp) ? src[s0 + i] : 0.f;
-            if (IN == kInMix) {
-                const float* nz = p.noise + u.sbase;
-                for (int i = lane; i < kTileSamples; i += 32)
-                    d[kTileSamples + i] = (s0 + i < u.nsamp) ? nz[s0 + i] : 0.f;
+        const float* src = reinterpret_cast<const float*>(p.samples) + m.sbase;
+        const float* nz = p.noise ? p.noise + m.sbase : nullptr;
+        const float K = m.gain;
+        constexpr int kChunks = kHopRows * 40;   // 16-byte chunks of 4 samples
+        for (int c = hth; c < kChunks; c += kHelperThreads) {
+            const long long us = t0 + (long long)c * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* g = src + us;
+            if (us + 4 <= m.nsamp && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) &&
+                (!nz || ((reinterpret_cast<uintptr_t>(nz + us) & 15) == 0))) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(g));
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                if (nz) {
+                    const float4 n4 = __ldg(reinterpret_cast<const float4*>(nz + us));
+                    // noise.py:108  (signal + K * noise).astype(float32): two roundings, no FMA
+                    v[0] = __fadd_rn(v[0], __fmul_rn(K, n4.x));
+                    v[1] = __fadd_rn(v[1], __fmul_rn(K, n4.y));
+                    v[2] = __fadd_rn(v[2], __fmul_rn(K, n4.z));
+                    v[3] = __fadd_rn(v[3], __fmul_rn(K, n4.w));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (us + e < m.nsamp) {
+                        float s = g[e];
+                        if (nz) s = __fadd_rn(s, __fmul_rn(K, nz[us + e]));
+                        v[e] = s;
+                    }
+                }
             }
+            float* d = reinterpret_cast<float*>(dst) + (c / 40) * kHopWordsF32 + (c % 40) * 4;
+            *reinterpret_cast<float2*>(d) = make_float2(v[0], v[1]);
+            *reinterpret_cast<float2*>(d + 2) = make_float2(v[2], v[3]);
         }
     }
-    cp_async_commit();
 }
 
-// Block -> utterance, frame range and the utterance's constants (thread 0 only).
-template <int IN, int kFB>
-__device__ void locate_block(const Params& p, const int* blk_off, int blk, Utt& u) {
+// Asynchronous staging of one PCM tile (no arithmetic on the way): 16-byte LDGSTS
+// copies into the padded hop rows, zero-filled past the end of the utterance.
+// Needs the utterance start to be 16-byte aligned.
+template <bool F32>
+__device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta& m, uint32_t* dst, int hth) {
+    const long long t0 = (long long)m.f0 * kHop;
+    constexpr int kPerChunk = F32 ? 4 : 8;             // samples per 16 bytes
+    constexpr int kChunksPerHop = kHop / kPerChunk;    // 40 / 20
+    constexpr int kChunks = kHopRows * kChunksPerHop;
+    constexpr int kBytes = F32 ? 4 : 2;
+    constexpr int kRowWords = F32 ? kHopWordsF32 : kHopWordsI16;
+    const char* src = reinterpret_cast<const char*>(p.samples) + m.sbase * kBytes;
+    for (int c = hth; c < kChunks; c += kHelperThreads) {
+        const long long us = t0 + (long long)c * kPerChunk;
+        const long long rem = (m.nsamp - us) * kBytes;
+        const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+        cp_async16(dst + (c / kChunksPerHop) * kRowWords + (c % kChunksPerHop) * 4,
+                   nb ? src + us * kBytes : src, nb);
+    }
+}
+
+// Tile -> utterance, frame range and the utterance's constants (helper thread 0).
+__device__ void fill_meta(const Params& p, const int* tile_off, int tile, Meta& m) {
     int lo = 0, hi = p.batch - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (blk_off[mid] <= blk) lo = mid; else hi = mid - 1;
+        if (tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
     }
     int b = lo;
-    while (blk >= blk_off[b + 1]) ++b;          // skip utterances without blocks
-    u.b = b;
-    u.nblk = blk_off[b + 1] - blk_off[b];
-    u.f0 = (blk - blk_off[b]) * kFB;
+    while (tile >= tile_off[b + 1]) ++b;          // skip utterances without tiles
+    m.valid = 1;
+    m.tile = tile;
+    m.b = b;
+    m.ntiles_b = tile_off[b + 1] - tile_off[b];
+    m.f0 = (tile - tile_off[b]) * kTile;
     const long long fo = p.frame_offsets[b];
-    u.nfr = p.frame_offsets[b + 1] - fo;
-    const long long rem = u.nfr - u.f0;
-    const int nfb = rem < kFB ? (int)rem : kFB;
-    u.nt = (nfb + kTileFrames - 1) / kTileFrames;
-    u.sbase = p.sample_offsets[b];
-    u.nsamp = p.sample_counts[b];
-    u.row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
-    u.half_mag = 0.5f * ((p.mode == ASRK_SPEC_ASRT) ? (1.0f / (float)u.nsamp) : 1.0f);
-    u.gain = (IN == kInMix && p.gain) ? p.gain[b] : 0.0f;
-    u.aligned = (((reinterpret_cast<uintptr_t>(p.samples) + u.sbase * (IN == kInI16 ? 2 : 4)) & 15) == 0) &&
-                (IN != kInMix || ((reinterpret_cast<uintptr_t>(p.noise) + u.sbase * 4) & 15) == 0);
+    m.nfr = p.frame_offsets[b + 1] - fo;
+    const long long rem = m.nfr - m.f0;
+    m.nf = rem < kTile ? (int)rem : kTile;
+    m.sbase = p.sample_offsets[b];
+    m.nsamp = p.sample_counts[b];
+    m.row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
+    m.half_mag = 0.5f * ((p.mode == ASRK_SPEC_ASRT) ? (1.0f / (float)m.nsamp) : 1.0f);
+    m.gain = (p.noise && p.gain) ? p.gain[b] : 0.0f;
 }
 
 // ---------------------------------------------------------------------------
-// the kernel
+// main kernel
 // ---------------------------------------------------------------------------
-template <int IN>
-__global__ void __launch_bounds__(InTraits<IN>::kWarps * 32, 1) spectrogram_kernel(Params p) {
-    constexpr int kWarps = InTraits<IN>::kWarps;
-    constexpr int kThreads = kWarps * 32;
-    constexpr int kPcmBytes = InTraits<IN>::kPcmBytes;
-    constexpr int kFB = frames_per_block(kWarps);
-    constexpr int kWarpBytes = kExchCplx * 16 + kPcmBytes;
+// Named barriers (id 0 is __syncthreads).  FULL/EMPTY pairs hand the PCM stages and
+// the two out tiles between the FFT warps and the helper warps so that neither side
+// waits for the other unless it is a whole tile behind.
+enum : int {
+    kBarHelpers = 1,      // helper warps only
+    kBarExchA = 2,        // FFT warps only: pass 1 stores -> pass 2 loads
+    kBarExchB = 3,        // FFT warps only: pass 2 loads -> next pass 1 stores
+    kBarPcmFull = 4,      // +stage (4,5,6)
+    kBarPcmEmpty = 7,     // +stage (7,8,9)
+    kBarOutFull = 10,     // +slot (10,11)
+    kBarOutEmpty = 12,    // +slot (12,13)
+};
+constexpr int kPipeThreads = kThreads;   // threads on a FULL/EMPTY barrier
 
+__device__ __forceinline__ void bar_sync(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+template <bool F32>
+struct Cfg {
+    static constexpr int kStages = F32 ? 2 : 3;          // PCM stages (tiles staged ahead: kStages - 1)
+    static constexpr int kPcmWords = kHopRows * (F32 ? kHopWordsF32 : kHopWordsI16);
+};
+
+// Synchronisation protocol.  Both groups walk the same iteration space t = 0, 1, ...
+// The tiles a CTA claims are valid for t < V and invalid from V on (the counter ran
+// out); both groups stop in iteration V:
+//   helpers, iteration t : claim + stage tile t + kAhead (waits PcmEmpty of the stage),
+//                          arrive PcmFull(t + 1), [valid] wait OutFull(t), store rows +
+//                          column sums, arrive OutEmpty(t), publish the tile's partial
+//                          sums, retire the tile
+//   FFT,     iteration t : wait PcmFull(t), [valid] pass 1 (arrive PcmEmpty after the
+//                          loads), ExchA, pass-2 loads, ExchB, wait OutEmpty(t - 2),
+//                          pass 2, arrive OutFull(t)
+template <bool F32>
+__global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
+    constexpr int kStages = Cfg<F32>::kStages;
+    constexpr int kAhead = kStages - 1;
+    constexpr int kPcmWords = Cfg<F32>::kPcmWords;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tab = reinterpret_cast<double*>(smem_raw);                        // 1200 doubles
-    int* blk_off = reinterpret_cast<int*>(tab + kTabDoubles);                 // [kMaxBatch + 1]
-    float* s_stat = reinterpret_cast<float*>(blk_off + kMaxBatch + 1);        // [3][200]
-    unsigned char* warp_base = reinterpret_cast<unsigned char*>(s_stat + 3 * kBins);
-    __shared__ int s_blk[2];
+    cplx* exch = reinterpret_cast<cplx*>(smem_raw);                           // [200][32]
+    float* outt = reinterpret_cast<float*>(exch + 200 * kTile);               // [2][32*201]
+    uint32_t* pcm = reinterpret_cast<uint32_t*>(outt + 2 * kTile * kOutStride);  // [kStages][kPcmWords]
+    int* tile_off = reinterpret_cast<int*>(pcm + kStages * kPcmWords);        // [kMaxBatch + 1]
+    float* s_col = reinterpret_cast<float*>(tile_off + kMaxBatch + 1);        // [4][3][200] helper column sums
+    double* tab = reinterpret_cast<double*>(s_col + kHelperWarps * 3 * kBins);   // [1200], 16-byte aligned
+    __shared__ Meta meta[kRing];
     __shared__ int s_last;
-    __shared__ Utt s_utt[2];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    cplx* exch = reinterpret_cast<cplx*>(warp_base + (size_t)warp * kWarpBytes);
-    unsigned char* pcm = reinterpret_cast<unsigned char*>(exch + kExchCplx);
-    float* ot = reinterpret_cast<float*>(exch);                               // out tile aliases the exchange
 
-    for (int i = tid; i < kTabDoubles; i += kThreads) tab[i] = g_tables[i];
+    for (int i = tid; i < kTabDoubles; i += kThreads) tab[i] = g_tab[i];
     if (warp == 0) {
-        // exclusive scan of ceil(n_frames / kFB) over the utterances
+        // exclusive scan of ceil(n_frames / 32) over the utterances
         int carry = 0;
         for (int base = 0; base < p.batch; base += 32) {
             const int i = base + lane;
@@ -257,7 +318,7 @@ __global__ void __launch_bounds__(InTraits<IN>::kWarps * 32, 1) spectrogram_kern
             if (i < p.batch) {
                 long long n = p.frame_offsets[i + 1] - p.frame_offsets[i];
                 if (n < 0) n = 0;
-                v = (int)((n + kFB - 1) / kFB);
+                v = (int)((n + kTile - 1) / kTile);
             }
             int incl = v;
 #pragma unroll
@@ -265,248 +326,294 @@ __global__ void __launch_bounds__(InTraits<IN>::kWarps * 32, 1) spectrogram_kern
                 const int n = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += n;
             }
-            if (i < p.batch) blk_off[i] = carry + incl - v;
+            if (i < p.batch) tile_off[i] = carry + incl - v;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        __syncwarp();
-        if (lane == 0) {
-            blk_off[p.batch] = carry;
-            const int first = atomicAdd(p.counters, 1);
-            s_blk[0] = first;
-            if (first < carry) locate_block<IN, kFB>(p, blk_off, first, s_utt[0]);
-        }
+        if (lane == 0) tile_off[p.batch] = carry;
     }
     __syncthreads();
-    const int total_blocks = blk_off[p.batch];
-
-    const double2* tabW2 = reinterpret_cast<const double2*>(tab);
-    const cplx* tabT = reinterpret_cast<const cplx*>(tab + 400);
-    const cplx* tabP = reinterpret_cast<const cplx*>(tab + 800);
-
-    // lane -> (role r, frame slot g); lanes 30 and 31 shadow lane 29 (same addresses,
-    // same values) so that nothing in the transform is predicated
-    const int ll = lane < 30 ? lane : 29;
-    const int r = ll / 3, g = ll - 3 * r;
-    const bool j0 = (r == 0);
-    const int k1a = lane_k1a(r), k1b = lane_k1b(r);
-    const int kb_hi = j0 ? -110 : r;          // bin of slot s >= 6 is kb_hi + 20 s
+    const int total_tiles = tile_off[p.batch];
     const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
 
-    for (int it = 0;; ++it) {
-        const int blk = s_blk[it & 1];
-        if (blk >= total_blocks) break;
-        // claim the next block now; the result is only needed at the end of this one
-        int next_blk = 0;
-        if (tid == 0) next_blk = atomicAdd(p.counters, 1);
-
-        const Utt& u = s_utt[it & 1];
-        // this warp's tiles: an even split of the block's tiles
-        const int t_begin = (warp * u.nt) / kWarps;
-        const int t_end = ((warp + 1) * u.nt) / kWarps;
-
-        if (t_begin < t_end) stage_tile<IN>(p, u, u.f0 + t_begin * kTileFrames, pcm, lane);
-        for (int t = t_begin; t < t_end; ++t) {
-            const int f = u.f0 + t * kTileFrames;
-            const long long remf = u.nfr - f;
-            const int nf = remf < kTileFrames ? (int)remf : kTileFrames;
-            cp_async_wait<0>();
-            __syncwarp();
-            // ---------------- pass 1: window, DFT20 of residue r, twiddle ----------------
+    if (warp < kFftWarps) {
+        // ------------------------------ FFT warps ------------------------------
+        // the role: residue class in pass 1, row pair in pass 2; window values and twiddles
+        // are warp-uniform shared-memory broadcasts
+        const int r = warp;
+        const double2* tabW2 = reinterpret_cast<const double2*>(tab);
+        const cplx* tabT = reinterpret_cast<const cplx*>(tab + 400) + r * 20;
+        const cplx* tabP = reinterpret_cast<const cplx*>(tab + 800);
+        for (int t = 0;; ++t) {
+            const int st = t % kStages;
+            const int s = t & 1;
+            bar_sync(kBarPcmFull + st, kPipeThreads);
+            if (!meta[t % kRing].valid) break;
+            const uint32_t* pc = pcm + st * kPcmWords;
             {
                 cplx z[20], y[20];
 #pragma unroll
                 for (int n1 = 0; n1 < 20; ++n1) {
+                    const int q = n1 / 8;                 // hop row offset of sample 2*(10 n1 + r)
+                    const int wq = 10 * (n1 % 8) + r;     // int16-pair index inside the hop
                     double x0, x1;
-                    if (IN == kInI16) {
-                        const uint32_t w = reinterpret_cast<const uint32_t*>(pcm)[(80 + kHopPadWords) * g + r + 10 * n1 +
-                                                                                 kHopPadWords * (n1 / 8)];
+                    if (!F32) {
+                        const uint32_t w = pc[(lane + q) * kHopWordsI16 + wq];
                         x0 = i16_to_f64((int)(short)(w & 0xffffu));
                         x1 = i16_to_f64((int)(short)(w >> 16));
                     } else {
-                        float2 v = reinterpret_cast<const float2*>(pcm)[80 * g + 10 * n1 + r];
-                        if (IN == kInMix) {
-                            const float2 nz = reinterpret_cast<const float2*>(pcm + kTileSamples * 4)[80 * g + 10 * n1 + r];
-                            // noise.py:108  (signal + K * noise).astype(float32): two roundings, no FMA
-                            v.x = __fadd_rn(v.x, __fmul_rn(u.gain, nz.x));
-                            v.y = __fadd_rn(v.y, __fmul_rn(u.gain, nz.y));
-                        }
+                        const float2 v = *reinterpret_cast<const float2*>(
+                            reinterpret_cast<const float*>(pc) + (lane + q) * kHopWordsF32 + 2 * wq);
                         x0 = (double)v.x;
                         x1 = (double)v.y;
                     }
                     const double2 w2 = tabW2[10 * n1 + r];
                     z[n1] = cplx{x0 * w2.x, x1 * w2.y};   // wav_util.py:71 data_line * w
                 }
-                __syncwarp();
-                // the staging buffer is free: bring in the next tile behind the arithmetic
-                if (t + 1 < t_end) stage_tile<IN>(p, u, f + kTileFrames, pcm, lane);
+                bar_arrive(kBarPcmEmpty + st, kPipeThreads);
                 dft20(z, y);
-                cplx* row = exch + g * kSlotStride + r;
-                row[0] = y[0];
+                exch[r * kTile + lane] = y[0];
 #pragma unroll
-                for (int k1 = 1; k1 < 20; ++k1) row[k1 * kRowStride] = cmul(y[k1], tabT[k1 * 10 + r]);
+                for (int k1 = 1; k1 < 20; ++k1) exch[(k1 * 10 + r) * kTile + lane] = cmul(y[k1], tabT[k1]);
             }
-            __syncwarp();
-            // ---------------- pass 2: DFT10 of rows j and 20-j, split, log ----------------
+            bar_sync(kBarExchA, kFftThreads);
             {
-                cplx in[10], za[10], zb[10];
-                const cplx* ra = exch + g * kSlotStride + k1a * kRowStride;
-                const cplx* rb = exch + g * kSlotStride + k1b * kRowStride;
+                const int k1a = r, k1b = (r == 0) ? 10 : 20 - r;
+                cplx ia[10], ib[10], za[10], zb[10];
 #pragma unroll
-                for (int n2 = 0; n2 < 10; ++n2) in[n2] = ra[n2];
-                dft10(in, za);
+                for (int n2 = 0; n2 < 10; ++n2) ia[n2] = exch[(k1a * 10 + n2) * kTile + lane];
 #pragma unroll
-                for (int n2 = 0; n2 < 10; ++n2) in[n2] = rb[n2];
-                __syncwarp();                       // every lane has its rows: the exchange becomes the out tile
-                dft10(in, zb);
-                float* orow = ot + g * kOutStride;
-                const float hm = u.half_mag;
-                auto loadP = [&](int s) { return tabP[(s < 6 ? r : kb_hi) + 20 * (s < 10 ? s : (j0 ? 10 : 0))]; };
-                auto emit = [&](int s, double pk, double pm) {
-                    const int k = (s < 6 ? r : kb_hi) + 20 * s;
-                    const float vk = log_mag((float)pk, hm), vm = log_mag((float)pm, hm);
-                    if (s < 10) {
-                        orow[200 - k] = vm;         // role 0, slot 0 writes bin "200" into the row padding
-                        orow[k] = vk;               // role 0, slot 5: bin 100 from pk, as the last store
-                    } else if (j0) {
-                        orow[200 - k] = vm;
-                        orow[k] = vk;
+                for (int n2 = 0; n2 < 10; ++n2) ib[n2] = exch[(k1b * 10 + n2) * kTile + lane];
+                bar_sync(kBarExchB, kFftThreads);     // every warp holds its rows: the exchange is free
+                dft10(ia, za);   // za[k2] = Z[k1a + 20 k2]
+                dft10(ib, zb);   // zb[k2] = Z[k1b + 20 k2]
+                if (t >= 2) bar_sync(kBarOutEmpty + s, kPipeThreads);
+                float* ot = outt + s * (kTile * kOutStride) + lane * kOutStride;
+                const float hm = meta[t % kRing].half_mag;
+                if (r != 0) {
+#pragma unroll
+                    for (int k2 = 0; k2 < 10; ++k2) {
+                        const int k = r + 20 * k2;
+                        double pk, pm;
+                        split_pair(za[k2], zb[9 - k2], tabP[k], pk, pm);
+                        ot[k] = log_mag((float)pk, hm);
+                        ot[200 - k] = log_mag((float)pm, hm);
                     }
-                };
-                split_lane(j0, za, zb, loadP, emit);
-            }
-            __syncwarp();
-            // ---------------- rows out (16-byte stores) + column sums ----------------
-            if (lane < 25) {
-                const float4* o4 = reinterpret_cast<const float4*>(ot);
-                float4* dst = reinterpret_cast<float4*>(p.out + (size_t)(u.row0 + f) * kBins);
+                } else {
+                    // row k1 = 0: bins 20 k2, mirror 20 (10 - k2); k2 = 0 and 5 are their own mirror
 #pragma unroll
-                for (int gg = 0; gg < kTileFrames; ++gg) {
-                    if (gg < nf) {
-                        const float4 a = o4[gg * (kOutStride / 4) + lane];
-                        const float4 b = o4[gg * (kOutStride / 4) + 25 + lane];
-                        dst[gg * (kBins / 4) + lane] = a;
-                        dst[gg * (kBins / 4) + 25 + lane] = b;
+                    for (int k2 = 0; k2 <= 5; ++k2) {
+                        const int k = 20 * k2;
+                        double pk, pm;
+                        split_pair(za[k2], za[(10 - k2) % 10], tabP[k], pk, pm);
+                        ot[k] = log_mag((float)pk, hm);
+                        if (k2 != 0 && k2 != 5) ot[200 - k] = log_mag((float)pm, hm);
+                    }
+                    // row k1 = 10: bins 10 + 20 k2, mirror 10 + 20 (9 - k2)
+#pragma unroll
+                    for (int k2 = 0; k2 < 5; ++k2) {
+                        const int k = 10 + 20 * k2;
+                        double pk, pm;
+                        split_pair(zb[k2], zb[9 - k2], tabP[k], pk, pm);
+                        ot[k] = log_mag((float)pk, hm);
+                        ot[200 - k] = log_mag((float)pm, hm);
                     }
                 }
             }
+            bar_arrive(kBarOutFull + s, kPipeThreads);
         }
-        __syncwarp();
+    } else {
+        // ----------------------------- helper warps ----------------------------
+        const int hw = warp - kFftWarps;                          // 0..3
+        const int hth = hw * 32 + lane;
+        const bool mix = (p.noise != nullptr);
+        // (helper thread 0) the next tile of this CTA, claimed one issue ahead so that
+        // the atomic's round trip is off the staging path
+        int next_tile = total_tiles;
+        if (hth == 0) next_tile = atomicAdd(p.counters, 1);
 
-        // ---- block epilogue -------------------------------------------------------
-        __syncthreads();
-        if (tid == 0) {
-            // release: the barrier above orders every thread's row stores before this
-            // fence (cumulativity), the counter publishes them
-            int last = 0;
-            if (want_stats) {
-                __threadfence();
-                const int old = atomicAdd(p.counters + 1 + u.b, 1);
-                last = (old + 1 == u.nblk);
+        // tile t: metadata, then start filling PCM stage t % kStages.  The async path
+        // returns with the copies in flight (one commit group per tile).
+        auto issue = [&](int t) {
+            if (hth == 0) {
+                Meta& mn = meta[t % kRing];
+                const int tile = next_tile;
+                if (tile < total_tiles) {
+                    next_tile = atomicAdd(p.counters, 1);
+                    fill_meta(p, tile_off, tile, mn);
+                } else {
+                    mn.valid = 0;
+                }
             }
-            s_last = last;
-            s_blk[(it + 1) & 1] = next_blk;
-            if (next_blk < total_blocks) locate_block<IN, kFB>(p, blk_off, next_blk, s_utt[(it + 1) & 1]);
-        }
-        __syncthreads();
-        if (s_last) {
-            // The last block of utterance b has retired: z-score the utterance in place
-            // (sklearn.preprocessing.scale, wav_util.py:79: mean, std with ddof=0,
-            // std < 10 eps -> 1) from its L2-resident rows, in two sweeps.
-            __threadfence();
-            float4* base = reinterpret_cast<float4*>(p.out + (size_t)u.row0 * kBins);
-            const int nfr = (int)u.nfr;
-            constexpr int kPh = kThreads / 50 < 10 ? kThreads / 50 : 10;   // row phases
-            float4* scr = reinterpret_cast<float4*>(warp_base);             // [2][kPh][50], warps are idle
-            // sweep A: per-column sums of (y - c) and (y - c)^2, c = row 0 (no cancellation)
-            if (tid < kPh * 50) {
-                const int c4 = tid % 50, ph = tid / 50;
-                const float4 c = __ldcg(base + c4);
-                float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), qa = sa;
-                constexpr int kU = 8;
-                for (int r0 = ph; r0 < nfr; r0 += kU * kPh) {
-                    float4 v[kU];
+            bar_sync(kBarHelpers, kHelperThreads);
+            if (t >= kStages) bar_sync(kBarPcmEmpty + (t % kStages), kPipeThreads);
+            const Meta& m = meta[t % kRing];
+            if (m.valid) {
+                uint32_t* dst = pcm + (t % kStages) * kPcmWords;
+                const bool aligned = (((reinterpret_cast<uintptr_t>(p.samples) + m.sbase * (F32 ? 4 : 2)) & 15) == 0);
+                if (!mix && aligned) issue_pcm_tile_async<F32>(p, m, dst, hth);
+                else load_pcm_tile<F32>(p, m, dst, hth);
+            }
+            cp_async_commit();
+        };
+
+        // rows of tile t to global memory (coalesced), and this warp's column sums of
+        // (y - c), (y - c)^2 with c = the warp's first row, into shared memory
+        auto epilogue = [&](int t) {
+            const Meta& m = meta[t % kRing];
+            const float* ot = outt + (t & 1) * (kTile * kOutStride);
+            float c[7], sm[7], sq[7];
 #pragma unroll
-                    for (int e = 0; e < kU; ++e) {
-                        const int row = r0 + e * kPh;
-                        v[e] = (row < nfr) ? __ldcg(base + (size_t)row * 50 + c4) : c;
-                    }
+            for (int e = 0; e < 7; ++e) { c[e] = 0.f; sm[e] = 0.f; sq[e] = 0.f; }
+#pragma unroll 2
+            for (int ff = 0; ff < 8; ++ff) {
+                const int f = hw * 8 + ff;
+                if (f >= m.nf) break;
+                float* orow = p.out + (size_t)(m.row0 + m.f0 + f) * kBins;
 #pragma unroll
-                    for (int e = 0; e < kU; ++e) {
-                        float d;
-                        d = v[e].x - c.x; sa.x += d; qa.x = fmaf(d, d, qa.x);
-                        d = v[e].y - c.y; sa.y += d; qa.y = fmaf(d, d, qa.y);
-                        d = v[e].z - c.z; sa.z += d; qa.z = fmaf(d, d, qa.z);
-                        d = v[e].w - c.w; sa.w += d; qa.w = fmaf(d, d, qa.w);
+                for (int e = 0; e < 7; ++e) {
+                    const int k = lane + 32 * e;
+                    if (k < kBins) {
+                        const float y = ot[f * kOutStride + k];
+                        orow[k] = y;
+                        if (ff == 0) c[e] = y;
+                        const float d = y - c[e];
+                        sm[e] += d;
+                        sq[e] = fmaf(d, d, sq[e]);
                     }
                 }
-                scr[ph * 50 + c4] = sa;
-                scr[(kPh + ph) * 50 + c4] = qa;
             }
-            __syncthreads();
-            for (int i = tid; i < kBins; i += kThreads) {
-                const float* sf = reinterpret_cast<const float*>(scr);
+            if (want_stats) {
+                float* sc = s_col + hw * 3 * kBins;
+#pragma unroll
+                for (int e = 0; e < 7; ++e) {
+                    const int k = lane + 32 * e;
+                    if (k < kBins) { sc[k] = c[e]; sc[kBins + k] = sm[e]; sc[2 * kBins + k] = sq[e]; }
+                }
+            }
+        };
+
+#pragma unroll 1
+        for (int t = 0; t < kAhead; ++t) issue(t);
+        cp_async_wait<kAhead - 1>();
+        bar_arrive(kBarPcmFull + 0, kPipeThreads);
+        for (int t = 0;; ++t) {
+            issue(t + kAhead);
+            cp_async_wait<kAhead - 1>();          // everything but the newest group(s): tile t+1 has landed
+            bar_arrive(kBarPcmFull + ((t + 1) % kStages), kPipeThreads);
+            if (!meta[t % kRing].valid) break;
+            bar_sync(kBarOutFull + (t & 1), kPipeThreads);
+            epilogue(t);
+            bar_sync(kBarHelpers, kHelperThreads);          // the out tile has been read by all four warps
+            bar_arrive(kBarOutEmpty + (t & 1), kPipeThreads);
+            if (!want_stats) continue;
+            // per-tile column sums, un-shifted, in fp64 and a fixed order:
+            //   sum y = s + n c,  sum y^2 = q + 2 c s + n c^2   over the four warps' row groups
+            const Meta& m = meta[t % kRing];
+            for (int k = hth; k < kBins; k += kHelperThreads) {
                 double a1 = 0.0, a2 = 0.0;
 #pragma unroll
-                for (int ph = 0; ph < kPh; ++ph) {          // fixed order: reproducible
-                    a1 += (double)sf[ph * 200 + i];
-                    a2 += (double)sf[(kPh + ph) * 200 + i];
+                for (int w = 0; w < kHelperWarps; ++w) {
+                    int nw = m.nf - 8 * w;
+                    nw = nw < 0 ? 0 : (nw > 8 ? 8 : nw);
+                    const double n = (double)nw;
+                    const double cc = (double)s_col[w * 3 * kBins + k];
+                    const double ss = (double)s_col[w * 3 * kBins + kBins + k];
+                    const double qq = (double)s_col[w * 3 * kBins + 2 * kBins + k];
+                    a1 += fma(n, cc, ss);
+                    a2 += fma(cc, fma(n, cc, 2.0 * ss), qq);
                 }
-                const double n = (double)nfr;
-                const double md = a1 / n;
-                const double mean = (double)__ldcg(p.out + (size_t)u.row0 * kBins + i) + md;
-                double var = a2 / n - md * md;
-                if (var < 0.0) var = 0.0;
-                double sd = sqrt(var);
-                if (sd < 10.0 * 2.220446049250313e-16) sd = 1.0;
-                const float mh = (float)mean;
-                s_stat[i] = mh;
-                s_stat[kBins + i] = (float)(mean - (double)mh);
-                s_stat[2 * kBins + i] = (float)(1.0 / sd);
+                p.partials[(size_t)m.tile * kBins + k] = make_double2(a1, a2);
             }
-            __syncthreads();
-            // sweep B: (y - mean) / std
-            const long long n4 = (long long)nfr * (kBins / 4);
-            constexpr int kUnroll = 8;       // 8 x 16-byte L2 reads in flight per thread
-            for (long long i0 = tid; i0 < n4; i0 += (long long)kUnroll * kThreads) {
-                float4 v[kUnroll];
-#pragma unroll
-                for (int e = 0; e < kUnroll; ++e) {
-                    const long long i = i0 + (long long)e * kThreads;
-                    if (i < n4) v[e] = __ldcg(base + i);
-                }
-#pragma unroll
-                for (int e = 0; e < kUnroll; ++e) {
-                    const long long i = i0 + (long long)e * kThreads;
-                    if (i < n4) {
-                        const int k = (int)(i % (kBins / 4)) * 4;
-                        const float4 mh = *reinterpret_cast<const float4*>(s_stat + k);
-                        const float4 ml = *reinterpret_cast<const float4*>(s_stat + kBins + k);
-                        const float4 iv = *reinterpret_cast<const float4*>(s_stat + 2 * kBins + k);
-                        float4 o;
-                        o.x = ((v[e].x - mh.x) - ml.x) * iv.x;
-                        o.y = ((v[e].y - mh.y) - ml.y) * iv.y;
-                        o.z = ((v[e].z - mh.z) - ml.z) * iv.z;
-                        o.w = ((v[e].w - mh.w) - ml.w) * iv.w;
-                        base[i] = o;
+            // retire the tile (release); the CTA that retires the last tile of the utterance
+            // turns the partials into mean and 1/std (sklearn.preprocessing.scale, wav_util.py:79:
+            // std with ddof = 0, std < 10 eps -> 1)
+            bar_sync(kBarHelpers, kHelperThreads);
+            if (hth == 0) {
+                __threadfence();
+                const int old = atomicAdd(p.counters + 1 + m.b, 1);
+                s_last = (old + 1 == m.ntiles_b) ? 1 : 0;
+            }
+            bar_sync(kBarHelpers, kHelperThreads);
+            if (s_last) {
+                __threadfence();
+                const int t_lo = tile_off[m.b], t_hi = tile_off[m.b + 1];
+                for (int k = hth; k < kBins; k += kHelperThreads) {
+                    double a1 = 0.0, a2 = 0.0;
+                    for (int q = t_lo; q < t_hi; ++q) {
+                        const double2 v = __ldcg(p.partials + (size_t)q * kBins + k);
+                        a1 += v.x;
+                        a2 += v.y;
                     }
+                    const double n = (double)m.nfr;
+                    const double mean = a1 / n;
+                    double var = a2 / n - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    double sd = sqrt(var);
+                    if (sd < 10.0 * 2.220446049250313e-16) sd = 1.0;
+                    const float mh = (float)mean;
+                    float* st = p.stats + (size_t)m.b * 3 * kBins;
+                    st[k] = mh;
+                    st[kBins + k] = (float)(mean - (double)mh);
+                    st[2 * kBins + k] = (float)(1.0 / sd);
                 }
             }
-            __syncthreads();
         }
     }
 }
 
-template <int IN>
-static size_t main_smem_bytes() {
-    return sizeof(double) * kTabDoubles + sizeof(int) * (kMaxBatch + 1) + sizeof(float) * 3 * kBins +
-           (size_t)InTraits<IN>::kWarps * (kExchCplx * 16 + InTraits<IN>::kPcmBytes);
+// ---------------------------------------------------------------------------
+// z-score: out = (y - mean) / std, in place; grid (x, utterance), pure streaming
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) normalize_kernel(Params p) {
+    const int b = blockIdx.y;
+    __shared__ __align__(16) float s_stat[3 * kBins];
+    for (int k = threadIdx.x; k < 3 * kBins; k += blockDim.x) s_stat[k] = p.stats[(size_t)b * 3 * kBins + k];
+    __syncthreads();
+    const long long fo = p.frame_offsets[b];
+    const long long nfr = p.frame_offsets[b + 1] - fo;
+    const long long row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
+    float4* base = reinterpret_cast<float4*>(p.out + (size_t)row0 * kBins);
+    const long long n4 = nfr * (kBins / 4);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr int kU = 4;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += kU * stride) {
+        float4 v[kU];
+#pragma unroll
+        for (int e = 0; e < kU; ++e) {
+            const long long i = i0 + e * stride;
+            if (i < n4) v[e] = __ldcg(base + i);
+        }
+#pragma unroll
+        for (int e = 0; e < kU; ++e) {
+            const long long i = i0 + e * stride;
+            if (i < n4) {
+                const int k = (int)(i % (kBins / 4)) * 4;
+                const float4 mh = *reinterpret_cast<const float4*>(s_stat + k);
+                const float4 ml = *reinterpret_cast<const float4*>(s_stat + kBins + k);
+                const float4 iv = *reinterpret_cast<const float4*>(s_stat + 2 * kBins + k);
+                float4 o;
+                o.x = ((v[e].x - mh.x) - ml.x) * iv.x;
+                o.y = ((v[e].y - mh.y) - ml.y) * iv.y;
+                o.z = ((v[e].z - mh.z) - ml.z) * iv.z;
+                o.w = ((v[e].w - mh.w) - ml.w) * iv.w;
+                base[i] = o;
+            }
+        }
+    }
 }
 
-template <int IN>
+template <bool F32>
+static size_t main_smem_bytes() {
+    return sizeof(cplx) * 200 * kTile + sizeof(float) * 2 * kTile * kOutStride +
+           sizeof(uint32_t) * (size_t)Cfg<F32>::kStages * Cfg<F32>::kPcmWords + sizeof(int) * (kMaxBatch + 1) +
+           sizeof(float) * kHelperWarps * 3 * kBins + sizeof(double) * kTabDoubles + 16;
+}
+
+template <bool F32>
 static void launch_main(const Params& p, int grid, cudaStream_t stream) {
-    const size_t smem = main_smem_bytes<IN>();
-    cudaFuncSetAttribute(spectrogram_kernel<IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spectrogram_kernel<IN><<<grid, InTraits<IN>::kWarps * 32, smem, stream>>>(p);
+    const size_t smem = main_smem_bytes<F32>();
+    cudaFuncSetAttribute(spectrogram_kernel<F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spectrogram_kernel<F32><<<grid, kThreads, smem, stream>>>(p);
 }
 
 }  // namespace spec
@@ -556,9 +663,9 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         }
         gains = gw;
     }
-    if (!(phases & ASRK_PHASE_SPEC_MAIN)) return launch_status();
+    if (!(phases & (ASRK_PHASE_SPEC_MAIN | ASRK_PHASE_SPEC_NORMALIZE))) return launch_status();
 
-    // the kernel locates blocks through a prefix array in shared memory: at most
+    // the kernel locates tiles through a prefix array in shared memory: at most
     // kMaxBatch utterances per launch, larger batches go in slices
     for (int b0 = 0; b0 < batch; b0 += kMaxBatch) {
         const int nb = (batch - b0) < kMaxBatch ? (batch - b0) : kMaxBatch;
@@ -574,11 +681,17 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         p.mode = mode;
         p.out = out;
         p.counters = reinterpret_cast<int*>(ws + l.counters);
-        if (cudaMemsetAsync(p.counters, 0, sizeof(int) * (size_t)(nb + 1), stream) != cudaSuccess)
+        p.partials = reinterpret_cast<double2*>(ws + l.partials);
+        p.stats = reinterpret_cast<float*>(ws + l.stats) + (size_t)b0 * 3 * kBins;
+        if ((phases & ASRK_PHASE_SPEC_MAIN) &&
+            cudaMemsetAsync(p.counters, 0, sizeof(int) * (size_t)(nb + 1), stream) != cudaSuccess)
             return ASRK_E_CUDA;
-        if (sample_dtype == ASRK_DTYPE_I16) launch_main<kInI16>(p, grid, stream);
-        else if (noise) launch_main<kInMix>(p, grid, stream);
-        else launch_main<kInF32>(p, grid, stream);
+        if (phases & ASRK_PHASE_SPEC_MAIN) {
+            if (sample_dtype == ASRK_DTYPE_I16) launch_main<false>(p, grid, stream);
+            else launch_main<true>(p, grid, stream);
+        }
+        if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE))
+            normalize_kernel<<<dim3(16, nb), 256, 0, stream>>>(p);
     }
     return launch_status();
 }
