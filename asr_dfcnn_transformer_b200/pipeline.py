@@ -8,6 +8,37 @@ and the CTC kernels fill the rest.  Nothing here synchronises with the host.
 from . import _lib, ctc, features
 
 
+def shard_bounds(n_utterances, rank, world):
+    """Contiguous batch shard of rank ``rank``: utterances are
+    independent in all three parts, so no tensor ever crosses GPUs."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    lo = (n_utterances * rank) // world
+    hi = (n_utterances * (rank + 1)) // world
+    return lo, hi
+
+
+def all_reduce_loss(loss_sum_and_count, group=None, stream=None):
+    """The path's only collective: SUM all-reduce of the 2-element tensor
+    ``[sum of per-utterance losses, number of utterances]`` (float64), mirroring
+    ``tf.reduce_mean(self.loss)`` (acoustic_model2.py:83) across ranks.  Works with any
+    ``torch.distributed`` backend (NCCL on the GPUs, gloo in the CPU tests); when a CUDA
+    ``stream`` is given the collective is enqueued there so that it overlaps the next
+    step.  Returns the (in-place reduced) tensor; mean = t[0] / t[1]."""
+    import torch
+    import torch.distributed as dist
+    t = loss_sum_and_count
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    if stream is not None and t.is_cuda:
+        stream.wait_stream(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(stream):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
 class HotPathStep:
     def __init__(self, device=None, feature_ctas=0):
         torch = _lib.require_cuda()

@@ -117,3 +117,27 @@ def test_wav_file_surface(tmp_path):
     assert feature_err(got2, fbank_ref.compute_fbank_from_asrt(sig)) <= FEATURE_TOL
     wd, fr = wav_util.read_wav_data(p)
     assert fr == 16000 and wd.shape == (1, 16240) and np.array_equal(wd[0], sig)
+
+
+def test_loader_batch_assembly(tmp_path):
+    """data_loader.py:105-162 on the device path: rejected rows are dropped, the kept
+    rows land zero-padded in [B',1600,200,1] and match the oracle."""
+    from asr_dfcnn_transformer_b200 import data_loader as dl
+    d = tmp_path / "dict.txt"
+    d.write_text("a1\tx\nb2\ty\nc3\tw\n", encoding="utf-8")
+    _, s2i, _ = dl.load_acoustic_vocab(str(d))
+    rng = np.random.default_rng(11)
+    sigs = [synth.g2_voiced(rng, 24000), synth.g1_white(rng, 4000), synth.g1_white(rng, 16080),
+            synth.g1_white(rng, 12345)]
+    labs = ["a1 b2", "a1 b2 c3 a1", "c3", "b2 zz"]           # row 1: label >= T_ctc, row 3: unknown symbol
+    wav, il, lab, ll, keep = dl.data_generation(sigs, labs, s2i)
+    assert keep == [0, 2]
+    assert tuple(wav.shape) == (2, 1600, 200, 1) and il.tolist() == [19, 13] and ll.tolist() == [2, 1]
+    assert lab[0, :3].tolist() == [0, 1, 0] and lab[1, :2].tolist() == [2, 0]
+    got = wav.cpu().numpy()[..., 0]
+    for r, i in enumerate(keep):
+        ref = fbank_ref.compute_fbank(sigs[i])
+        n = ref.shape[0]
+        err = zscore_feature_err(got[r, :n], ref, fbank_ref.compute_fbank_unnormalised(sigs[i]))
+        assert err <= FEATURE_TOL, (i, err)
+        assert not got[r, n:].any()

@@ -1,4 +1,6 @@
 """CPU: host-side packing / frame rules / error behaviour (no device needed)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -56,3 +58,32 @@ def test_bench_workload_shapes():
     n = sum(len(p) for p in hb["pcm"])
     assert feat == 2 * n + 800 * int(hb["nfr"].sum())
     assert ctc_b == 8 * synth.VOCAB_DICT_TXT * int(hb["input_len"].sum())
+
+
+def test_loader_rules(tmp_path):
+    """data_loader.py:63-71 vocabulary, :44-60 pny2id, :132/:231 lengths, :139-141 rejects."""
+    from asr_dfcnn_transformer_b200 import data_loader as dl
+    d = tmp_path / "dict.txt"
+    d.write_text("a1\tx\nb2\ty\na1\tz\nc3\tw\n", encoding="utf-8")
+    size, s2i, i2s = dl.load_acoustic_vocab(str(d))
+    assert size == 5 and s2i["_"] == 4 and i2s[4] == "_"
+    assert s2i["a1"] == 2                      # duplicate symbol -> the LATER index
+    assert dl.pny2id(" b2 c3 ", s2i) == [1, 3]
+    with pytest.raises(ValueError):
+        dl.pny2id("b2 zz", s2i)
+    assert dl.ctc_input_length(998) == 125 and dl.ctc_input_length(1600) == 200
+    assert dl.ctc_input_length(1600, capped=False) == 201
+    # every row rejected -> no device work at all: too long, label >= input length, unknown symbol
+    rng = np.random.default_rng(0)
+    sigs = [synth.g1_white(rng, 16000 * 17), synth.g1_white(rng, 4000), synth.g1_white(rng, 16000)]
+    wav, il, lab, ll, keep = dl.data_generation(sigs, ["b2", "b2 c3 b2 c3", "b2 nope"], s2i)
+    assert wav is None and keep == [] and il.shape == (0,) and lab.shape == (0, 64)
+    ref = os.path.join("/root/reference", "dict.txt")
+    if os.path.isfile(ref):
+        size, s2i, _ = dl.load_acoustic_vocab(ref)
+        assert size == synth.VOCAB_DICT_TXT and s2i["_"] == size - 1
+        assert s2i["heng"] == 1364                                   # duplicate key: the later index
+        pd = pytest.importorskip("pandas")                            # the reference's own recipe (:64-69)
+        symbol_list = pd.read_table(ref, header=None).iloc[:, 0].tolist()
+        symbol_list.append("_")
+        assert dict([p, i] for i, p in enumerate(symbol_list)) == s2i
