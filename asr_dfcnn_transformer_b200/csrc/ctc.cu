@@ -67,6 +67,7 @@ struct Params {
     float* beta;         // [B][T][2 Ls+1] beta (small-lattice kernel only)
     double* coff;        // [B][T]        alpha offsets
     double* logp;        // [B]
+    int* need_generic;   // [1] set by prep when some utterance does not fit the fused kernel
     int Ls;              // label_stride
     int fused;           // 1: utterances with a small lattice are done by fused_small_kernel
 };
@@ -76,11 +77,11 @@ struct Params {
 // budget take the fused CTA-per-utterance kernel.
 constexpr int kSmallSmemFloats = 16 * 1024;   // 64 KB per CTA
 __host__ __device__ __forceinline__ bool small_lattice(int L, int T) {
-    return L <= 31 && (long long)T * (5 * L + 6) <= kSmallSmemFloats;
+    return L <= 31 && (long long)T * (5 * L + 14) <= kSmallSmemFloats;
 }
 
 struct WsLayout {
-    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, beta, coff, logp, total;
+    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, beta, coff, logp, flag, total;
 };
 
 static WsLayout ws_layout(int T, int B, int Ls) {
@@ -99,6 +100,7 @@ static WsLayout ws_layout(int T, int B, int Ls) {
     l.beta = o;        o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
     l.coff = o;        o = align_up(o + sizeof(double) * BT, 256);
     l.logp = o;        o = align_up(o + sizeof(double) * (size_t)B, 256);
+    l.flag = o;        o = align_up(o + sizeof(int), 256);
     l.total = o;
     return l;
 }
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(1024) prep_kernel(Params p) {
         if (status == ASRK_ROW_OK && tl < L + repeats) status = ASRK_ROW_NOT_ENOUGH_TIME;
         p.eff_len[b] = (status == ASRK_ROW_BAD_LENGTH) ? 0 : L;
         p.row_status[b] = status;
+        if (status != ASRK_ROW_BAD_LENGTH && !small_lattice(L, tl < p.T ? tl : p.T)) atomicOr(p.need_generic, 1);
     }
 }
 
@@ -264,6 +267,7 @@ __device__ __forceinline__ void row_stats_generic(const float* row, int V, int l
 
 template <int NV4, bool WANT_LSE>
 __global__ void __launch_bounds__(kRowWarps * 32) rows_kernel(Params p) {
+    if (WANT_LSE && p.fused && *p.need_generic == 0) return;   // every utterance took the fused kernel
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= (long long)p.T * p.B) return;
@@ -351,7 +355,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // gathered log-probabilities never leave shared memory.
 template <int NV4>
 __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     __shared__ double s_fin;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -374,10 +378,15 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
     if (!small_lattice(L, T)) return;          // generic path
     const int W = L + 1;                        // row width of the gathered log-probs
     const int Ub = 2 * L + 1;                   // lattice states
-    float* slse = sm;                           // [T]
+    double* sC = reinterpret_cast<double*>(sm); // [T] sum_{s<=t} log c_s
+    double* sD = sC + T;                        // [T] sum_{s>=t} log d_s
+    float* slse = reinterpret_cast<float*>(sD + T);  // [T]
     float* smax = slse + T;                     // [T]
     int* samax = reinterpret_cast<int*>(smax + T);   // [T]
-    float* slp = smax + 2 * T;                  // [T][W]
+    float* slogc = smax + 2 * T;                // [T] alpha column scales c_t
+    float* slogd = slogc + T;                   // [T] beta column scales d_t
+    float* sK = slogd + T;                      // [T] exp(C_t + D_t - log p)
+    float* slp = sK + T;                        // [T][W] y_t(l'_j)
     float* sal = slp + T * W;                   // [T][Ub]
     float* sbe = sal + T * Ub;                  // [T][Ub]
     const int* eff = p.eff_labels + (size_t)b * p.Ls;
@@ -396,12 +405,18 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         if (lane == 0) { slse[t] = lse; smax[t] = m; samax[t] = am; }
         for (int j = lane; j < W; j += 32) {
             const int c = (j == 0) ? p.blank : eff[j - 1];
-            slp[t * W + j] = x[c] - lse;
+            slp[t * W + j] = __expf(x[c] - lse);          // y_t(l'_j), linear domain
         }
     }
     __syncthreads();
 
     // ---- B: alpha || beta || greedy collapse ----------------------------------
+    // Linear-domain recursions, rescaled by the column maximum at every frame (one
+    // REDUX: positive floats order like their bit patterns), so a step is one shuffle,
+    // four adds/multiplies, one REDUX and one reciprocal -- no exp / log on the chain.
+    // True values: alpha_t = ahat_t * exp(sum_{s<=t} log c_s), beta_t (which excludes
+    // y_t, TF convention) = bhat_t * exp(sum_{s>=t} log d_s); the logs go to shared
+    // memory and are prefix-summed in double after the sweeps.
     const int i = lane;
     const int lab_i = (i < L) ? eff[i] : -1;
     const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
@@ -410,58 +425,65 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
     if (warp == 0) {
         // alpha: pair (blank 2i, label 2i+1)
         const bool has_lab = (i < L);
-        double a_b = ninf, a_l = ninf;
+        float a_b = 0.f, a_l = 0.f;
         if (i == 0) {
-            a_b = (double)slp[0];
-            if (L >= 1) a_l = (double)slp[1];
+            a_b = slp[0];
+            if (L >= 1) a_l = slp[1];
         }
-        if (has_blank) sal[2 * i] = (float)a_b;
-        if (has_lab) sal[2 * i + 1] = (float)a_l;
-        for (int t = 1; t < T; ++t) {
-            const double lb = (double)slp[t * W];
-            const double ll = has_lab ? (double)slp[t * W + 1 + i] : ninf;
-            double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
-            if (i == 0) p1 = ninf;
-            const double nb = lb + lse2(a_b, p1);
-            const double nl = ll + lse3(a_l, a_b, skip ? p1 : ninf);
-            a_b = has_blank ? nb : ninf;
-            a_l = has_lab ? nl : ninf;
+        for (int t = 0; t < T; ++t) {
+            if (t > 0) {
+                const float yb = slp[t * W];
+                const float yl = has_lab ? slp[t * W + 1 + i] : 0.f;
+                float p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+                if (i == 0) p1 = 0.f;
+                const float nb = yb * (a_b + p1);
+                const float nl = yl * (a_l + a_b + (skip ? p1 : 0.f));
+                a_b = has_blank ? nb : 0.f;
+                a_l = nl;
+            }
+            const float c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(a_b, a_l))));
+            const float inv = (c > 0.f) ? __frcp_rn(c) : 0.f;
+            a_b *= inv;
+            a_l *= inv;
             float* o = sal + t * Ub;
-            if (has_blank) o[2 * i] = (float)a_b;
-            if (has_lab) o[2 * i + 1] = (float)a_l;
+            if (has_blank) o[2 * i] = a_b;
+            if (has_lab) o[2 * i + 1] = a_l;
+            if (lane == 0) slogc[t] = c;
         }
-        // log p = LSE(alpha_{T-1}(2L), alpha_{T-1}(2L-1))
-        const double fb = __shfl_sync(0xffffffffu, a_b, L);
-        const double fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : ninf;
-        if (lane == 0) s_fin = lse2(fb, fl);
+        // mass of the two terminal states at T-1
+        const float fb = __shfl_sync(0xffffffffu, a_b, L);
+        const float fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : 0.f;
+        if (lane == 0) s_fin = (double)(fb + fl);
     } else if (warp == 1) {
         if (p.grad != nullptr) {
             // beta: pair (label 2i-1, blank 2i); excludes y_t
             const bool has_lab = (i >= 1 && i <= L);
-            double b_l = ninf, b_b = ninf;
+            float b_l = 0.f, b_b = 0.f;
             if (i == L) {
-                b_b = 0.0;
-                if (L >= 1) b_l = 0.0;
+                b_b = 1.f;
+                if (L >= 1) b_l = 1.f;
             }
-            {
-                float* o = sbe + (T - 1) * Ub;
-                if (has_blank) o[2 * i] = (float)b_b;
-                if (has_lab) o[2 * i - 1] = (float)b_l;
-            }
-            for (int t = T - 2; t >= 0; --t) {
-                const double lb = (double)slp[(t + 1) * W];
-                const double ll = has_lab ? (double)slp[(t + 1) * W + i] : ninf;
-                const double e_b = b_b + lb;
-                const double e_l = b_l + ll;
-                double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
-                if (i == 31) n1 = ninf;
-                const double nbb = lse2(e_b, n1);
-                const double nbl = lse3(e_l, e_b, skip ? n1 : ninf);
-                b_b = has_blank ? nbb : ninf;
-                b_l = has_lab ? nbl : ninf;
+            for (int t = T - 1; t >= 0; --t) {
+                if (t < T - 1) {
+                    const float yb = slp[(t + 1) * W];
+                    const float yl = has_lab ? slp[(t + 1) * W + i] : 0.f;
+                    const float e_b = b_b * yb;
+                    const float e_l = b_l * yl;
+                    float n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+                    if (i == 31) n1 = 0.f;
+                    const float nbb = e_b + n1;
+                    const float nbl = e_l + e_b + (skip ? n1 : 0.f);
+                    b_b = has_blank ? nbb : 0.f;
+                    b_l = has_lab ? nbl : 0.f;
+                }
+                const float d = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(b_b, b_l))));
+                const float inv = (d > 0.f) ? __frcp_rn(d) : 0.f;
+                b_b *= inv;
+                b_l *= inv;
                 float* o = sbe + t * Ub;
-                if (has_blank) o[2 * i] = (float)b_b;
-                if (has_lab) o[2 * i - 1] = (float)b_l;
+                if (has_blank) o[2 * i] = b_b;
+                if (has_lab) o[2 * i - 1] = b_l;
+                if (lane == 0) slogd[t] = d;
             }
         }
     } else if (warp == 2 && p.tokens != nullptr) {
@@ -490,7 +512,28 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         }
     }
     __syncthreads();
-    const double logp = s_fin;
+    // prefix sums of the column scales in double (T additions of ~7 each: fp32 would
+    // lose 1e-2 at T in the hundreds): warp 0 forward over log c, warp 1 backward over log d
+    if (warp < 2) {
+        double carry = 0.0;
+        for (int base = 0; base < T; base += 32) {
+            const int k = base + lane;                       // position in sweep order
+            const int t = (warp == 0) ? k : T - 1 - k;
+            double v = 0.0;
+            if (k < T) v = (double)__logf(warp == 0 ? slogc[t] : slogd[t]);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double n = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += n;
+            }
+            v += carry;
+            if (k < T) (warp == 0 ? sC : sD)[t] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    // log p = log(sum of the two terminal alphas at T-1) = C_{T-1} + log(scaled mass)
+    const double logp = sC[T - 1] + (double)__logf((float)s_fin);
     if (tid == 0) {
         p.logp[b] = logp;
         p.loss[b] = (float)(-logp);
@@ -500,6 +543,10 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
 
     // ---- C: gradient rows -----------------------------------------------------
     const bool fix = (logp != ninf) && (status == ASRK_ROW_OK);   // TF: no valid path -> dy = y
+    // occupancy(t, u) = alpha_t(u) beta_t(u) / p = ahat_t(u) bhat_t(u) K_t
+    if (fix)
+        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = __expf((float)(sC[t] + sD[t] - logp));
+    __syncthreads();
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
     const int* nxt = p.chain_next + (size_t)b * p.Ls;
     const int* fst = p.chain_first + (size_t)b * p.Ls;
@@ -535,22 +582,21 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         __syncwarp();
         const float* al = sal + t * Ub;
         const float* be = sbe + t * Ub;
+        const float Kt = sK[t];
         float ob = 0.f;
-        for (int j = lane; j <= L; j += 32)
-            ob += __expf((float)((double)al[2 * j] + (double)be[2 * j] - logp));
+        for (int j = lane; j <= L; j += 32) ob += al[2 * j] * be[2 * j];
         float extra = 0.f;
         for (int j = lane; j < L; j += 32) {
             const int c = eff[j];
-            if (c == p.blank) extra += __expf((float)((double)al[2 * j + 1] + (double)be[2 * j + 1] - logp));
+            if (c == p.blank) extra += al[2 * j + 1] * be[2 * j + 1];
             if (fst[j] && c != p.blank) {
                 float o = 0.f;
-                for (int k = j; k >= 0; k = nxt[k])
-                    o += __expf((float)((double)al[2 * k + 1] + (double)be[2 * k + 1] - logp));
-                g[c] = (__expf(slp[t * W + 1 + j]) - o) * scale;
+                for (int k = j; k >= 0; k = nxt[k]) o += al[2 * k + 1] * be[2 * k + 1];
+                g[c] = (slp[t * W + 1 + j] - o * Kt) * scale;
             }
         }
         ob = warp_sum(ob + extra);
-        if (lane == 0) g[p.blank] = (__expf(slp[t * W]) - ob) * scale;
+        if (lane == 0) g[p.blank] = (slp[t * W] - ob * Kt) * scale;
     }
 }
 
@@ -680,6 +726,7 @@ __global__ void lattice_kernel(Params p) {
 // ---------------------------------------------------------------------------
 template <int NV4>
 __global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
+    if (p.fused && *p.need_generic == 0) return;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= (long long)p.T * p.B) return;
@@ -882,6 +929,7 @@ static void bind_workspace(Params& p, void* workspace, const WsLayout& l) {
     p.beta = reinterpret_cast<float*>(ws + l.beta);
     p.coff = reinterpret_cast<double*>(ws + l.coff);
     p.logp = reinterpret_cast<double*>(ws + l.logp);
+    p.need_generic = reinterpret_cast<int*>(ws + l.flag);
 }
 
 extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stride_t, long long stride_b,
@@ -923,6 +971,7 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     const int nv4 = pick_nv4(p, logits, stride_t, stride_b, grad, gstride_t, gstride_b);
     p.fused = (nv4 > 0) ? 1 : 0;
     if (phases & ASRK_PHASE_CTC_PREP) {
+        if (cudaMemsetAsync(p.need_generic, 0, sizeof(int), stream) != cudaSuccess) return ASRK_E_CUDA;
         const int pt = ((label_stride > 0 ? label_stride : 1) + 31) / 32 * 32;
         prep_kernel<<<B, pt, sizeof(int) * (Ls + 40), stream>>>(p);
     }
