@@ -26,11 +26,12 @@
 //   * z-score: the helpers accumulate the per-bin column sums of every tile while
 //     they copy it out (fp32, shifted by the tile's first row so that nothing
 //     cancels), combine them per tile in fp64 in a fixed order (reproducible, no float
-//     atomics), and the CTA that retires the LAST tile of an utterance turns the tile
-//     partials into mean and 1/std.  A second, purely streaming kernel with the whole
-//     chip's memory parallelism normalises in place (the rows are largely still in
-//     L2).  [An in-kernel z-score by the retiring CTA was measured: one CTA's 448
-//     threads cannot keep enough L2 requests in flight -- 40 us per utterance.]
+//     atomics).  A tiny kernel turns the tile partials of every utterance into mean and
+//     1/std, and a purely streaming kernel with the whole chip's memory parallelism
+//     normalises in place (the rows are largely still in L2).  [Measured alternatives:
+//     an in-kernel z-score by the CTA that retires an utterance's last tile -- one
+//     CTA's 448 threads cannot keep enough L2 requests in flight, 40 us per utterance;
+//     per-tile release fence + counter in the helpers -- the membar costs 19 us.]
 #include <math.h>
 
 #include "asrk_common.cuh"
@@ -89,19 +90,21 @@ struct Params {
     int mode;
     float* out;
     // workspace
-    int* counters;           // [0] next tile, [1 + b] retired tiles of utterance b (zeroed per launch)
+    int* counters;           // [0] next tile (zeroed per launch)
+    int* tile_off_g;         // [B + 1] first tile of every utterance (written by CTA 0)
     double2* partials;       // [tiles][200]: per-tile column sums (sum y, sum y^2)
     float* stats;            // [B][3][200]: mean (hi, lo), 1/std
 };
 
 struct WsLayout {
-    size_t counters, gains, stats, partials, total;
+    size_t counters, tile_off, gains, stats, partials, total;
 };
 
 static WsLayout ws_layout(int batch, long long total_frames) {
     WsLayout l;
     size_t o = 0;
-    l.counters = o;  o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
+    l.counters = o;  o = align_up(o + sizeof(int) * 4, 256);
+    l.tile_off = o;  o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
     l.gains = o;     o = align_up(o + sizeof(float) * (size_t)batch, 256);
     l.stats = o;     o = align_up(o + sizeof(float) * 3 * kBins * (size_t)batch, 256);
     l.partials = o;
@@ -303,7 +306,6 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     float* s_col = reinterpret_cast<float*>(tile_off + kMaxBatch + 1);        // [4][3][200] helper column sums
     double* tab = reinterpret_cast<double*>(s_col + kHelperWarps * 3 * kBins);   // [1200], 16-byte aligned
     __shared__ Meta meta[kRing];
-    __shared__ int s_last;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -334,6 +336,8 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     __syncthreads();
     const int total_tiles = tile_off[p.batch];
     const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
+    if (blockIdx.x == 0 && want_stats)
+        for (int i = tid; i <= p.batch; i += kThreads) p.tile_off_g[i] = tile_off[i];
 
     if (warp < kFftWarps) {
         // ------------------------------ FFT warps ------------------------------
@@ -426,15 +430,15 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
         const int hw = warp - kFftWarps;                          // 0..3
         const int hth = hw * 32 + lane;
         const bool mix = (p.noise != nullptr);
-        // (helper thread 0) the next tile of this CTA, claimed one issue ahead so that
-        // the atomic's round trip is off the staging path
+        // Tile metadata is prepared one iteration before it is needed by the first lane of
+        // helper warp 1 (claim from the atomic counter, look the utterance up), the retire
+        // bookkeeping below runs on the first lane of helper warp 0: neither serialises the
+        // other, and neither round trip is on the staging path.
+        constexpr int kMetaThread = 32;
         int next_tile = total_tiles;
-        if (hth == 0) next_tile = atomicAdd(p.counters, 1);
-
-        // tile t: metadata, then start filling PCM stage t % kStages.  The async path
-        // returns with the copies in flight (one commit group per tile).
-        auto issue = [&](int t) {
-            if (hth == 0) {
+        if (hth == kMetaThread) next_tile = atomicAdd(p.counters, 1);
+        auto prepare_meta = [&](int t) {
+            if (hth == kMetaThread) {
                 Meta& mn = meta[t % kRing];
                 const int tile = next_tile;
                 if (tile < total_tiles) {
@@ -444,6 +448,11 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                     mn.valid = 0;
                 }
             }
+        };
+
+        // tile t (metadata prepared earlier): start filling PCM stage t % kStages.  The
+        // async path returns with the copies in flight (one commit group per tile).
+        auto issue = [&](int t) {
             bar_sync(kBarHelpers, kHelperThreads);
             if (t >= kStages) bar_sync(kBarPcmEmpty + (t % kStages), kPipeThreads);
             const Meta& m = meta[t % kRing];
@@ -493,11 +502,14 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
         };
 
 #pragma unroll 1
+        for (int t = 0; t <= kAhead; ++t) prepare_meta(t);
+#pragma unroll 1
         for (int t = 0; t < kAhead; ++t) issue(t);
         cp_async_wait<kAhead - 1>();
         bar_arrive(kBarPcmFull + 0, kPipeThreads);
         for (int t = 0;; ++t) {
             issue(t + kAhead);
+            prepare_meta(t + kAhead + 1);
             cp_async_wait<kAhead - 1>();          // everything but the newest group(s): tile t+1 has landed
             bar_arrive(kBarPcmFull + ((t + 1) % kStages), kPipeThreads);
             if (!meta[t % kRing].valid) break;
@@ -524,40 +536,36 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                 }
                 p.partials[(size_t)m.tile * kBins + k] = make_double2(a1, a2);
             }
-            // retire the tile (release); the CTA that retires the last tile of the utterance
-            // turns the partials into mean and 1/std (sklearn.preprocessing.scale, wav_util.py:79:
-            // std with ddof = 0, std < 10 eps -> 1)
-            bar_sync(kBarHelpers, kHelperThreads);
-            if (hth == 0) {
-                __threadfence();
-                const int old = atomicAdd(p.counters + 1 + m.b, 1);
-                s_last = (old + 1 == m.ntiles_b) ? 1 : 0;
-            }
-            bar_sync(kBarHelpers, kHelperThreads);
-            if (s_last) {
-                __threadfence();
-                const int t_lo = tile_off[m.b], t_hi = tile_off[m.b + 1];
-                for (int k = hth; k < kBins; k += kHelperThreads) {
-                    double a1 = 0.0, a2 = 0.0;
-                    for (int q = t_lo; q < t_hi; ++q) {
-                        const double2 v = __ldcg(p.partials + (size_t)q * kBins + k);
-                        a1 += v.x;
-                        a2 += v.y;
-                    }
-                    const double n = (double)m.nfr;
-                    const double mean = a1 / n;
-                    double var = a2 / n - mean * mean;
-                    if (var < 0.0) var = 0.0;
-                    double sd = sqrt(var);
-                    if (sd < 10.0 * 2.220446049250313e-16) sd = 1.0;
-                    const float mh = (float)mean;
-                    float* st = p.stats + (size_t)m.b * 3 * kBins;
-                    st[k] = mh;
-                    st[kBins + k] = (float)(mean - (double)mh);
-                    st[2 * kBins + k] = (float)(1.0 / sd);
-                }
-            }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// mean and 1/std of every utterance from its tiles' partial sums, one CTA each
+// (sklearn.preprocessing.scale, wav_util.py:79: std with ddof = 0, std < 10 eps -> 1)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stats_kernel(Params p) {
+    const int b = blockIdx.x;
+    const int t_lo = p.tile_off_g[b], t_hi = p.tile_off_g[b + 1];
+    const long long nfr = p.frame_offsets[b + 1] - p.frame_offsets[b];
+    for (int k = threadIdx.x; k < kBins; k += blockDim.x) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int q = t_lo; q < t_hi; ++q) {               // fixed order: reproducible
+            const double2 v = p.partials[(size_t)q * kBins + k];
+            a1 += v.x;
+            a2 += v.y;
+        }
+        const double n = (double)(nfr > 0 ? nfr : 1);
+        const double mean = a1 / n;
+        double var = a2 / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double sd = sqrt(var);
+        if (sd < 10.0 * 2.220446049250313e-16) sd = 1.0;
+        const float mh = (float)mean;
+        float* st = p.stats + (size_t)b * 3 * kBins;
+        st[k] = mh;
+        st[kBins + k] = (float)(mean - (double)mh);
+        st[2 * kBins + k] = (float)(1.0 / sd);
     }
 }
 
@@ -681,17 +689,20 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         p.mode = mode;
         p.out = out;
         p.counters = reinterpret_cast<int*>(ws + l.counters);
+        p.tile_off_g = reinterpret_cast<int*>(ws + l.tile_off);
         p.partials = reinterpret_cast<double2*>(ws + l.partials);
         p.stats = reinterpret_cast<float*>(ws + l.stats) + (size_t)b0 * 3 * kBins;
         if ((phases & ASRK_PHASE_SPEC_MAIN) &&
-            cudaMemsetAsync(p.counters, 0, sizeof(int) * (size_t)(nb + 1), stream) != cudaSuccess)
+            cudaMemsetAsync(p.counters, 0, sizeof(int) * 4, stream) != cudaSuccess)
             return ASRK_E_CUDA;
         if (phases & ASRK_PHASE_SPEC_MAIN) {
             if (sample_dtype == ASRK_DTYPE_I16) launch_main<false>(p, grid, stream);
             else launch_main<true>(p, grid, stream);
         }
-        if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE))
+        if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE)) {
+            stats_kernel<<<nb, 256, 0, stream>>>(p);
             normalize_kernel<<<dim3(16, nb), 256, 0, stream>>>(p);
+        }
     }
     return launch_status();
 }
