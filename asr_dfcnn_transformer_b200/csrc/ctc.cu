@@ -266,11 +266,7 @@ __device__ __forceinline__ void row_stats_generic(const float* row, int V, int l
 }
 
 template <int NV4, bool WANT_LSE>
-__global__ void __launch_bounds__(kRowWarps * 32) rows_kernel(Params p) {
-    if (WANT_LSE && p.fused && *p.need_generic == 0) return;   // every utterance took the fused kernel
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    if (row >= (long long)p.T * p.B) return;
+__device__ __forceinline__ void rows_body(const Params& p, long long row, int lane) {
     const int t = (int)(row / p.B), b = (int)(row % p.B);
     int tl = p.input_len[b];
     if (tl > p.T) tl = p.T;
@@ -303,6 +299,17 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_kernel(Params p) {
             dst[j] = x[c] - lse;
         }
     }
+}
+
+// one warp per (t,b) row, grid-stride (a no-op launch costs a launch, not a sweep)
+template <int NV4, bool WANT_LSE>
+__global__ void __launch_bounds__(kRowWarps * 32) rows_kernel(Params p) {
+    if (WANT_LSE && p.fused && *p.need_generic == 0) return;   // every utterance took the fused kernel
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)p.T * p.B;
+    for (long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * kRowWarps)
+        rows_body<NV4, WANT_LSE>(p, row, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -725,11 +732,7 @@ __global__ void lattice_kernel(Params p) {
 // grad
 // ---------------------------------------------------------------------------
 template <int NV4>
-__global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
-    if (p.fused && *p.need_generic == 0) return;
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    if (row >= (long long)p.T * p.B) return;
+__device__ __forceinline__ void grad_body(const Params& p, long long row, int lane) {
     const int t = (int)(row / p.B), b = (int)(row % p.B);
     float* g = p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b;
     const int tl = p.input_len[b];
@@ -806,6 +809,16 @@ __global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
     if (lane == 0) g[p.blank] = (__expf(lpl[0]) - (ob + extra)) * scale;
 }
 
+template <int NV4>
+__global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
+    if (p.fused && *p.need_generic == 0) return;
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)p.T * p.B;
+    for (long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * kRowWarps)
+        grad_body<NV4>(p, row, lane);
+}
+
 // ---------------------------------------------------------------------------
 // greedy decode: collapse repeats / drop blanks with a warp ballot + prefix count
 // ---------------------------------------------------------------------------
@@ -844,6 +857,26 @@ __global__ void __launch_bounds__(128) collapse_kernel(Params p) {
     }
 }
 
+// [sum of the losses of the rows TF would accept, number of such rows] in float64, one
+// CTA, fixed order (reproducible): the operand of the path's only collective.
+__global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const int* row_status, int B, double* out2) {
+    __shared__ double s_sum[256];
+    __shared__ int s_cnt[256];
+    double a = 0.0;
+    int c = 0;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        if (row_status == nullptr || row_status[b] == ASRK_ROW_OK) { a += (double)loss[b]; ++c; }
+    }
+    s_sum[threadIdx.x] = a;
+    s_cnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_sum[threadIdx.x] += s_sum[threadIdx.x + o]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = s_sum[0]; out2[1] = (double)s_cnt[0]; }
+}
+
 static int pick_nv4(const Params& p, const void* a, long long st, long long sb, const void* g,
                     long long gt, long long gb) {
     // vector path: V % 4 == 0, 16-byte aligned bases and strides, V <= 2048
@@ -860,7 +893,9 @@ static int pick_nv4(const Params& p, const void* a, long long st, long long sb, 
 template <bool WANT_LSE>
 static void launch_rows(const Params& p, int nv4, cudaStream_t stream) {
     const long long rows = (long long)p.T * p.B;
-    const unsigned grid = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+    long long want = (rows + kRowWarps - 1) / kRowWarps;
+    const long long cap = (long long)sm_count() * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     switch (nv4) {
         case 4: rows_kernel<4, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
         case 8: rows_kernel<8, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
@@ -889,7 +924,9 @@ static void launch_fused(const Params& p, int nv4, cudaStream_t stream) {
 
 static void launch_grad(const Params& p, int nv4, cudaStream_t stream) {
     const long long rows = (long long)p.T * p.B;
-    const unsigned grid = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+    long long want = (rows + kRowWarps - 1) / kRowWarps;
+    const long long cap = (long long)sm_count() * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     switch (nv4) {
         case 4: grad_kernel<4><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
         case 8: grad_kernel<8><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
@@ -1029,5 +1066,12 @@ extern "C" int asrk_ctc_greedy_decode_run(const float* logits, long long stride_
         launch_rows<false>(p, nv4, stream);
     }
     collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
+    return launch_status();
+}
+
+extern "C" int asrk_ctc_loss_sum_run(const float* loss, const int* row_status, int B, double* out2,
+                                     asrk_stream_t stream_) {
+    if (B < 0 || !out2 || (B > 0 && !loss)) return ASRK_E_BADARG;
+    loss_sum_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(loss, row_status, B, out2);
     return launch_status();
 }

@@ -102,6 +102,18 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
     return CtcResult(loss, grad, status, tokens, tlen, nsl)
 
 
+def loss_sum(loss, row_status=None, out=None, stream=None):
+    """[sum of the accepted rows' losses, their number] as a float64 device tensor of 2
+    (the operand of the batch mean / of the cross-rank all-reduce)."""
+    torch = _lib.require_cuda()
+    if out is None:
+        out = torch.empty(2, dtype=torch.float64, device=loss.device)
+    st = _lib.lib().asrk_ctc_loss_sum_run(_lib.ptr(loss), _lib.ptr(row_status), int(loss.numel()), _lib.ptr(out),
+                                          _lib.stream_ptr(stream))
+    _lib.check(st, "asrk_ctc_loss_sum_run")
+    return out
+
+
 def _raise_on_status(status):
     st = status.cpu().numpy()
     bad = np.nonzero(st == _lib.ROW_NOT_ENOUGH_TIME)[0]

@@ -37,6 +37,15 @@ POOL = 3          # distinct device-resident batches rotated through the timed l
 METRIC = "audio-sec/sec (fbank+CTC loss+grad)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from
+    the committed `ncu --set full` capture of this workload (profiles/traffic.json)."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["dram_bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -318,6 +327,21 @@ def main():
         reference_arm(args, rank, world)
         return
 
+    # ---- (0) CPU baseline on rank 0 (N = 1 only), BEFORE CUDA is initialised so that the
+    # worker processes can be forked safely ---------------------------------------------
+    cpu = None
+    hb0 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_utt = max(16, min(64, 2 * cores))
+        hb0 = make_batch(2000)
+        cpu_sample(hb0, min(n_utt, cores), cores)          # warm the pool / page cache
+        a, tf_, tc_ = cpu_sample(hb0, n_utt, cores)
+        cpu = {"value": a / (tf_ + tc_), "unit": "audio-sec/sec", "cores": cores, "kind": "port",
+               "sample": "first %d utterances (%.0f audio-s) of the C2 batch: oracle/fbank_ref.py features "
+                         "(per-frame scipy FFT, %d processes, %.2f s) + oracle/ctc_ref.c float32 CTC "
+                         "loss/grad (OpenMP, %.2f s)" % (n_utt, a, cores, tf_, tc_)}
+
     import torch
     import torch.distributed as dist
     from asr_dfcnn_transformer_b200 import _lib
@@ -330,19 +354,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- data: POOL distinct batches per rank, resident in HBM --------------
-    pool = [DeviceBatch(make_batch(2000 + 100 * rank + i), dev, torch) for i in range(POOL)]
+    pool = [DeviceBatch(hb0 if (i == 0 and rank == 0 and hb0 is not None) else make_batch(2000 + 100 * rank + i),
+                        dev, torch) for i in range(POOL)]
     audio_per_step = float(np.mean([d.audio_s for d in pool]))
     red = torch.zeros(2, dtype=torch.float64, device=dev)
     side = torch.cuda.Stream(device=dev)
 
     def reduce_loss(r, db):
-        # the path's only collective: all-reduce of [sum loss, n], off the critical path
-        red[0] = r.loss.sum(dtype=torch.float64)
-        red[1] = float(db.B)
+        # the path's only collective: all-reduce of [sum loss, n] (one tiny kernel fills
+        # the operand), on a side stream so that it overlaps the next step
+        from asr_dfcnn_transformer_b200 import ctc, pipeline
+        ctc.loss_sum(r.loss, r.row_status, out=red)
         if world > 1:
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                dist.all_reduce(red)
+            pipeline.all_reduce_loss(red, stream=side)
 
     def barrier():
         if world > 1:
@@ -354,6 +378,7 @@ def main():
         r = run_step(pool[i % POOL])
         reduce_loss(r, pool[i % POOL])
     barrier()
+    loss_check = red.clone()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -427,17 +452,6 @@ def main():
         dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
     e2e_value = float(t[1]) / (float(t[0]) * 1e-3)
 
-    # ---- (4) CPU baseline on rank 0 (N = 1 only) ----------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        n_utt = max(16, min(64, 2 * cores))
-        a, tf_, tc_ = cpu_sample(pool[0].hb, n_utt, cores)
-        cpu = {"value": a / (tf_ + tc_), "unit": "audio-sec/sec", "cores": cores, "kind": "port",
-               "sample": "first %d utterances (%.0f audio-s) of the C2 batch: oracle/fbank_ref.py features "
-                         "(per-frame scipy FFT, %d processes, %.2f s) + oracle/ctc_ref.c float32 CTC "
-                         "loss/grad (OpenMP, %.2f s)" % (n_utt, a, cores, tf_, tc_)}
-
     if rank == 0:
         peak, peak_src = peaks()
         dom = max(("spec_main", "ctc_fused", "ctc_rows", "ctc_grad"), key=lambda k: kms[k])
@@ -457,14 +471,16 @@ def main():
                        "l2": "inputs larger than L2: %d distinct batches rotated, ~%.0f MB touched per step"
                              % (POOL, (step_alg + bc / 2) / 1e6)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg,
                          "step_frac": (step_alg / (ms / args.steps * 1e-3) / 1e9) / peak / world},
             "kernel_ms": kms,
+            "loss_mean": float(loss_check[0] / max(float(loss_check[1]), 1.0)),
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
-            "gpu_launches": 8 * args.steps,
+            # per step: spectrogram, stats, z-score, CTC prep, fused, rows, lattice, grad, loss sum
+            "gpu_launches": 9 * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -149,6 +149,14 @@ int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long st
                            float* neg_sum_logits,               /* device float32 [B] or NULL     */
                            void* workspace, size_t workspace_bytes, asrk_stream_t stream);
 
+/* Batch reduction feeding the path's only collective (tf.reduce_mean(self.loss),
+ * acoustic_model2.py:83): out2[0] = sum of loss[b] over the rows with row_status[b] ==
+ * ASRK_ROW_OK (all rows when row_status == NULL), out2[1] = their number, float64,
+ * summed in a fixed order.  The caller all-reduces out2 across ranks. */
+int asrk_ctc_loss_sum_run(const float* loss, const int* row_status, int B,
+                          double* out2, /* device float64 [2] */
+                          asrk_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Part 3: greedy CTC decode
  *   replaces  tf.nn.ctc_greedy_decoder, lm_and_am/model/acoustic_model2.py:69
