@@ -75,7 +75,7 @@ struct Params {
 // Utterances whose lattice fits one warp (L <= 31 labels -> 32 state pairs) and whose
 // per-frame scalars + gathered log-probabilities + alpha + beta fit the shared-memory
 // budget take the fused CTA-per-utterance kernel.
-constexpr int kSmallSmemFloats = 16 * 1024;   // 64 KB per CTA
+constexpr int kSmallSmemFloats = 15 * 1024;   // 60 KB per CTA (+ one row buffer per warp)
 __host__ __device__ __forceinline__ bool small_lattice(int L, int T) {
     return L <= 31 && (long long)T * (5 * L + 14) <= kSmallSmemFloats;
 }
@@ -204,6 +204,23 @@ __device__ __forceinline__ void load_row(const float* row, int V4, int lane, Row
         if (i < V4) r.v[k] = __ldg(x4 + i);
         else r.v[k] = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
     }
+}
+
+// the same from a row staged in shared memory
+template <int NV4>
+__device__ __forceinline__ void lds_row(const float4* rb, int V4, int lane, RowRegs<NV4>& r) {
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+        const int i = lane + 32 * k;
+        if (i < V4) r.v[k] = rb[i];
+        else r.v[k] = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+    }
+}
+// start the copy of one row into the warp's buffer: 16-byte LDGSTS through L2 only
+__device__ __forceinline__ void issue_row(float4* rb, const float* row, int V4, int lane) {
+    const float4* x4 = reinterpret_cast<const float4*>(row);
+    for (int i = lane; i < V4; i += 32) cp_async16(rb + i, x4 + i, 16);
+    cp_async_commit();
 }
 
 // first maximum over the row: strict '>' scan order == lowest index among equals
@@ -398,22 +415,29 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
     float* sbe = sal + T * Ub;                  // [T][Ub]
     const int* eff = p.eff_labels + (size_t)b * p.Ls;
     const int V4 = p.V >> 2;
+    // one row buffer per warp behind the lattice region: the next row of the warp arrives
+    // by cp.async while the current one is reduced, so HBM / L2 latency is off the chain
+    float4* rb = reinterpret_cast<float4*>(sm + kSmallSmemFloats) + (size_t)warp * V4;
+    const float* xb = p.logits + (size_t)b * p.stride_b;
 
     // ---- A: row statistics + gather -----------------------------------------
+    const int gc = (lane == 0) ? p.blank : ((lane < W) ? eff[lane - 1] : 0);   // class gathered by this lane
+    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane);
     for (int t = warp; t < T; t += kRowWarps) {
-        const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
+        cp_async_wait<0>();
+        __syncwarp();
         RowRegs<NV4> r;
-        load_row(x, V4, lane, r);
+        lds_row(rb, V4, lane, r);
+        const float xg = reinterpret_cast<const float*>(rb)[gc];
+        __syncwarp();
+        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane);
         float m;
         int am;
         row_argmax(r, lane, m, am);
         const float ssum = row_sumexp(r, m);
         const float lse = m + __logf(ssum);
         if (lane == 0) { slse[t] = lse; smax[t] = m; samax[t] = am; }
-        for (int j = lane; j < W; j += 32) {
-            const int c = (j == 0) ? p.blank : eff[j - 1];
-            slp[t * W + j] = __expf(x[c] - lse);          // y_t(l'_j), linear domain
-        }
+        if (lane < W) slp[t * W + lane] = __expf(xg - lse);          // y_t(l'_j), linear domain
     }
     __syncthreads();
 
@@ -437,10 +461,12 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
             a_b = slp[0];
             if (L >= 1) a_l = slp[1];
         }
+        float yb_n = 0.f, yl_n = 0.f;            // y of the next frame, loaded ahead of the chain
+        if (T > 1) { yb_n = slp[W]; yl_n = has_lab ? slp[W + 1 + i] : 0.f; }
         for (int t = 0; t < T; ++t) {
             if (t > 0) {
-                const float yb = slp[t * W];
-                const float yl = has_lab ? slp[t * W + 1 + i] : 0.f;
+                const float yb = yb_n, yl = yl_n;
+                if (t + 1 < T) { yb_n = slp[(t + 1) * W]; yl_n = has_lab ? slp[(t + 1) * W + 1 + i] : 0.f; }
                 float p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
                 if (i == 0) p1 = 0.f;
                 const float nb = yb * (a_b + p1);
@@ -449,7 +475,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
                 a_l = nl;
             }
             const float c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(a_b, a_l))));
-            const float inv = (c > 0.f) ? __frcp_rn(c) : 0.f;
+            const float inv = (c > 0.f) ? __fdividef(1.0f, c) : 0.f;   // any positive scale is exact algebra
             a_b *= inv;
             a_l *= inv;
             float* o = sal + t * Ub;
@@ -470,10 +496,12 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
                 b_b = 1.f;
                 if (L >= 1) b_l = 1.f;
             }
+            float yb_n = 0.f, yl_n = 0.f;
+            if (T > 1) { yb_n = slp[(T - 1) * W]; yl_n = has_lab ? slp[(T - 1) * W + i] : 0.f; }
             for (int t = T - 1; t >= 0; --t) {
                 if (t < T - 1) {
-                    const float yb = slp[(t + 1) * W];
-                    const float yl = has_lab ? slp[(t + 1) * W + i] : 0.f;
+                    const float yb = yb_n, yl = yl_n;
+                    if (t >= 1) { yb_n = slp[t * W]; yl_n = has_lab ? slp[t * W + i] : 0.f; }
                     const float e_b = b_b * yb;
                     const float e_l = b_l * yl;
                     float n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
@@ -484,7 +512,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
                     b_l = has_lab ? nbl : 0.f;
                 }
                 const float d = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(b_b, b_l))));
-                const float inv = (d > 0.f) ? __frcp_rn(d) : 0.f;
+                const float inv = (d > 0.f) ? __fdividef(1.0f, d) : 0.f;
                 b_b *= inv;
                 b_l *= inv;
                 float* o = sbe + t * Ub;
@@ -555,8 +583,13 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = __expf((float)(sC[t] + sD[t] - logp));
     __syncthreads();
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
-    const int* nxt = p.chain_next + (size_t)b * p.Ls;
-    const int* fst = p.chain_first + (size_t)b * p.Ls;
+    // lane j < L owns label position j: the positions that carry the same label (one
+    // MATCH), so repeated labels are summed in a fixed order without touching memory
+    const int my_lab = (lane < L) ? eff[lane] : -1 - lane;
+    const unsigned same = __match_any_sync(0xffffffffu, my_lab);
+    const bool owner = (lane < L) && ((int)__ffs(same) - 1 == lane) && (my_lab != p.blank);
+    const bool is_blank_lab = (lane < L) && (my_lab == p.blank);
+    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane);      // L2 hits: read a moment ago
     for (int t = warp; t < p.T; t += kRowWarps) {
         float* g = p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b;
         float4* g4 = reinterpret_cast<float4*>(g);
@@ -565,14 +598,17 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
             for (int k = lane; k < V4; k += 32) stg_stream(g4 + k, z);
             continue;
         }
-        const float4* x4 = reinterpret_cast<const float4*>(p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b);
         const float lse = slse[t];
+        cp_async_wait<0>();
+        __syncwarp();
         float4 v[NV4];
 #pragma unroll
         for (int k = 0; k < NV4; ++k) {
             const int idx = lane + 32 * k;
-            if (idx < V4) v[k] = ldg_stream(x4 + idx);
+            if (idx < V4) v[k] = rb[idx];
         }
+        __syncwarp();
+        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane);
 #pragma unroll
         for (int k = 0; k < NV4; ++k) {
             const int idx = lane + 32 * k;
@@ -590,19 +626,17 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         const float* al = sal + t * Ub;
         const float* be = sbe + t * Ub;
         const float Kt = sK[t];
-        float ob = 0.f;
-        for (int j = lane; j <= L; j += 32) ob += al[2 * j] * be[2 * j];
-        float extra = 0.f;
-        for (int j = lane; j < L; j += 32) {
-            const int c = eff[j];
-            if (c == p.blank) extra += al[2 * j + 1] * be[2 * j + 1];
-            if (fst[j] && c != p.blank) {
-                float o = 0.f;
-                for (int k = j; k >= 0; k = nxt[k]) o += al[2 * k + 1] * be[2 * k + 1];
-                g[c] = (slp[t * W + 1 + j] - o * Kt) * scale;
+        float ob = (lane <= L) ? al[2 * lane] * be[2 * lane] : 0.f;          // blank states (L <= 31)
+        if (is_blank_lab) ob += al[2 * lane + 1] * be[2 * lane + 1];           // a label equal to the blank index
+        if (owner) {
+            float o = 0.f;
+            for (unsigned mset = same; mset; mset &= mset - 1) {
+                const int k = __ffs(mset) - 1;
+                o += al[2 * k + 1] * be[2 * k + 1];
             }
+            g[my_lab] = (slp[t * W + 1 + lane] - o * Kt) * scale;
         }
-        ob = warp_sum(ob + extra);
+        ob = warp_sum(ob);
         if (lane == 0) g[p.blank] = (slp[t * W] - ob * Kt) * scale;
     }
 }
@@ -906,7 +940,7 @@ static void launch_rows(const Params& p, int nv4, cudaStream_t stream) {
 }
 
 static void launch_fused(const Params& p, int nv4, cudaStream_t stream) {
-    const size_t smem = sizeof(float) * kSmallSmemFloats;
+    const size_t smem = sizeof(float) * (kSmallSmemFloats + (size_t)kRowWarps * p.V);
     switch (nv4) {
 #define ASRK_FUSED_CASE(N)                                                                              \
     case N:                                                                                             \
