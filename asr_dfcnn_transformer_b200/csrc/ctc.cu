@@ -216,10 +216,11 @@ __device__ __forceinline__ void lds_row(const float4* rb, int V4, int lane, RowR
         else r.v[k] = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
     }
 }
-// start the copy of one row into the warp's buffer: 16-byte LDGSTS through L2 only
-__device__ __forceinline__ void issue_row(float4* rb, const float* row, int V4, int lane) {
+// start the copy of one row into the warp's buffer: 16-byte LDGSTS through L2 only, with
+// an L2 eviction priority (first read: keep the row for the gradient pass; second: drop it)
+__device__ __forceinline__ void issue_row(float4* rb, const float* row, int V4, int lane, uint64_t policy) {
     const float4* x4 = reinterpret_cast<const float4*>(row);
-    for (int i = lane; i < V4; i += 32) cp_async16(rb + i, x4 + i, 16);
+    for (int i = lane; i < V4; i += 32) cp_async16_hint(rb + i, x4 + i, policy);
     cp_async_commit();
 }
 
@@ -422,7 +423,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
 
     // ---- A: row statistics + gather -----------------------------------------
     const int gc = (lane == 0) ? p.blank : ((lane < W) ? eff[lane - 1] : 0);   // class gathered by this lane
-    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane);
+    const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, keep);
     for (int t = warp; t < T; t += kRowWarps) {
         cp_async_wait<0>();
         __syncwarp();
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         lds_row(rb, V4, lane, r);
         const float xg = reinterpret_cast<const float*>(rb)[gc];
         __syncwarp();
-        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane);
+        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane, keep);
         float m;
         int am;
         row_argmax(r, lane, m, am);
@@ -589,13 +591,13 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
     const unsigned same = __match_any_sync(0xffffffffu, my_lab);
     const bool owner = (lane < L) && ((int)__ffs(same) - 1 == lane) && (my_lab != p.blank);
     const bool is_blank_lab = (lane < L) && (my_lab == p.blank);
-    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane);      // L2 hits: read a moment ago
+    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, drop);      // L2 hits: read a moment ago
     for (int t = warp; t < p.T; t += kRowWarps) {
         float* g = p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b;
         float4* g4 = reinterpret_cast<float4*>(g);
         if (t >= T) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int k = lane; k < V4; k += 32) stg_stream(g4 + k, z);
+            for (int k = lane; k < V4; k += 32) stg_evict_first(g4 + k, z);
             continue;
         }
         const float lse = slse[t];
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
             if (idx < V4) v[k] = rb[idx];
         }
         __syncwarp();
-        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane);
+        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane, drop);
 #pragma unroll
         for (int k = 0; k < NV4; ++k) {
             const int idx = lane + 32 * k;
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
                 y.y = __expf(v[k].y - lse) * scale;
                 y.z = __expf(v[k].z - lse) * scale;
                 y.w = __expf(v[k].w - lse) * scale;
-                stg_stream(g4 + idx, y);
+                stg_evict_first(g4 + idx, y);
             }
         }
         if (!fix) continue;

@@ -467,6 +467,8 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
 
         // rows of tile t to global memory (coalesced), and this warp's column sums of
         // (y - c), (y - c)^2 with c = the warp's first row, into shared memory
+        // the un-normalised rows are read again by the z-score kernel: keep them in L2
+        const uint64_t keep = want_stats ? l2_policy_evict_last() : l2_policy_evict_first();
         auto epilogue = [&](int t) {
             const Meta& m = meta[t % kRing];
             const float* ot = outt + (t & 1) * (kTile * kOutStride);
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
                     const int k = lane + 32 * e;
                     if (k < kBins) {
                         const float y = ot[f * kOutStride + k];
-                        orow[k] = y;
+                        stg_hint(orow + k, y, keep);
                         if (ff == 0) c[e] = y;
                         const float d = y - c[e];
                         sm[e] += d;
@@ -584,12 +586,13 @@ __global__ void __launch_bounds__(256) normalize_kernel(Params p) {
     const long long n4 = nfr * (kBins / 4);
     const long long stride = (long long)gridDim.x * blockDim.x;
     constexpr int kU = 4;
+    const uint64_t drop = l2_policy_evict_first();
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += kU * stride) {
         float4 v[kU];
 #pragma unroll
         for (int e = 0; e < kU; ++e) {
             const long long i = i0 + e * stride;
-            if (i < n4) v[e] = __ldcg(base + i);
+            if (i < n4) v[e] = ldg_hint(base + i, drop);
         }
 #pragma unroll
         for (int e = 0; e < kU; ++e) {
@@ -604,7 +607,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(Params p) {
                 o.y = ((v[e].y - mh.y) - ml.y) * iv.y;
                 o.z = ((v[e].z - mh.z) - ml.z) * iv.z;
                 o.w = ((v[e].w - mh.w) - ml.w) * iv.w;
-                base[i] = o;
+                stg_evict_first(base + i, o);
             }
         }
     }
