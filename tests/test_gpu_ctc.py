@@ -176,3 +176,41 @@ def test_tf_decoder_surface_and_decode_ctc():
     ids = ctc.decode_ctc(np.transpose(p, (1, 0, 2)).astype(np.float32), 30)
     ref1, _ = ctc_ref.greedy_decode(np.log(p.astype(np.float32) + np.float32(1e-7)), [30])
     assert ids.tolist() == ref1[0]
+
+
+def test_full_size_c2_batch_properties():
+    """BASELINE.json configs[1] at full size: properties that do not need the oracle on all
+    of it -- every valid gradient row sums to 0 (softmax minus a distribution), rows past
+    input_len are exactly 0, the loss is finite and positive, and the batch reduction kernel
+    agrees with a float64 sum; a slice of utterances is checked against the oracle."""
+    import torch
+    import bench
+    from asr_dfcnn_transformer_b200 import ctc
+    hb = bench.make_batch(2001)
+    x, labels, ll, il = hb["logits"], hb["labels"], hb["label_len"], hb["input_len"]
+    r = ctc.ctc_loss_grad(torch.as_tensor(x).cuda(), labels, ll, il, x.shape[2] - 1, decode=True)
+    loss = r.loss.cpu().numpy()
+    grad = r.grad.cpu().numpy()
+    assert int(r.row_status.max()) == 0 and np.all(np.isfinite(loss)) and np.all(loss > 0)
+    T = x.shape[0]
+    valid = np.arange(T)[:, None] < il[None, :]
+    assert np.abs(grad.sum(-1))[valid].max() < 2e-5
+    assert not grad[~valid].any()
+    red = ctc.loss_sum(r.loss, r.row_status).cpu().numpy()
+    assert red[1] == 256 and abs(red[0] - loss.astype(np.float64).sum()) < 1e-6 * red[0]
+    sl = slice(40, 56)
+    rl, rg, ok = ctc_ref.ctc_loss_grad_batch(np.ascontiguousarray(x[:, sl]), labels[sl], ll[sl], il[sl], x.shape[2] - 1)
+    np.testing.assert_allclose(loss[sl], rl, rtol=CTC_RTOL, atol=CTC_ATOL)
+    assert_ctc_grad_close(grad[:, sl], rg, x[:, sl], il[sl])
+    ref_tok, _ = ctc_ref.greedy_decode(x, il)
+    assert ctc.tokens_to_lists(r.tokens, r.token_len) == ref_tok
+
+
+def test_edge_shapes():
+    """T = 1, empty label, single class besides blank, batch of one, label length == T-repeats."""
+    rng = np.random.default_rng(9)
+    x, labels, ll, il = synth.ctc_batch(rng, [1, 1, 5, 4], 6, 0, 1)
+    ll[0] = 0                                   # empty label with one frame: p = y(blank)
+    _check(x, labels, ll, il, 5)
+    x = rng.standard_normal((7, 1, 2)).astype(np.float32)
+    _check(x, np.array([[0, 0, 0]]), np.array([3]), np.array([5]), 1)      # "0 _ 0 _ 0": the only path

@@ -141,3 +141,60 @@ def test_loader_batch_assembly(tmp_path):
         err = zscore_feature_err(got[r, :n], ref, fbank_ref.compute_fbank_unnormalised(sigs[i]))
         assert err <= FEATURE_TOL, (i, err)
         assert not got[r, n:].any()
+
+
+def test_batch_larger_than_one_launch_slice():
+    """More utterances than the kernel's per-launch prefix array (2047): the C ABI slices
+    the batch; every utterance must still come out right (1- and 2-frame utterances)."""
+    rng = np.random.default_rng(3)
+    base = [synth.g1_white(rng, 400), synth.g2_voiced(rng, 560), synth.g1_white(rng, 401)]
+    sigs = [base[i % 3] for i in range(2100)]
+    out, fo = _gpu(sigs, "fbank_raw")
+    refs = [fbank_ref.compute_fbank_unnormalised(s) for s in base]
+    assert fo[-1] == sum(r.shape[0] for r in refs) * 700
+    for i in (0, 1, 2, 2045, 2046, 2047, 2048, 2049, 2099):
+        assert feature_err(out[fo[i]:fo[i + 1]], refs[i % 3]) <= FEATURE_TOL, i
+    out, fo = _gpu(sigs[:2050], "fbank")                     # z-scored: 1-frame utterances are all zeros
+    for i in (0, 2046, 2047, 2049):
+        ref = fbank_ref.compute_fbank(sigs[i])
+        assert feature_err(out[fo[i]:fo[i + 1]], ref) <= FEATURE_TOL, i
+
+
+def test_unaligned_sample_offsets_scalar_path():
+    """Utterance starts that are not 16-byte aligned take the synchronous staging path."""
+    import torch
+    from asr_dfcnn_transformer_b200 import features
+    rng = np.random.default_rng(4)
+    a, b = synth.g2_voiced(rng, 8000), synth.g1_white(rng, 4321)
+    buf = np.concatenate([np.zeros(3, np.int16), a, np.zeros(5, np.int16), b])
+    so = np.array([3, 3 + len(a) + 5], dtype=np.int64)
+    sc = np.array([len(a), len(b)], dtype=np.int64)
+    nf = [features.n_frames_for(len(a)), features.n_frames_for(len(b))]
+    fo = np.array([0, nf[0], nf[0] + nf[1]], dtype=np.int64)
+    dev = torch.device("cuda")
+    out = features.spectrogram_device(torch.from_numpy(buf).to(dev), torch.from_numpy(so).to(dev),
+                                      torch.from_numpy(sc).to(dev), torch.from_numpy(fo).to(dev), 2, int(fo[-1]),
+                                      "fbank").cpu().numpy()
+    for i, s in enumerate((a, b)):
+        ref = fbank_ref.compute_fbank(s)
+        err = zscore_feature_err(out[fo[i]:fo[i + 1]], ref, fbank_ref.compute_fbank_unnormalised(s))
+        assert err <= FEATURE_TOL, (i, err)
+
+
+def test_full_size_c2_batch_properties():
+    """BASELINE.json configs[1] at full size (256 utterances of 3..7 s): size-independent
+    properties of the z-scored output -- every column of every utterance has mean 0 and
+    standard deviation 1 (or is constant), and a spot-checked utterance matches the oracle."""
+    import bench
+    hb = bench.make_batch(2000)
+    out, fo = _gpu(hb["pcm"], "fbank")
+    assert fo[-1] == int(hb["nfr"].sum())
+    for i in range(0, 256, 7):
+        y = out[fo[i]:fo[i + 1]].astype(np.float64)
+        assert np.abs(y.mean(axis=0)).max() < 2e-4
+        sd = y.std(axis=0)
+        assert np.all((np.abs(sd - 1.0) < 2e-3) | (sd == 0.0))
+    i = 101
+    ref = fbank_ref.compute_fbank(hb["pcm"][i])
+    err = zscore_feature_err(out[fo[i]:fo[i + 1]], ref, fbank_ref.compute_fbank_unnormalised(hb["pcm"][i]))
+    assert err <= FEATURE_TOL, err
