@@ -363,6 +363,39 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     return warp_max(r);
 }
 
+// log2(2^a + 2^b [+ 2^c]) in fp32, branch-free, one MUFU per exp / log: the exp
+// arguments are <= 0 (flush below -126 is exact enough: 2^-126 of the column's mass), the
+// log argument is in [1, 3] where lg2.approx is good to 2^-22 absolute; -inf operands are
+// zeros and all -inf stays -inf (m + lg2(0)).
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lse2_log2(float a, float b) {
+    const float m = fmaxf(a, b);
+    const float ms = (m == kNegInf) ? 0.f : m;
+    return m + lg2_fast(ex2_fast(a - ms) + ex2_fast(b - ms));
+}
+__device__ __forceinline__ float lse3_log2(float a, float b, float c) {
+    const float m = fmaxf(fmaxf(a, b), c);
+    const float ms = (m == kNegInf) ? 0.f : m;
+    return m + lg2_fast(ex2_fast(a - ms) + ex2_fast(b - ms) + ex2_fast(c - ms));
+}
+// warp maximum of arbitrary-sign floats with ONE REDUX: floats order like the unsigned
+// patterns  bits ^ (sign ? 0xffffffff : 0x80000000)
+__device__ __forceinline__ float warp_max_redux(float v) {
+    const unsigned b = __float_as_uint(v);
+    const unsigned key = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    const unsigned m = __reduce_max_sync(0xffffffffu, key);
+    return __uint_as_float(m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
 // ---------------------------------------------------------------------------
 // fused CTA-per-utterance kernel (small lattices: the AISHELL-shaped case)
 // ---------------------------------------------------------------------------
@@ -439,17 +472,18 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         const float ssum = row_sumexp(r, m);
         const float lse = m + __logf(ssum);
         if (lane == 0) { slse[t] = lse; smax[t] = m; samax[t] = am; }
-        if (lane < W) slp[t * W + lane] = __expf(xg - lse);          // y_t(l'_j), linear domain
+        if (lane < W) slp[t * W + lane] = (xg - lse) * 1.4426950408889634f;   // log2 y_t(l'_j)
     }
     __syncthreads();
 
     // ---- B: alpha || beta || greedy collapse ----------------------------------
-    // Linear-domain recursions, rescaled by the column maximum at every frame (one
-    // REDUX: positive floats order like their bit patterns), so a step is one shuffle,
-    // four adds/multiplies, one REDUX and one reciprocal -- no exp / log on the chain.
-    // True values: alpha_t = ahat_t * exp(sum_{s<=t} log c_s), beta_t (which excludes
-    // y_t, TF convention) = bhat_t * exp(sum_{s>=t} log d_s); the logs go to shared
-    // memory and are prefix-summed in double after the sweeps.
+    // Log2-domain recursions in fp32, each column stored RELATIVE to its maximum (one
+    // REDUX per frame on order-preserving bit patterns), so stored values are <= 0 and
+    // small in magnitude: no drift with T (the absolute level, ~ -10 T, lives in the
+    // per-frame maxima, prefix-summed in double afterwards) and no underflow of the
+    // states that matter (a linear-domain variant rescaled by the column maximum was
+    // measured 2x faster per step but crushed low-mass terminal states into denormals).
+    //   alpha_t(u) = 2^(ahat_t(u) + sum_{s<=t} c_s),  beta_t(u) (excludes y_t, TF) = 2^(bhat_t(u) + sum_{s>=t} d_s)
     const int i = lane;
     const int lab_i = (i < L) ? eff[i] : -1;
     const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
@@ -458,65 +492,65 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
     if (warp == 0) {
         // alpha: pair (blank 2i, label 2i+1)
         const bool has_lab = (i < L);
-        float a_b = 0.f, a_l = 0.f;
+        float a_b = kNegInf, a_l = kNegInf;
         if (i == 0) {
             a_b = slp[0];
             if (L >= 1) a_l = slp[1];
         }
-        float yb_n = 0.f, yl_n = 0.f;            // y of the next frame, loaded ahead of the chain
-        if (T > 1) { yb_n = slp[W]; yl_n = has_lab ? slp[W + 1 + i] : 0.f; }
+        float yb_n = 0.f, yl_n = 0.f;            // log2 y of the next frame, loaded ahead of the chain
+        if (T > 1) { yb_n = slp[W]; yl_n = has_lab ? slp[W + 1 + i] : kNegInf; }
         for (int t = 0; t < T; ++t) {
             if (t > 0) {
                 const float yb = yb_n, yl = yl_n;
-                if (t + 1 < T) { yb_n = slp[(t + 1) * W]; yl_n = has_lab ? slp[(t + 1) * W + 1 + i] : 0.f; }
+                if (t + 1 < T) { yb_n = slp[(t + 1) * W]; yl_n = has_lab ? slp[(t + 1) * W + 1 + i] : kNegInf; }
                 float p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
-                if (i == 0) p1 = 0.f;
-                const float nb = yb * (a_b + p1);
-                const float nl = yl * (a_l + a_b + (skip ? p1 : 0.f));
-                a_b = has_blank ? nb : 0.f;
+                if (i == 0) p1 = kNegInf;
+                const float nb = yb + lse2_log2(a_b, p1);
+                const float nl = yl + lse3_log2(a_l, a_b, skip ? p1 : kNegInf);
+                a_b = has_blank ? nb : kNegInf;
                 a_l = nl;
             }
-            const float c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(a_b, a_l))));
-            const float inv = (c > 0.f) ? __fdividef(1.0f, c) : 0.f;   // any positive scale is exact algebra
-            a_b *= inv;
-            a_l *= inv;
+            const float c = warp_max_redux(fmaxf(a_b, a_l));
+            const float sub = (c == kNegInf) ? 0.f : c;      // all -inf: no valid prefix
+            a_b -= sub;
+            a_l -= sub;
             float* o = sal + t * Ub;
             if (has_blank) o[2 * i] = a_b;
             if (has_lab) o[2 * i + 1] = a_l;
             if (lane == 0) slogc[t] = c;
         }
-        // mass of the two terminal states at T-1
+        // mass of the two terminal states at T-1 (relative to the last column maximum)
         const float fb = __shfl_sync(0xffffffffu, a_b, L);
-        const float fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : 0.f;
-        if (lane == 0) s_fin = (double)(fb + fl);
+        const float fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : kNegInf;
+        if (lane == 0) s_fin = (double)lse2_log2(fb, fl);
     } else if (warp == 1) {
         if (p.grad != nullptr) {
             // beta: pair (label 2i-1, blank 2i); excludes y_t
             const bool has_lab = (i >= 1 && i <= L);
-            float b_l = 0.f, b_b = 0.f;
+            float b_l = kNegInf, b_b = kNegInf;
             if (i == L) {
-                b_b = 1.f;
-                if (L >= 1) b_l = 1.f;
+                b_b = 0.f;
+                if (L >= 1) b_l = 0.f;
             }
             float yb_n = 0.f, yl_n = 0.f;
-            if (T > 1) { yb_n = slp[(T - 1) * W]; yl_n = has_lab ? slp[(T - 1) * W + i] : 0.f; }
+            if (T > 1) { yb_n = slp[(T - 1) * W]; yl_n = has_lab ? slp[(T - 1) * W + i] : kNegInf; }
             for (int t = T - 1; t >= 0; --t) {
                 if (t < T - 1) {
                     const float yb = yb_n, yl = yl_n;
-                    if (t >= 1) { yb_n = slp[t * W]; yl_n = has_lab ? slp[t * W + i] : 0.f; }
-                    const float e_b = b_b * yb;
-                    const float e_l = b_l * yl;
+                    if (t >= 1) { yb_n = slp[t * W]; yl_n = has_lab ? slp[t * W + i] : kNegInf; }
+                    const float e_b = b_b + yb;
+                    const float e_l = b_l + yl;
                     float n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
-                    if (i == 31) n1 = 0.f;
-                    const float nbb = e_b + n1;
-                    const float nbl = e_l + e_b + (skip ? n1 : 0.f);
-                    b_b = has_blank ? nbb : 0.f;
-                    b_l = has_lab ? nbl : 0.f;
+                    if (i == 31) n1 = kNegInf;
+                    const float nbb = lse2_log2(e_b, n1);
+                    const float nbl = lse3_log2(e_l, e_b, skip ? n1 : kNegInf);
+                    b_b = has_blank ? nbb : kNegInf;
+                    b_l = has_lab ? nbl : kNegInf;
                 }
-                const float d = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(b_b, b_l))));
-                const float inv = (d > 0.f) ? __fdividef(1.0f, d) : 0.f;
-                b_b *= inv;
-                b_l *= inv;
+                const float d = warp_max_redux(fmaxf(b_b, b_l));
+                const float sub = (d == kNegInf) ? 0.f : d;
+                b_b -= sub;
+                b_l -= sub;
                 float* o = sbe + t * Ub;
                 if (has_blank) o[2 * i] = b_b;
                 if (has_lab) o[2 * i - 1] = b_l;
@@ -557,7 +591,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
             const int k = base + lane;                       // position in sweep order
             const int t = (warp == 0) ? k : T - 1 - k;
             double v = 0.0;
-            if (k < T) v = (double)__logf(warp == 0 ? slogc[t] : slogd[t]);
+            if (k < T) v = (double)(warp == 0 ? slogc[t] : slogd[t]);
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const double n = __shfl_up_sync(0xffffffffu, v, o);
@@ -569,8 +603,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         }
     }
     __syncthreads();
-    // log p = log(sum of the two terminal alphas at T-1) = C_{T-1} + log(scaled mass)
-    const double logp = sC[T - 1] + (double)__logf((float)s_fin);
+    // log2 p = C_{T-1} + log2(relative mass of the two terminal alphas at T-1)
+    const double logp2 = sC[T - 1] + s_fin;
+    const double logp = logp2 * 0.6931471805599453;
     if (tid == 0) {
         p.logp[b] = logp;
         p.loss[b] = (float)(-logp);
@@ -580,9 +615,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
 
     // ---- C: gradient rows -----------------------------------------------------
     const bool fix = (logp != ninf) && (status == ASRK_ROW_OK);   // TF: no valid path -> dy = y
-    // occupancy(t, u) = alpha_t(u) beta_t(u) / p = ahat_t(u) bhat_t(u) K_t
+    // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(ahat_t(u) + bhat_t(u) + K_t)
     if (fix)
-        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = __expf((float)(sC[t] + sD[t] - logp));
+        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = (float)(sC[t] + sD[t] - logp2);
     __syncthreads();
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
     // lane j < L owns label position j: the positions that carry the same label (one
@@ -628,18 +663,18 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
         const float* al = sal + t * Ub;
         const float* be = sbe + t * Ub;
         const float Kt = sK[t];
-        float ob = (lane <= L) ? al[2 * lane] * be[2 * lane] : 0.f;          // blank states (L <= 31)
-        if (is_blank_lab) ob += al[2 * lane + 1] * be[2 * lane + 1];           // a label equal to the blank index
+        float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;          // blank states (L <= 31)
+        if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);           // a label equal to the blank index
         if (owner) {
             float o = 0.f;
             for (unsigned mset = same; mset; mset &= mset - 1) {
                 const int k = __ffs(mset) - 1;
-                o += al[2 * k + 1] * be[2 * k + 1];
+                o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
             }
-            g[my_lab] = (slp[t * W + 1 + lane] - o * Kt) * scale;
+            g[my_lab] = (ex2_fast(slp[t * W + 1 + lane]) - o) * scale;
         }
         ob = warp_sum(ob);
-        if (lane == 0) g[p.blank] = (slp[t * W] - ob * Kt) * scale;
+        if (lane == 0) g[p.blank] = (ex2_fast(slp[t * W]) - ob) * scale;
     }
 }
 

@@ -194,7 +194,7 @@ def test_full_size_c2_batch_properties():
     assert int(r.row_status.max()) == 0 and np.all(np.isfinite(loss)) and np.all(loss > 0)
     T = x.shape[0]
     valid = np.arange(T)[:, None] < il[None, :]
-    assert np.abs(grad.sum(-1))[valid].max() < 2e-5
+    assert np.abs(grad.sum(-1))[valid].max() < 1e-4     # 10x inside the 1e-3 tolerance
     assert not grad[~valid].any()
     red = ctc.loss_sum(r.loss, r.row_status).cpu().numpy()
     assert red[1] == 256 and abs(red[0] - loss.astype(np.float64).sum()) < 1e-6 * red[0]
