@@ -180,4 +180,45 @@ ASRK_HD void fft200_pass2(int j, const LoadY& loadY, const cplx* P, const Emit& 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Lane-uniform pass 2: the same code for every role j, for warps whose lanes carry
+// different roles (spectrogram.cu: the two half-warps of a warp own two roles).  Role j
+// owns rows k1a = j and k1b = 20 - j of Z[k1 + 20 k2] (role 0: the two self-mirrored
+// rows 0 and 10), i.e. the bins k = j + 20 s and 200 - k.  Eleven "slots" s = 0..10,
+// operands picked with selects, so lanes never diverge:
+//   j != 0 : slot s <= 9 pairs za[s] with zb[9-s];                    slot 10 unused
+//   j == 0 : slots 0..5 pair za[s] with za[(10-s)%10]   (k = 20 s),
+//            slots 6..10 pair zb[s-6] with zb[15-s]     (k = 10 + 20 (s-6))
+// Emit(s, pk, pm): 4|X[k]|^2 and 4|X[200-k]|^2 of slot s (s is a constant after
+// unrolling).  k = j + 20 s, except for j == 0, s >= 6: k = 20 s - 110.
+// ---------------------------------------------------------------------------
+ASRK_HD cplx csel(bool c, cplx a, cplx b) { return cplx{c ? a.x : b.x, c ? a.y : b.y}; }
+
+ASRK_HD int lane_k1a(int j) { return j; }
+ASRK_HD int lane_k1b(int j) { return j ? 20 - j : 10; }
+// bin of slot s for role j
+ASRK_HD int lane_bin(int j, int s) { return (j == 0 && s >= 6) ? 20 * s - 110 : j + 20 * s; }
+
+template <class LoadP, class Emit>
+ASRK_HD void split_lane(bool j0, const cplx (&za)[10], const cplx (&zb)[10], const LoadP& loadP,
+                        const Emit& emit) {
+#pragma unroll
+    for (int s = 0; s < 11; ++s) {
+        cplx A, B;
+        if (s <= 5) {
+            A = za[s];
+            B = csel(j0, za[(10 - s) % 10], zb[9 - s]);
+        } else if (s <= 9) {
+            A = csel(j0, zb[s - 6], za[s]);
+            B = csel(j0, zb[15 - s], zb[9 - s]);
+        } else {
+            A = zb[4];
+            B = zb[5];
+        }
+        double pk, pm;
+        split_pair(A, B, loadP(s), pk, pm);
+        emit(s, pk, pm);
+    }
+}
+
 }  // namespace asrk

@@ -10,23 +10,26 @@
 //     has a half-rate fp64 pipe (64 lanes/SM/clk), which is the bound of this
 //     kernel (register-resident codelets reach > 90 % of it, tools/ubench);
 //     everything after |X|^2 (sqrt, log, z-score) is fp32.
-//   * ONE persistent kernel, one CTA per SM.  A tile is 32 consecutive frames of
-//     one utterance: LANE = FRAME, WARP = ROLE.  The 400-point real DFT is a
-//     200-point complex DFT (20 x 10 Cooley-Tukey, both factors twiddle-free
-//     prime-factor codelets) + the real-input split; ten "FFT warps" each own one
-//     of the ten residues, so window values and twiddles are warp-uniform and come
-//     from the constant bank (no load/store-unit traffic), the PCM tile is staged
-//     in padded shared memory by cp.async, and the only exchange between the two
-//     passes is one conflict-free 100 KB fp64 buffer.
-//   * four "helper warps" run concurrently: they claim tiles from an atomic counter
-//     (in utterance order), stage the PCM two tiles ahead (mixing in K*noise on the
-//     fly in noise mode), and move finished 32 x 200 log-magnitude tiles to global
-//     memory with coalesced stores.  FULL/EMPTY named barriers decouple the two
-//     groups by up to a tile.
-//   * z-score: the helpers accumulate the per-bin column sums of every tile while
-//     they copy it out (fp32, shifted by the tile's first row so that nothing
-//     cancels), combine them per tile in fp64 in a fixed order (reproducible, no float
-//     atomics).  A tiny kernel turns the tile partials of every utterance into mean and
+//   * ONE persistent kernel, one CTA per SM, THREE independent teams of five warps.
+//     A team transforms 16 consecutive frames at a time: lane = (frame, role half), the
+//     two half-warps of warp q own roles q and q + 5 of the 20 x 10 Cooley-Tukey split
+//     of the 200-point complex DFT (400-point real DFT = 200-point complex DFT + real-
+//     input split; both factors twiddle-free prime-factor codelets), so window values
+//     and twiddles are half-warp broadcasts from shared memory and the two passes
+//     exchange through the team's own conflict-free 50 KB fp64 buffer with team-wide
+//     named barriers only.  15 transform warps sit 4/4/4/3 on the four schedulers (a
+//     single 10-role team sits 3/3/2/2 and leaves a sixth of the fp64 pipe idle), and
+//     while one team loads, exchanges or copies out, the other two keep the pipe busy.
+//   * a team claims units of 32 consecutive frames of one utterance from an atomic
+//     counter (in utterance order), stages their PCM with 16-byte cp.async while the
+//     previous unit's last sub-tile is still in flight (zero-filled past the end; the
+//     noise mix fl32(s + fl32(K n)) is applied on the way in), and copies finished
+//     16 x 200 log-magnitude tiles to global memory column-wise: warp q owns bins
+//     40 q .. 40 q + 39, so every store is a full 32-byte sector and every bin's
+//     z-score sums live in exactly one lane.
+//   * z-score: the per-bin sums of every unit are accumulated during the copy-out
+//     (fp32, shifted by the unit's first row so that nothing cancels) and written
+//     un-shifted in fp64 per unit (fixed order: reproducible, no float atomics).  A tiny kernel turns the tile partials of every utterance into mean and
 //     1/std, and a purely streaming kernel with the whole chip's memory parallelism
 //     normalises in place (the rows are largely still in L2).  [Measured alternatives:
 //     an in-kernel z-score by the CTA that retires an utterance's last tile -- one
@@ -40,24 +43,20 @@
 namespace asrk {
 namespace spec {
 
-constexpr int kFftWarps = 10;
-constexpr int kHelperWarps = 4;
-constexpr int kFftThreads = kFftWarps * 32;          // 320
-constexpr int kHelperThreads = kHelperWarps * 32;    // 128
-constexpr int kThreads = kFftThreads + kHelperThreads;
-constexpr int kTile = 32;                            // frames per tile (= lanes)
+constexpr int kTeams = 3;
+constexpr int kTeamWarps = 5;
+constexpr int kTeamThreads = kTeamWarps * 32;        // 160
+constexpr int kThreads = kTeams * kTeamThreads;      // 480
+constexpr int kSub = 16;                             // frames per sub-tile (= lanes of a half-warp)
 constexpr int kHop = 160, kFrameLen = 400, kBins = 200;
-constexpr int kHopRows = 34;                         // 31*160+400 = 5360 samples -> 34 hops
 constexpr int kOutStride = 201;                      // padded row of the out tile
 // hop rows stay 16-byte aligned (for 16-byte async copies) and are padded by 16
-// bytes: lane f reads word 84 f + c -> 8 distinct banks, a 4-way conflict on the
-// 20 sample loads of a thread per tile (its only other shared accesses are the
-// conflict-free exchange), instead of the 16-way conflict of the unpadded layout.
+// bytes: frame f reads word 84 f + c -> the 16 frames of a half-warp hit 8 distinct
+// banks (2-way conflict on the 20 sample loads of a thread per sub-tile).
 constexpr int kHopWordsI16 = 84;                     // 80 words of int16 pairs + 4 pad
 constexpr int kHopWordsF32 = 164;                    // 160 words + 4 pad
 constexpr int kTabDoubles = 1200;                    // window[400] | tw[r][k1] | P[k]
-constexpr int kMaxBatch = 2047;                      // utterances per launch (tile prefix in smem)
-constexpr int kRing = 8;                             // tile metadata ring
+constexpr int kMaxBatch = 2047;                      // utterances per launch (unit prefix in smem)
 
 __device__ const double g_tab[kTabDoubles] = {
 #include "asrk_tables.inc"
@@ -108,7 +107,7 @@ static WsLayout ws_layout(int batch, long long total_frames) {
     l.gains = o;     o = align_up(o + sizeof(float) * (size_t)batch, 256);
     l.stats = o;     o = align_up(o + sizeof(float) * 3 * kBins * (size_t)batch, 256);
     l.partials = o;
-    const size_t max_tiles = (size_t)(total_frames / kTile) + (size_t)batch + 1;
+    const size_t max_tiles = (size_t)(total_frames / kSub) + (size_t)batch + 1;
     o = align_up(o + sizeof(double2) * kBins * max_tiles, 256);
     l.total = o;
     return l;
@@ -141,8 +140,9 @@ __device__ __forceinline__ float log_mag(float p4, float half_mag) {
 
 // Synchronous staging of one PCM tile (unaligned utterances, and the noise mix:
 // fl32(signal + fl32(K * noise)) is formed on the way in).
-template <bool F32>
+template <bool F32, int kHopRows>
 __device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, uint32_t* dst, int hth) {
+    constexpr int kHelperThreads = kTeamThreads;
     const long long t0 = (long long)m.f0 * kHop;   // utterance-local first sample of the tile
     if (!F32) {
         const short* src = reinterpret_cast<const short*>(p.samples) + m.sbase;
@@ -209,8 +209,9 @@ __device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, ui
 // Asynchronous staging of one PCM tile (no arithmetic on the way): 16-byte LDGSTS
 // copies into the padded hop rows, zero-filled past the end of the utterance.
 // Needs the utterance start to be 16-byte aligned.
-template <bool F32>
+template <bool F32, int kHopRows>
 __device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta& m, uint32_t* dst, int hth) {
+    constexpr int kHelperThreads = kTeamThreads;
     const long long t0 = (long long)m.f0 * kHop;
     constexpr int kPerChunk = F32 ? 4 : 8;             // samples per 16 bytes
     constexpr int kChunksPerHop = kHop / kPerChunk;    // 40 / 20
@@ -228,7 +229,7 @@ __device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta
 }
 
 // Tile -> utterance, frame range and the utterance's constants (helper thread 0).
-__device__ void fill_meta(const Params& p, const int* tile_off, int tile, Meta& m) {
+__device__ void fill_meta(const Params& p, const int* tile_off, int tile, int kTile, Meta& m) {
     int lo = 0, hi = p.batch - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -255,64 +256,42 @@ __device__ void fill_meta(const Params& p, const int* tile_off, int tile, Meta& 
 // ---------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------
-// Named barriers (id 0 is __syncthreads).  FULL/EMPTY pairs hand the PCM stages and
-// the two out tiles between the FFT warps and the helper warps so that neither side
-// waits for the other unless it is a whole tile behind.
-enum : int {
-    kBarHelpers = 1,      // helper warps only
-    kBarExchA = 2,        // FFT warps only: pass 1 stores -> pass 2 loads
-    kBarExchB = 3,        // FFT warps only: pass 2 loads -> next pass 1 stores
-    kBarPcmFull = 4,      // +stage (4,5,6)
-    kBarPcmEmpty = 7,     // +stage (7,8,9)
-    kBarOutFull = 10,     // +slot (10,11)
-    kBarOutEmpty = 12,    // +slot (12,13)
-};
-constexpr int kPipeThreads = kThreads;   // threads on a FULL/EMPTY barrier
-
-__device__ __forceinline__ void bar_sync(int id, int n) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(int id, int n) {
-    __threadfence_block();
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-
 template <bool F32>
 struct Cfg {
-    static constexpr int kStages = F32 ? 2 : 3;          // PCM stages (tiles staged ahead: kStages - 1)
+    // frames per claimed unit: 32 (two sub-tiles) for int16; 16 for float32 so that the
+    // staging buffers of three teams still fit next to the exchange buffers
+    static constexpr int kUnit = F32 ? 16 : 32;
+    static constexpr int kHopRows = kUnit + 2;                   // (kUnit-1)*160+400 samples
     static constexpr int kPcmWords = kHopRows * (F32 ? kHopWordsF32 : kHopWordsI16);
 };
 
-// Synchronisation protocol.  Both groups walk the same iteration space t = 0, 1, ...
-// The tiles a CTA claims are valid for t < V and invalid from V on (the counter ran
-// out); both groups stop in iteration V:
-//   helpers, iteration t : claim + stage tile t + kAhead (waits PcmEmpty of the stage),
-//                          arrive PcmFull(t + 1), [valid] wait OutFull(t), store rows +
-//                          column sums, arrive OutEmpty(t), publish the tile's partial
-//                          sums, retire the tile
-//   FFT,     iteration t : wait PcmFull(t), [valid] pass 1 (arrive PcmEmpty after the
-//                          loads), ExchA, pass-2 loads, ExchB, wait OutEmpty(t - 2),
-//                          pass 2, arrive OutFull(t)
+__device__ __forceinline__ void team_bar(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kTeamThreads) : "memory");
+}
+
 template <bool F32>
 __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
-    constexpr int kStages = Cfg<F32>::kStages;
-    constexpr int kAhead = kStages - 1;
+    constexpr int kUnit = Cfg<F32>::kUnit;
+    constexpr int kHopRows = Cfg<F32>::kHopRows;
     constexpr int kPcmWords = Cfg<F32>::kPcmWords;
+    constexpr int kExchBytes = 200 * kSub * (int)sizeof(cplx);                // 51 200
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* exch = reinterpret_cast<cplx*>(smem_raw);                           // [200][32]
-    float* outt = reinterpret_cast<float*>(exch + 200 * kTile);               // [2][32*201]
-    uint32_t* pcm = reinterpret_cast<uint32_t*>(outt + 2 * kTile * kOutStride);  // [kStages][kPcmWords]
-    int* tile_off = reinterpret_cast<int*>(pcm + kStages * kPcmWords);        // [kMaxBatch + 1]
-    float* s_col = reinterpret_cast<float*>(tile_off + kMaxBatch + 1);        // [4][3][200] helper column sums
-    double* tab = reinterpret_cast<double*>(s_col + kHelperWarps * 3 * kBins);   // [1200], 16-byte aligned
-    __shared__ Meta meta[kRing];
+    double* tab = reinterpret_cast<double*>(smem_raw);                        // [1200]
+    int* tile_off = reinterpret_cast<int*>(tab + kTabDoubles);                // [kMaxBatch + 1]
+    unsigned char* team_base = reinterpret_cast<unsigned char*>(tile_off + kMaxBatch + 1);
+    __shared__ Meta meta[kTeams][2];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    const int team = warp / kTeamWarps, q = warp - team * kTeamWarps;
+    const int tt = tid - team * kTeamThreads;
+    cplx* exch = reinterpret_cast<cplx*>(team_base + (size_t)team * (kExchBytes + kPcmWords * 4));   // [200][16]
+    uint32_t* pcm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(exch) + kExchBytes);
+    float* ot = reinterpret_cast<float*>(exch);                               // out tile [16][201] aliases the exchange
 
     for (int i = tid; i < kTabDoubles; i += kThreads) tab[i] = g_tab[i];
     if (warp == 0) {
-        // exclusive scan of ceil(n_frames / 32) over the utterances
+        // exclusive scan of ceil(n_frames / kUnit) over the utterances
         int carry = 0;
         for (int base = 0; base < p.batch; base += 32) {
             const int i = base + lane;
@@ -320,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
             if (i < p.batch) {
                 long long n = p.frame_offsets[i + 1] - p.frame_offsets[i];
                 if (n < 0) n = 0;
-                v = (int)((n + kTile - 1) / kTile);
+                v = (int)((n + kUnit - 1) / kUnit);
             }
             int incl = v;
 #pragma unroll
@@ -339,204 +318,143 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     if (blockIdx.x == 0 && want_stats)
         for (int i = tid; i <= p.batch; i += kThreads) p.tile_off_g[i] = tile_off[i];
 
-    if (warp < kFftWarps) {
-        // ------------------------------ FFT warps ------------------------------
-        // the role: residue class in pass 1, row pair in pass 2; window values and twiddles
-        // are warp-uniform shared-memory broadcasts
-        const int r = warp;
-        const double2* tabW2 = reinterpret_cast<const double2*>(tab);
-        const cplx* tabT = reinterpret_cast<const cplx*>(tab + 400) + r * 20;
-        const cplx* tabP = reinterpret_cast<const cplx*>(tab + 800);
-        for (int t = 0;; ++t) {
-            const int st = t % kStages;
-            const int s = t & 1;
-            bar_sync(kBarPcmFull + st, kPipeThreads);
-            if (!meta[t % kRing].valid) break;
-            const uint32_t* pc = pcm + st * kPcmWords;
+    // lane -> (frame of the sub-tile, role): the two half-warps of warp q own roles q, q + 5
+    const int f = lane & 15;
+    const int r = q + 5 * (lane >> 4);
+    const bool j0 = (r == 0);
+    const int k1a = lane_k1a(r), k1b = lane_k1b(r);
+    const int kb_hi = j0 ? -110 : r;          // bin of slot s >= 6 is kb_hi + 20 s
+    const double2* tabW2 = reinterpret_cast<const double2*>(tab);
+    const cplx* tabT = reinterpret_cast<const cplx*>(tab + 400) + r * 20;
+    const cplx* tabP = reinterpret_cast<const cplx*>(tab + 800);
+    const bool mix = (p.noise != nullptr);
+    // the un-normalised rows are read again by the z-score kernel: keep them in L2
+    const uint64_t keep = want_stats ? l2_policy_evict_last() : l2_policy_evict_first();
+
+    // unit metadata: claimed and looked up by the team's first thread, one unit ahead
+    int next_tile = total_tiles;
+    if (tt == 0) next_tile = atomicAdd(p.counters, 1);
+    auto prepare_meta = [&](int slot) {
+        if (tt == 0) {
+            Meta& mn = meta[team][slot];
+            const int tile = next_tile;
+            if (tile < total_tiles) {
+                next_tile = atomicAdd(p.counters, 1);
+                fill_meta(p, tile_off, tile, kUnit, mn);
+            } else {
+                mn.valid = 0;
+            }
+        }
+    };
+    auto stage = [&](const Meta& m) {
+        const bool aligned = (((reinterpret_cast<uintptr_t>(p.samples) + m.sbase * (F32 ? 4 : 2)) & 15) == 0);
+        if (!mix && aligned) issue_pcm_tile_async<F32, kHopRows>(p, m, pcm, tt);
+        else load_pcm_tile<F32, kHopRows>(p, m, pcm, tt);
+        cp_async_commit();
+    };
+
+    prepare_meta(0);
+    team_bar(team);
+    if (meta[team][0].valid) stage(meta[team][0]);
+    for (int u = 0;; ++u) {
+        const Meta& m = meta[team][u & 1];
+        if (!m.valid) break;
+        cp_async_wait<0>();
+        team_bar(team);                         // the unit's PCM is in place; everyone is done with unit u - 1
+        prepare_meta((u + 1) & 1);              // (visible to the team after the next barrier)
+        const Meta& mnext = meta[team][(u + 1) & 1];
+        const int nsub = (m.nf + kSub - 1) / kSub;
+        // z-score sums of this lane's bins over the unit: bin 40 q + lane, and 40 q + 32 + lane (lane < 8)
+        float cA = 0.f, sA = 0.f, qA = 0.f, cB = 0.f, sB = 0.f, qB = 0.f;
+        for (int sub = 0; sub < nsub; ++sub) {
+            // ---------------- pass 1: window, DFT20 of residue r, twiddle ----------------
             {
                 cplx z[20], y[20];
+                const int F = sub * kSub + f;            // frame inside the unit
 #pragma unroll
                 for (int n1 = 0; n1 < 20; ++n1) {
-                    const int q = n1 / 8;                 // hop row offset of sample 2*(10 n1 + r)
+                    const int hq = n1 / 8;                // hop row offset of sample 2*(10 n1 + r)
                     const int wq = 10 * (n1 % 8) + r;     // int16-pair index inside the hop
                     double x0, x1;
                     if (!F32) {
-                        const uint32_t w = pc[(lane + q) * kHopWordsI16 + wq];
+                        const uint32_t w = pcm[(F + hq) * kHopWordsI16 + wq];
                         x0 = i16_to_f64((int)(short)(w & 0xffffu));
                         x1 = i16_to_f64((int)(short)(w >> 16));
                     } else {
                         const float2 v = *reinterpret_cast<const float2*>(
-                            reinterpret_cast<const float*>(pc) + (lane + q) * kHopWordsF32 + 2 * wq);
+                            reinterpret_cast<const float*>(pcm) + (F + hq) * kHopWordsF32 + 2 * wq);
                         x0 = (double)v.x;
                         x1 = (double)v.y;
                     }
                     const double2 w2 = tabW2[10 * n1 + r];
                     z[n1] = cplx{x0 * w2.x, x1 * w2.y};   // wav_util.py:71 data_line * w
                 }
-                bar_arrive(kBarPcmEmpty + st, kPipeThreads);
                 dft20(z, y);
-                exch[r * kTile + lane] = y[0];
+                exch[r * kSub + f] = y[0];
 #pragma unroll
-                for (int k1 = 1; k1 < 20; ++k1) exch[(k1 * 10 + r) * kTile + lane] = cmul(y[k1], tabT[k1]);
+                for (int k1 = 1; k1 < 20; ++k1) exch[(k1 * 10 + r) * kSub + f] = cmul(y[k1], tabT[k1]);
             }
-            bar_sync(kBarExchA, kFftThreads);
+            team_bar(team);                     // ExchA: pass-1 stores -> pass-2 loads; the PCM has been read
+            if (sub == nsub - 1 && mnext.valid) stage(mnext);    // next unit's PCM arrives behind the arithmetic
+            // ---------------- pass 2: DFT10 of rows j and 20-j, split, log ----------------
             {
-                const int k1a = r, k1b = (r == 0) ? 10 : 20 - r;
                 cplx ia[10], ib[10], za[10], zb[10];
 #pragma unroll
-                for (int n2 = 0; n2 < 10; ++n2) ia[n2] = exch[(k1a * 10 + n2) * kTile + lane];
+                for (int n2 = 0; n2 < 10; ++n2) ia[n2] = exch[(k1a * 10 + n2) * kSub + f];
 #pragma unroll
-                for (int n2 = 0; n2 < 10; ++n2) ib[n2] = exch[(k1b * 10 + n2) * kTile + lane];
-                bar_sync(kBarExchB, kFftThreads);     // every warp holds its rows: the exchange is free
+                for (int n2 = 0; n2 < 10; ++n2) ib[n2] = exch[(k1b * 10 + n2) * kSub + f];
+                team_bar(team);                 // ExchB: every lane holds its rows; the exchange becomes the out tile
                 dft10(ia, za);   // za[k2] = Z[k1a + 20 k2]
                 dft10(ib, zb);   // zb[k2] = Z[k1b + 20 k2]
-                if (t >= 2) bar_sync(kBarOutEmpty + s, kPipeThreads);
-                float* ot = outt + s * (kTile * kOutStride) + lane * kOutStride;
-                const float hm = meta[t % kRing].half_mag;
-                if (r != 0) {
-#pragma unroll
-                    for (int k2 = 0; k2 < 10; ++k2) {
-                        const int k = r + 20 * k2;
-                        double pk, pm;
-                        split_pair(za[k2], zb[9 - k2], tabP[k], pk, pm);
-                        ot[k] = log_mag((float)pk, hm);
-                        ot[200 - k] = log_mag((float)pm, hm);
+                float* orow = ot + f * kOutStride;
+                const float hm = m.half_mag;
+                auto loadP = [&](int s) { return tabP[(s < 6 ? r : kb_hi) + 20 * (s < 10 ? s : (j0 ? 10 : 0))]; };
+                auto emit = [&](int s, double pk, double pm) {
+                    const int k = (s < 6 ? r : kb_hi) + 20 * s;
+                    const float vk = log_mag((float)pk, hm), vm = log_mag((float)pm, hm);
+                    if (s < 10 || j0) {
+                        orow[200 - k] = vm;         // role 0, slot 0 writes bin "200" into the row padding
+                        orow[k] = vk;               // role 0, slot 5: bin 100 from pk, as the last store
                     }
-                } else {
-                    // row k1 = 0: bins 20 k2, mirror 20 (10 - k2); k2 = 0 and 5 are their own mirror
-#pragma unroll
-                    for (int k2 = 0; k2 <= 5; ++k2) {
-                        const int k = 20 * k2;
-                        double pk, pm;
-                        split_pair(za[k2], za[(10 - k2) % 10], tabP[k], pk, pm);
-                        ot[k] = log_mag((float)pk, hm);
-                        if (k2 != 0 && k2 != 5) ot[200 - k] = log_mag((float)pm, hm);
-                    }
-                    // row k1 = 10: bins 10 + 20 k2, mirror 10 + 20 (9 - k2)
-#pragma unroll
-                    for (int k2 = 0; k2 < 5; ++k2) {
-                        const int k = 10 + 20 * k2;
-                        double pk, pm;
-                        split_pair(zb[k2], zb[9 - k2], tabP[k], pk, pm);
-                        ot[k] = log_mag((float)pk, hm);
-                        ot[200 - k] = log_mag((float)pm, hm);
-                    }
+                };
+                split_lane(j0, za, zb, loadP, emit);
+            }
+            team_bar(team);                     // the out tile is complete
+            // ---------------- copy-out by columns + column sums ----------------
+            {
+                const int rows = (m.nf - sub * kSub) < kSub ? (m.nf - sub * kSub) : kSub;
+                float* obase = p.out + (size_t)(m.row0 + m.f0 + sub * kSub) * kBins;
+                const int colA = 40 * q + lane, colB = 40 * q + 32 + lane;
+                const bool hasB = lane < 8;
+#pragma unroll 4
+                for (int row = 0; row < rows; ++row) {
+                    const float yA = ot[row * kOutStride + colA];
+                    const float yB = hasB ? ot[row * kOutStride + colB] : 0.f;
+                    stg_hint(obase + (size_t)row * kBins + colA, yA, keep);
+                    if (hasB) stg_hint(obase + (size_t)row * kBins + colB, yB, keep);
+                    if (sub == 0 && row == 0) { cA = yA; cB = yB; }
+                    float d = yA - cA;
+                    sA += d;
+                    qA = fmaf(d, d, qA);
+                    d = yB - cB;
+                    sB += d;
+                    qB = fmaf(d, d, qB);
                 }
             }
-            bar_arrive(kBarOutFull + s, kPipeThreads);
+            team_bar(team);                     // the out tile has been read: the exchange is free again
         }
-    } else {
-        // ----------------------------- helper warps ----------------------------
-        const int hw = warp - kFftWarps;                          // 0..3
-        const int hth = hw * 32 + lane;
-        const bool mix = (p.noise != nullptr);
-        // Tile metadata is prepared one iteration before it is needed by the first lane of
-        // helper warp 1 (claim from the atomic counter, look the utterance up), the retire
-        // bookkeeping below runs on the first lane of helper warp 0: neither serialises the
-        // other, and neither round trip is on the staging path.
-        constexpr int kMetaThread = 32;
-        int next_tile = total_tiles;
-        if (hth == kMetaThread) next_tile = atomicAdd(p.counters, 1);
-        auto prepare_meta = [&](int t) {
-            if (hth == kMetaThread) {
-                Meta& mn = meta[t % kRing];
-                const int tile = next_tile;
-                if (tile < total_tiles) {
-                    next_tile = atomicAdd(p.counters, 1);
-                    fill_meta(p, tile_off, tile, mn);
-                } else {
-                    mn.valid = 0;
-                }
+        if (want_stats) {
+            // un-shifted sums of the unit in fp64:  sum y = s + n c,  sum y^2 = q + 2 c s + n c^2
+            const double n = (double)m.nf;
+            {
+                const double c = (double)cA, s1 = (double)sA, q1 = (double)qA;
+                p.partials[(size_t)m.tile * kBins + 40 * q + lane] =
+                    make_double2(fma(n, c, s1), fma(c, fma(n, c, 2.0 * s1), q1));
             }
-        };
-
-        // tile t (metadata prepared earlier): start filling PCM stage t % kStages.  The
-        // async path returns with the copies in flight (one commit group per tile).
-        auto issue = [&](int t) {
-            bar_sync(kBarHelpers, kHelperThreads);
-            if (t >= kStages) bar_sync(kBarPcmEmpty + (t % kStages), kPipeThreads);
-            const Meta& m = meta[t % kRing];
-            if (m.valid) {
-                uint32_t* dst = pcm + (t % kStages) * kPcmWords;
-                const bool aligned = (((reinterpret_cast<uintptr_t>(p.samples) + m.sbase * (F32 ? 4 : 2)) & 15) == 0);
-                if (!mix && aligned) issue_pcm_tile_async<F32>(p, m, dst, hth);
-                else load_pcm_tile<F32>(p, m, dst, hth);
-            }
-            cp_async_commit();
-        };
-
-        // rows of tile t to global memory (coalesced), and this warp's column sums of
-        // (y - c), (y - c)^2 with c = the warp's first row, into shared memory
-        // the un-normalised rows are read again by the z-score kernel: keep them in L2
-        const uint64_t keep = want_stats ? l2_policy_evict_last() : l2_policy_evict_first();
-        auto epilogue = [&](int t) {
-            const Meta& m = meta[t % kRing];
-            const float* ot = outt + (t & 1) * (kTile * kOutStride);
-            float c[7], sm[7], sq[7];
-#pragma unroll
-            for (int e = 0; e < 7; ++e) { c[e] = 0.f; sm[e] = 0.f; sq[e] = 0.f; }
-#pragma unroll 2
-            for (int ff = 0; ff < 8; ++ff) {
-                const int f = hw * 8 + ff;
-                if (f >= m.nf) break;
-                float* orow = p.out + (size_t)(m.row0 + m.f0 + f) * kBins;
-#pragma unroll
-                for (int e = 0; e < 7; ++e) {
-                    const int k = lane + 32 * e;
-                    if (k < kBins) {
-                        const float y = ot[f * kOutStride + k];
-                        stg_hint(orow + k, y, keep);
-                        if (ff == 0) c[e] = y;
-                        const float d = y - c[e];
-                        sm[e] += d;
-                        sq[e] = fmaf(d, d, sq[e]);
-                    }
-                }
-            }
-            if (want_stats) {
-                float* sc = s_col + hw * 3 * kBins;
-#pragma unroll
-                for (int e = 0; e < 7; ++e) {
-                    const int k = lane + 32 * e;
-                    if (k < kBins) { sc[k] = c[e]; sc[kBins + k] = sm[e]; sc[2 * kBins + k] = sq[e]; }
-                }
-            }
-        };
-
-#pragma unroll 1
-        for (int t = 0; t <= kAhead; ++t) prepare_meta(t);
-#pragma unroll 1
-        for (int t = 0; t < kAhead; ++t) issue(t);
-        cp_async_wait<kAhead - 1>();
-        bar_arrive(kBarPcmFull + 0, kPipeThreads);
-        for (int t = 0;; ++t) {
-            issue(t + kAhead);
-            prepare_meta(t + kAhead + 1);
-            cp_async_wait<kAhead - 1>();          // everything but the newest group(s): tile t+1 has landed
-            bar_arrive(kBarPcmFull + ((t + 1) % kStages), kPipeThreads);
-            if (!meta[t % kRing].valid) break;
-            bar_sync(kBarOutFull + (t & 1), kPipeThreads);
-            epilogue(t);
-            bar_sync(kBarHelpers, kHelperThreads);          // the out tile has been read by all four warps
-            bar_arrive(kBarOutEmpty + (t & 1), kPipeThreads);
-            if (!want_stats) continue;
-            // per-tile column sums, un-shifted, in fp64 and a fixed order:
-            //   sum y = s + n c,  sum y^2 = q + 2 c s + n c^2   over the four warps' row groups
-            const Meta& m = meta[t % kRing];
-            for (int k = hth; k < kBins; k += kHelperThreads) {
-                double a1 = 0.0, a2 = 0.0;
-#pragma unroll
-                for (int w = 0; w < kHelperWarps; ++w) {
-                    int nw = m.nf - 8 * w;
-                    nw = nw < 0 ? 0 : (nw > 8 ? 8 : nw);
-                    const double n = (double)nw;
-                    const double cc = (double)s_col[w * 3 * kBins + k];
-                    const double ss = (double)s_col[w * 3 * kBins + kBins + k];
-                    const double qq = (double)s_col[w * 3 * kBins + 2 * kBins + k];
-                    a1 += fma(n, cc, ss);
-                    a2 += fma(cc, fma(n, cc, 2.0 * ss), qq);
-                }
-                p.partials[(size_t)m.tile * kBins + k] = make_double2(a1, a2);
+            if (lane < 8) {
+                const double c = (double)cB, s1 = (double)sB, q1 = (double)qB;
+                p.partials[(size_t)m.tile * kBins + 40 * q + 32 + lane] =
+                    make_double2(fma(n, c, s1), fma(c, fma(n, c, 2.0 * s1), q1));
             }
         }
     }
@@ -615,9 +533,8 @@ __global__ void __launch_bounds__(256) normalize_kernel(Params p) {
 
 template <bool F32>
 static size_t main_smem_bytes() {
-    return sizeof(cplx) * 200 * kTile + sizeof(float) * 2 * kTile * kOutStride +
-           sizeof(uint32_t) * (size_t)Cfg<F32>::kStages * Cfg<F32>::kPcmWords + sizeof(int) * (kMaxBatch + 1) +
-           sizeof(float) * kHelperWarps * 3 * kBins + sizeof(double) * kTabDoubles + 16;
+    return sizeof(double) * kTabDoubles + sizeof(int) * (kMaxBatch + 1) +
+           (size_t)kTeams * (200 * kSub * sizeof(cplx) + sizeof(uint32_t) * Cfg<F32>::kPcmWords) + 16;
 }
 
 template <bool F32>

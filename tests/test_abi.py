@@ -7,6 +7,7 @@ import re
 import subprocess
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -56,9 +57,11 @@ def test_argument_validation_without_device():
                                         None) == _lib.OK
 
 
-def test_fft_codelets_on_host(tmp_path):
+@pytest.mark.parametrize("harness", ["fft_codelets_host.cpp", "fft_lanes_host.cpp"])
+def test_fft_codelets_on_host(tmp_path, harness):
+    """Both pass-2 formulations (role-uniform warps / lane-uniform selects) with the generated tables."""
     exe = str(tmp_path / "fft_host")
-    subprocess.check_call(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tests", "host", "fft_codelets_host.cpp")])
+    subprocess.check_call(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tests", "host", harness)])
     rng = np.random.default_rng(1)
     w = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(400) / 399)
     for trial in range(3):
