@@ -249,15 +249,29 @@ __device__ __forceinline__ void row_argmax(const RowRegs<NV4>& r, int lane, floa
     if (am == 0x7fffffff) am = 0;   // all -inf / NaN row: TF's scan leaves index 0
 }
 
+// one-MUFU exp2 / log2 (flush-to-zero: a softmax term below 2^-126 is zero anyway)
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 template <int NV4>
 __device__ __forceinline__ float row_sumexp(const RowRegs<NV4>& r, float m) {
+    const float m2 = -m * kLog2e;            // exp(x - m) = 2^(x log2e - m log2e): one FFMA + one MUFU per term
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < NV4; ++k) {
-        s += __expf(r.v[k].x - m);
-        s += __expf(r.v[k].y - m);
-        s += __expf(r.v[k].z - m);
-        s += __expf(r.v[k].w - m);
+        s += ex2_fast(fmaf(r.v[k].x, kLog2e, m2));
+        s += ex2_fast(fmaf(r.v[k].y, kLog2e, m2));
+        s += ex2_fast(fmaf(r.v[k].z, kLog2e, m2));
+        s += ex2_fast(fmaf(r.v[k].w, kLog2e, m2));
     }
     return warp_sum(s);
 }
@@ -367,16 +381,6 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // arguments are <= 0 (flush below -126 is exact enough: 2^-126 of the column's mass), the
 // log argument is in [1, 3] where lg2.approx is good to 2^-22 absolute; -inf operands are
 // zeros and all -inf stays -inf (m + lg2(0)).
-__device__ __forceinline__ float ex2_fast(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2_fast(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ float lse2_log2(float a, float b) {
     const float m = fmaxf(a, b);
     const float ms = (m == kNegInf) ? 0.f : m;
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
             for (int k = lane; k < V4; k += 32) stg_evict_first(g4 + k, z);
             continue;
         }
-        const float lse = slse[t];
+        const float nlse2 = -slse[t] * kLog2e;
         cp_async_wait<0>();
         __syncwarp();
         float4 v[NV4];
@@ -651,10 +655,10 @@ __global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
             const int idx = lane + 32 * k;
             if (idx < V4) {
                 float4 y;
-                y.x = __expf(v[k].x - lse) * scale;
-                y.y = __expf(v[k].y - lse) * scale;
-                y.z = __expf(v[k].z - lse) * scale;
-                y.w = __expf(v[k].w - lse) * scale;
+                y.x = ex2_fast(fmaf(v[k].x, kLog2e, nlse2)) * scale;
+                y.y = ex2_fast(fmaf(v[k].y, kLog2e, nlse2)) * scale;
+                y.z = ex2_fast(fmaf(v[k].z, kLog2e, nlse2)) * scale;
+                y.w = ex2_fast(fmaf(v[k].w, kLog2e, nlse2)) * scale;
                 stg_evict_first(g4 + idx, y);
             }
         }
@@ -823,6 +827,7 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
     const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
     const size_t bt = (size_t)b * p.T + t;
     const float lse = p.lse[bt];
+    const float nlse2 = -lse * kLog2e;
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
     if constexpr (NV4 > 0) {
         const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -839,10 +844,10 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
             const int i = lane + 32 * k;
             if (i < V4) {
                 float4 y;
-                y.x = __expf(v[k].x - lse) * scale;
-                y.y = __expf(v[k].y - lse) * scale;
-                y.z = __expf(v[k].z - lse) * scale;
-                y.w = __expf(v[k].w - lse) * scale;
+                y.x = ex2_fast(fmaf(v[k].x, kLog2e, nlse2)) * scale;
+                y.y = ex2_fast(fmaf(v[k].y, kLog2e, nlse2)) * scale;
+                y.z = ex2_fast(fmaf(v[k].z, kLog2e, nlse2)) * scale;
+                y.w = ex2_fast(fmaf(v[k].w, kLog2e, nlse2)) * scale;
                 stg_stream(g4 + i, y);
             }
         }
