@@ -178,6 +178,25 @@ int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long lon
                                void* workspace, size_t workspace_bytes, asrk_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Steps adjacent to the path
+ *   asrk_lfr_run            replaces util/utils.py:7-31 build_LFR_features (stack m frames, skip n; the
+ *                           tail repeats the last frame), on a ragged batch: utterance b owns input rows
+ *                           [in_offsets[b], in_offsets[b+1]) of `dim` floats and output rows
+ *                           [out_offsets[b], out_offsets[b+1]) of m*dim floats, out rows = ceil(T_b / n).
+ *   asrk_edit_distance_run  replaces tf.edit_distance(decoded, labels) (normalize=True by default),
+ *                           lm_and_am/model/acoustic_model2.py:72: Levenshtein distance of hyp[b][0..hyp_len[b])
+ *                           against truth[b][0..truth_len[b]) (truth_stride <= 64), divided by truth_len when
+ *                           normalize != 0 (empty truth: +inf for a non-empty hypothesis, else 0).
+ * ------------------------------------------------------------------------ */
+int asrk_lfr_run(const float* in, const long long* in_offsets, float* out, const long long* out_offsets,
+                 int batch, int dim, int m, int n, long long total_out_rows, asrk_stream_t stream);
+
+int asrk_edit_distance_run(const int* hyp, int hyp_stride, const int* hyp_len,
+                           const int* truth, int truth_stride, const int* truth_len,
+                           int batch, int normalize, float* out /* device float32 [B] */,
+                           asrk_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Measurement entry points: the same calls with a bit mask of the launches to
  * enqueue, so that a harness can bracket every kernel with its own CUDA events
  * on the launching stream.  ASRK_PHASE_ALL is what the plain entry points pass;

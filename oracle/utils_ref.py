@@ -1,0 +1,48 @@
+"""ORACLE (test infrastructure only): restatement of the helpers next to the hot path.
+
+  build_LFR_features   /root/reference/util/utils.py:7-31, followed line by line
+  edit_distance        tf.edit_distance semantics (tensorflow/core/kernels/edit_distance_op.cc,
+                       lib/gtl/edit_distance.h: Levenshtein; normalize divides by the truth
+                       length; empty truth -> inf for a non-empty hypothesis, 0 otherwise)
+                       as called at lm_and_am/model/acoustic_model2.py:72.  TensorFlow is not
+                       installable here: parity unpinned by the reference, known answers below
+                       are hand-computed.
+"""
+import numpy as np
+
+
+def build_LFR_features(inputs, m, n):
+    LFR_inputs = []
+    T = inputs.shape[0]
+    T_lfr = int(np.ceil(T / n))
+    for i in range(T_lfr):
+        if m <= T - i * n:
+            LFR_inputs.append(np.hstack(inputs[i * n:i * n + m]))
+        else:
+            num_padding = m - (T - i * n)
+            frame = np.hstack(inputs[i * n:])
+            for _ in range(num_padding):
+                frame = np.hstack((frame, inputs[-1]))
+            LFR_inputs.append(frame)
+    return np.vstack(LFR_inputs)
+
+
+def levenshtein(hyp, truth):
+    hyp, truth = list(hyp), list(truth)
+    prev = list(range(len(truth) + 1))
+    for i, h in enumerate(hyp, 1):
+        cur = [i]
+        for j, t in enumerate(truth, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (0 if h == t else 1)))
+        prev = cur
+    return prev[-1]
+
+
+def edit_distance(hyps, truths, normalize=True):
+    out = []
+    for h, t in zip(hyps, truths):
+        d = float(levenshtein(h, t))
+        if normalize:
+            d = d / len(t) if len(t) else (float("inf") if len(h) else 0.0)
+        out.append(d)
+    return np.array(out, dtype=np.float64)
