@@ -188,6 +188,20 @@ int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long lon
  *                           against truth[b][0..truth_len[b]) (truth_stride <= 64), divided by truth_len when
  *                           normalize != 0 (empty truth: +inf for a non-empty hypothesis, else 0).
  * ------------------------------------------------------------------------ */
+/*   asrk_logfbank_run       replaces util/wav_util.py:22-31 compute_fbank_from_api =
+ *                           python_speech_features.logfbank(signal, fs, nfilt) + sklearn scale (the feature
+ *                           call of the live loaders, lm_and_am/data_loader.py:129): float64 samples (as
+ *                           soundfile returns them), pre-emphasis `preemph`, rectangular frames of frame_len
+ *                           samples at hop frame_step zero-padded at the end (frame counts decided by the host:
+ *                           1 + ceil((N - frame_len)/frame_step)), 512-point power spectrum / 512, triangular mel
+ *                           filters between the FFT bins mel_bins[0..nfilt+1] (device int32, from the host's
+ *                           numpy evaluation of get_filterbanks), log with 0 -> eps; normalise != 0 z-scores
+ *                           every filter over the frames of the utterance.  nfilt <= 224, frame_len <= 512. */
+int asrk_logfbank_run(const double* samples, const long long* sample_offsets, const long long* sample_counts,
+                      const long long* frame_offsets, const long long* out_row_offsets, const int* mel_bins,
+                      int batch, long long total_frames, int nfilt, int frame_len, int frame_step,
+                      double preemph, int normalise, float* out, asrk_stream_t stream);
+
 int asrk_lfr_run(const float* in, const long long* in_offsets, float* out, const long long* out_offsets,
                  int batch, int dim, int m, int n, long long total_out_rows, asrk_stream_t stream);
 
