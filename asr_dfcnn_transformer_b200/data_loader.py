@@ -11,12 +11,14 @@ Mirrors /root/reference/lm_and_am/data_loader.py:
   * get_fbank_and_pinyin_data (:213-244): ``input_length = n_frames//8+1`` (no cap),
                     reject ``len_label > input_length`` (strict '>')
 The reference reads files one by one on the host; here the features of the whole
-batch are computed in one GPU pass (in-repo spectrogram) and
-stay on the device.  Pure control logic stays on the host, as in the reference.
+batch are computed in one GPU pass and stay on the device: by default with the mel
+front end the live loader calls (``compute_fbank_from_api``, data_loader.py:129), or
+with the in-repo FFT spectrogram (``front_end="spectrogram"``).
+Pure control logic stays on the host, as in the reference.
 """
 import numpy as np
 
-from . import features
+from . import features, wav_util
 
 FEATURE_MAX_LENGTH = 1600     # util/hparams.py feature_max_length
 LABEL_MAX = 64                # data_loader.py:109,141
@@ -54,7 +56,7 @@ def ctc_input_length(n_frames, capped=True):
     return min(T_CTC_CAP, t) if capped else t
 
 
-def data_generation(signals, py_labels, sym2idx, fs=16000, batch_size=None, device=None):
+def data_generation(signals, py_labels, sym2idx, fs=16000, batch_size=None, device=None, front_end="logfbank"):
     """Batch assembly of data_loader.py:105-162 for in-memory utterances.
 
     signals: list of 1-D int16 / float32 arrays; py_labels: list of pinyin strings.
@@ -67,7 +69,11 @@ def data_generation(signals, py_labels, sym2idx, fs=16000, batch_size=None, devi
     keep, labels, in_len, lab_len = [], [], [], []
     for i, (sig, py) in enumerate(zip(signals, py_labels)):
         try:
-            n = features.n_frames_for(len(sig), fs, "fbank")          # the reference's float expression
+            if front_end == "logfbank":
+                n = wav_util.logfbank_frames(len(sig), wav_util._round_half_up(0.025 * fs),
+                                             wav_util._round_half_up(0.01 * fs))
+            else:
+                n = features.n_frames_for(len(sig), fs, "fbank")      # the reference's float expression
             if n < 1:
                 raise ValueError
             ids = pny2id(py, sym2idx)
@@ -86,8 +92,12 @@ def data_generation(signals, py_labels, sym2idx, fs=16000, batch_size=None, devi
     for r, ids in enumerate(labels):
         batch_label[r, :len(ids)] = ids
     if keep:
-        fb = features.compute_features([signals[i] for i in keep], fs=fs, mode="fbank", device=device,
-                                       padded_rows=FEATURE_MAX_LENGTH)
+        if front_end == "logfbank":
+            fb = wav_util.compute_fbank_from_api_batch([signals[i] for i in keep], fs, 200, device=device,
+                                                       padded_rows=FEATURE_MAX_LENGTH)
+        else:
+            fb = features.compute_features([signals[i] for i in keep], fs=fs, mode="fbank", device=device,
+                                           padded_rows=FEATURE_MAX_LENGTH)
         wav = fb.features.reshape(len(keep), FEATURE_MAX_LENGTH, 200, 1)
     else:
         wav = None

@@ -130,7 +130,7 @@ def test_loader_batch_assembly(tmp_path):
     sigs = [synth.g2_voiced(rng, 24000), synth.g1_white(rng, 4000), synth.g1_white(rng, 16080),
             synth.g1_white(rng, 12345)]
     labs = ["a1 b2", "a1 b2 c3 a1", "c3", "b2 zz"]           # row 1: label >= T_ctc, row 3: unknown symbol
-    wav, il, lab, ll, keep = dl.data_generation(sigs, labs, s2i)
+    wav, il, lab, ll, keep = dl.data_generation(sigs, labs, s2i, front_end="spectrogram")
     assert keep == [0, 2]
     assert tuple(wav.shape) == (2, 1600, 200, 1) and il.tolist() == [19, 13] and ll.tolist() == [2, 1]
     assert lab[0, :3].tolist() == [0, 1, 0] and lab[1, :2].tolist() == [2, 0]
@@ -198,3 +198,24 @@ def test_full_size_c2_batch_properties():
     ref = fbank_ref.compute_fbank(hb["pcm"][i])
     err = zscore_feature_err(out[fo[i]:fo[i + 1]], ref, fbank_ref.compute_fbank_unnormalised(hb["pcm"][i]))
     assert err <= FEATURE_TOL, err
+
+
+def test_loader_batch_assembly_live_front_end(tmp_path):
+    """The same rules with the front end the live loader calls (compute_fbank_from_api)."""
+    from asr_dfcnn_transformer_b200 import data_loader as dl
+    from oracle import psf_ref
+    d = tmp_path / "dict.txt"
+    d.write_text("a1\tx\nb2\ty\n", encoding="utf-8")
+    _, s2i, _ = dl.load_acoustic_vocab(str(d))
+    rng = np.random.default_rng(12)
+    sigs = [synth.g2_voiced(rng, 24000).astype(np.float64) / 32768, synth.g1_white(rng, 8000).astype(np.float64) / 32768]
+    wav, il, lab, ll, keep = dl.data_generation(sigs, ["a1 b2", "b2"], s2i)
+    assert keep == [0, 1] and il.tolist() == [149 // 8 + 1, 49 // 8 + 1]
+    got = wav.cpu().numpy()[..., 0]
+    for r, s in enumerate(sigs):
+        raw = psf_ref.logfbank(s)
+        ref = psf_ref.compute_fbank_from_api(s)
+        live = raw.std(axis=0) > 1e-9
+        n = ref.shape[0]
+        assert feature_err(got[r, :n][:, live], ref[:, live]) <= FEATURE_TOL
+        assert not got[r, n:].any()
