@@ -57,6 +57,7 @@ constexpr int kHopWordsI16 = 84;                     // 80 words of int16 pairs 
 constexpr int kHopWordsF32 = 164;                    // 160 words + 4 pad
 constexpr int kTabDoubles = 1200;                    // window[400] | tw[r][k1] | P[k]
 constexpr int kMaxBatch = 2047;                      // utterances per launch (unit prefix in smem)
+constexpr int kUttCache = 512;                       // utterances whose constants are cached in smem
 
 __device__ const double g_tab[kTabDoubles] = {
 #include "asrk_tables.inc"
@@ -229,7 +230,17 @@ __device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta
 }
 
 // Tile -> utterance, frame range and the utterance's constants (helper thread 0).
-__device__ void fill_meta(const Params& p, const int* tile_off, int tile, int kTile, Meta& m) {
+// per-utterance constants, staged once per CTA when the batch is small enough, so that a
+// claim costs a binary search and a few shared-memory reads instead of a global round trip
+struct UttCache {
+    long long sbase[kUttCache];
+    long long nsamp[kUttCache];
+    long long row0[kUttCache];
+    int nfr[kUttCache];
+    float gain[kUttCache];
+};
+
+__device__ void fill_meta(const Params& p, const int* tile_off, const UttCache* uc, int tile, int kTile, Meta& m) {
     int lo = 0, hi = p.batch - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -242,15 +253,23 @@ __device__ void fill_meta(const Params& p, const int* tile_off, int tile, int kT
     m.b = b;
     m.ntiles_b = tile_off[b + 1] - tile_off[b];
     m.f0 = (tile - tile_off[b]) * kTile;
-    const long long fo = p.frame_offsets[b];
-    m.nfr = p.frame_offsets[b + 1] - fo;
+    if (uc != nullptr) {
+        m.nfr = uc->nfr[b];
+        m.sbase = uc->sbase[b];
+        m.nsamp = uc->nsamp[b];
+        m.row0 = uc->row0[b];
+        m.gain = uc->gain[b];
+    } else {
+        const long long fo = p.frame_offsets[b];
+        m.nfr = p.frame_offsets[b + 1] - fo;
+        m.sbase = p.sample_offsets[b];
+        m.nsamp = p.sample_counts[b];
+        m.row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
+        m.gain = (p.noise && p.gain) ? p.gain[b] : 0.0f;
+    }
     const long long rem = m.nfr - m.f0;
     m.nf = rem < kTile ? (int)rem : kTile;
-    m.sbase = p.sample_offsets[b];
-    m.nsamp = p.sample_counts[b];
-    m.row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
     m.half_mag = 0.5f * ((p.mode == ASRK_SPEC_ASRT) ? (1.0f / (float)m.nsamp) : 1.0f);
-    m.gain = (p.noise && p.gain) ? p.gain[b] : 0.0f;
 }
 
 // ---------------------------------------------------------------------------
@@ -278,7 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);                        // [1200]
     int* tile_off = reinterpret_cast<int*>(tab + kTabDoubles);                // [kMaxBatch + 1]
-    unsigned char* team_base = reinterpret_cast<unsigned char*>(tile_off + kMaxBatch + 1);
+    UttCache* ucache = reinterpret_cast<UttCache*>(tile_off + kMaxBatch + 1);
+    unsigned char* team_base = reinterpret_cast<unsigned char*>(ucache + 1);
     __shared__ Meta meta[kTeams][2];
 
     const int tid = threadIdx.x;
@@ -290,6 +310,17 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
     float* ot = reinterpret_cast<float*>(exch);                               // out tile [16][201] aliases the exchange
 
     for (int i = tid; i < kTabDoubles; i += kThreads) tab[i] = g_tab[i];
+    const UttCache* uc = (p.batch <= kUttCache) ? ucache : nullptr;
+    if (uc != nullptr) {
+        for (int b = tid; b < p.batch; b += kThreads) {
+            const long long fo = p.frame_offsets[b];
+            ucache->nfr[b] = (int)(p.frame_offsets[b + 1] - fo);
+            ucache->sbase[b] = p.sample_offsets[b];
+            ucache->nsamp[b] = p.sample_counts[b];
+            ucache->row0[b] = p.out_row_offsets ? p.out_row_offsets[b] : fo;
+            ucache->gain[b] = (p.noise && p.gain) ? p.gain[b] : 0.0f;
+        }
+    }
     if (warp == 0) {
         // exclusive scan of ceil(n_frames / kUnit) over the utterances
         int carry = 0;
@@ -340,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
             const int tile = next_tile;
             if (tile < total_tiles) {
                 next_tile = atomicAdd(p.counters, 1);
-                fill_meta(p, tile_off, tile, kUnit, mn);
+                fill_meta(p, tile_off, uc, tile, kUnit, mn);
             } else {
                 mn.valid = 0;
             }
@@ -540,7 +571,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(Params p) {
 
 template <bool F32>
 static size_t main_smem_bytes() {
-    return sizeof(double) * kTabDoubles + sizeof(int) * (kMaxBatch + 1) +
+    return sizeof(double) * kTabDoubles + sizeof(int) * (kMaxBatch + 1) + sizeof(UttCache) +
            (size_t)kTeams * (200 * kSub * sizeof(cplx) + sizeof(uint32_t) * Cfg<F32>::kPcmWords) + 16;
 }
 
