@@ -501,17 +501,11 @@ __global__ void __launch_bounds__(256) stats_kernel(Params p) {
     const long long nfr = p.frame_offsets[b + 1] - p.frame_offsets[b];
     for (int k = threadIdx.x; k < kBins; k += blockDim.x) {
         double a1 = 0.0, a2 = 0.0;
-        // fixed order (reproducible); eight loads in flight so that the L2 round trips overlap
-        for (int q0 = t_lo; q0 < t_hi; q0 += 8) {
-            double2 v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                v[e] = (q0 + e < t_hi) ? p.partials[(size_t)(q0 + e) * kBins + k] : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                a1 += v[e].x;
-                a2 += v[e].y;
-            }
+#pragma unroll 4
+        for (int q = t_lo; q < t_hi; ++q) {               // fixed order: reproducible
+            const double2 v = __ldcg(p.partials + (size_t)q * kBins + k);
+            a1 += v.x;
+            a2 += v.y;
         }
         const double n = (double)(nfr > 0 ? nfr : 1);
         const double mean = a1 / n;
