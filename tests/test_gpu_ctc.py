@@ -214,3 +214,30 @@ def test_edge_shapes():
     _check(x, labels, ll, il, 5)
     x = rng.standard_normal((7, 1, 2)).astype(np.float32)
     _check(x, np.array([[0, 0, 0]]), np.array([3]), np.array([5]), 1)      # "0 _ 0 _ 0": the only path
+
+
+def test_full_size_c3_long_utterance_batch_properties():
+    """BASELINE.json configs[2] at full size: 64 utterances, T = 1998 frames, ~300 labels (the
+    generic row / lattice / gradient kernels).  Properties on all of it, the oracle on one row."""
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    rng = np.random.default_rng(3001)
+    V = synth.VOCAB_DICT_TXT
+    il = np.full(64, 1998, dtype=np.int32)
+    il[5], il[17] = 1500, 1001
+    x, labels, ll, il = synth.ctc_batch(rng, il, V, 280, 320)
+    r = ctc.ctc_loss_grad(torch.as_tensor(x).cuda(), labels, ll, il, V - 1, decode=True)
+    loss = r.loss.cpu().numpy()
+    assert int(r.row_status.max()) == 0 and np.all(np.isfinite(loss)) and np.all(loss > 0)
+    T = x.shape[0]
+    valid = np.arange(T)[:, None] < il[None, :]
+    s = torch.abs(r.grad.sum(-1)).cpu().numpy()
+    assert s[valid].max() < 1e-4
+    assert not s[~valid].any()
+    b = 17
+    rl, rg, ok = ctc_ref.ctc_loss_grad_batch(np.ascontiguousarray(x[:, b:b + 1]), labels[b:b + 1], ll[b:b + 1],
+                                             il[b:b + 1], V - 1)
+    np.testing.assert_allclose(loss[b], rl[0], rtol=CTC_RTOL, atol=CTC_ATOL)
+    assert_ctc_grad_close(r.grad[:, b:b + 1].cpu().numpy(), rg, x[:, b:b + 1], il[b:b + 1])
+    ref_tok, _ = ctc_ref.greedy_decode(x[:, :8], il[:8])
+    assert ctc.tokens_to_lists(r.tokens, r.token_len)[:8] == ref_tok

@@ -219,3 +219,31 @@ def test_loader_batch_assembly_live_front_end(tmp_path):
         n = ref.shape[0]
         assert feature_err(got[r, :n][:, live], ref[:, live]) <= FEATURE_TOL
         assert not got[r, n:].any()
+
+
+def test_c4_noise_augmented_batch():
+    """BASELINE.json configs[3] shape (scaled to 96 utterances of ~2 s so that the float64 oracle
+    stays in seconds): float32 signal + coloured noise at 5..10 dB, gains computed on the device,
+    mix fused into the frame load, z-scored features vs the oracle of the mixed signal."""
+    from asr_dfcnn_transformer_b200 import features
+    rng = np.random.default_rng(4000)
+    sigs, noises, dbs = [], [], []
+    for i in range(96):
+        n = int(rng.integers(24000, 40000))
+        sigs.append((synth.g2_voiced(rng, n).astype(np.float32) / 32768.0))
+        x = rng.standard_normal(n)                       # coloured noise stand-in (the generator is an input)
+        nz = np.cumsum(x) if i % 2 else x
+        nz = nz - nz.mean()
+        noises.append((nz / nz.max()).astype(np.float32))
+        dbs.append(int(rng.integers(5, 11)))
+    fb = features.compute_features(sigs, noises=noises, snr_db=dbs)
+    out = fb.features.cpu().numpy()
+    worst = 0.0
+    for i in range(0, 96, 5):
+        s, nz = sigs[i], noises[i]
+        K = np.float32(np.sqrt(np.mean(s ** 2) / np.mean(nz ** 2))) * np.float32(10 ** (-dbs[i] / 20))
+        mixed = (s + np.float32(K) * nz).astype(np.float32)
+        ref = fbank_ref.compute_fbank(mixed)
+        got = out[fb.frame_offsets[i]:fb.frame_offsets[i + 1]]
+        worst = max(worst, zscore_feature_err(got, ref, fbank_ref.compute_fbank_unnormalised(mixed)))
+    assert worst <= 2 * FEATURE_TOL, worst      # the gain itself may differ by one float32 ulp from this numpy recipe
