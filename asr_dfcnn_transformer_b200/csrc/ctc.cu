@@ -7,22 +7,28 @@
 // 48-52), util/utils.py:57-66 decode_ctc.  The arithmetic is TensorFlow's
 // CTCLossOp / CTCGreedyDecoderOp (third-party, restated in oracle/ctc_ref.py).
 //
-// Four launches per call (DESIGN.md "CTC kernels"):
-//   prep    : one thread per utterance -- effective label list (by length / drop
-//             zeros), feasibility, chains of repeated labels.
-//   rows    : one WARP per (t,b) row -- the 5.7 KB row is read once with 16-byte
-//             streaming loads into registers: max, first arg-max (greedy decode),
-//             log-sum-exp, and the gather of the few log-probabilities the lattice
-//             needs (blank + labels).  HBM-bound.
-//   lattice : one CTA per utterance -- log-space alpha / beta over the
-//             label-extended lattice, one (blank,label) state pair per thread so a
-//             step needs ONE neighbour value; periodic exact max-renormalisation
-//             keeps fp32 accurate for T in the thousands.  Latency-bound, tiny.
-//   grad    : one WARP per row -- softmax from the (L2-resident) row and the
-//             stored log-sum-exp, minus the lattice occupancies of blank and
-//             labels, written once with 16-byte stores; zero rows for t >= len.
-//             HBM-bound.  Repeated labels are summed along precomputed chains in
-//             a fixed order (no atomics): results are bit-reproducible.
+// Launches per call (DESIGN.md "CTC kernels"):
+//   prep    : one CTA per utterance -- effective label list (by length / drop zeros),
+//             feasibility, chains of repeated labels, and the flag that tells the generic
+//             kernels whether any utterance needs them.
+//   fused   : one CTA per utterance whose lattice fits a warp and 60 KB of shared memory
+//             (every AISHELL-shaped utterance): rows streamed through per-warp cp.async
+//             buffers (max / first arg-max / log-sum-exp / gather), alpha and beta on two
+//             warps concurrently in the fp32 log2 domain relative to the column maxima,
+//             greedy collapse on a third, then the rows again from L2 for softmax minus
+//             occupancy, written once.  Logits cross HBM once in, the gradient once out.
+//   generic path for long lattices (T in the thousands, hundreds of labels), skipped by a
+//   device flag when every utterance was fused:
+//   rows    : one WARP per (t,b) row, grid-stride -- max, first arg-max, log-sum-exp and the
+//             gather of the log-probabilities the lattice needs.  HBM-bound.
+//   lattice : one CTA per utterance -- log-space alpha / beta, one (blank,label) state pair
+//             per thread so a step needs ONE neighbour value; running values in fp64 with
+//             fp32 transcendentals and periodic max-renormalisation of the stored alpha.
+//   grad    : one WARP per row -- softmax from the (L2-resident) row and the stored
+//             log-sum-exp, minus the lattice occupancies, written once with 16-byte stores;
+//             zero rows for t >= len.  Repeated labels are summed along precomputed chains
+//             in a fixed order (no atomics): results are bit-reproducible.
+//   collapse: greedy decode from the stored arg-max path (warp ballot + prefix count).
 #include <math.h>
 
 #include "asrk_common.cuh"
@@ -64,7 +70,6 @@ struct Params {
     int* argmax;         // [B][T]
     float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (log-softmax)
     float* occ;          // [B][T][2 Ls+1] alpha (scaled) then occupancy, lattice order
-    float* beta;         // [B][T][2 Ls+1] beta (small-lattice kernel only)
     double* coff;        // [B][T]        alpha offsets
     double* logp;        // [B]
     int* need_generic;   // [1] set by prep when some utterance does not fit the fused kernel
@@ -81,7 +86,7 @@ __host__ __device__ __forceinline__ bool small_lattice(int L, int T) {
 }
 
 struct WsLayout {
-    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, beta, coff, logp, flag, total;
+    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, coff, logp, flag, total;
 };
 
 static WsLayout ws_layout(int T, int B, int Ls) {
@@ -97,7 +102,6 @@ static WsLayout ws_layout(int T, int B, int Ls) {
     l.argmax = o;      o = align_up(o + sizeof(int) * BT, 256);
     l.lpl = o;         o = align_up(o + sizeof(float) * BT * (size_t)(Ls + 1), 256);
     l.occ = o;         o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
-    l.beta = o;        o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
     l.coff = o;        o = align_up(o + sizeof(double) * BT, 256);
     l.logp = o;        o = align_up(o + sizeof(double) * (size_t)B, 256);
     l.flag = o;        o = align_up(o + sizeof(int), 256);
@@ -1039,7 +1043,6 @@ static void bind_workspace(Params& p, void* workspace, const WsLayout& l) {
     p.argmax = reinterpret_cast<int*>(ws + l.argmax);
     p.lpl = reinterpret_cast<float*>(ws + l.lpl);
     p.occ = reinterpret_cast<float*>(ws + l.occ);
-    p.beta = reinterpret_cast<float*>(ws + l.beta);
     p.coff = reinterpret_cast<double*>(ws + l.coff);
     p.logp = reinterpret_cast<double*>(ws + l.logp);
     p.need_generic = reinterpret_cast<int*>(ws + l.flag);
