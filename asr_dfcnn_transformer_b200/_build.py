@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libasrk.so")
-SOURCES = ["asrk_api.cu", "spectrogram.cu", "noise.cu", "ctc.cu", "post.cu", "logfbank.cu"]
+SOURCES = ["asrk_api.cu", "spectrogram.cu", "noise.cu", "ctc.cu", "post.cu", "logfbank.cu", "color_noise.cu"]
 HEADERS = ["asrk_common.cuh", "asrk_fft.cuh", os.path.join("..", "..", "include", "asrk.h")]
 NVCC_FLAGS = (os.environ.get("ASRK_EXTRA_NVCC", "").split()) + [
     "-gencode", "arch=compute_100a,code=sm_100a",

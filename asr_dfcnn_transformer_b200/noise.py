@@ -3,13 +3,51 @@
 ``SNR2K`` (noise.py:48-52) and the mix of noise.py:108 run on the GPU; the mix is
 normally not materialised at all but fused into the feature kernel's load stage
 (``features.compute_features(..., noises=..., snr_db=...)``).  ``color_noise``
-(noise.py:17-34) generation is the next row of the scope table:
-until it has its own kernel the noise is an INPUT of this module.
+(noise.py:17-34) draws its normal deviates on the host exactly like the reference
+(numpy's global generator, so ``np.random.seed`` reproduces the reference's noise) and
+runs the two arbitrary-length FFTs, the spectral shaping and the normalisation on the device.
 """
 import numpy as np
 
 from . import _lib
 from . import features
+
+
+def color_noise_batch(normals, colours, device=None):
+    """Coloured noise for a batch: ``normals`` is a list of float64 arrays of N(0,1) deviates
+    (one per utterance, any lengths), ``colours`` the exponents in [-1, 1].  Returns
+    (float32 device tensor with the noises back to back, int64 host offsets [B+1])."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    xs = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in normals]
+    if len(xs) == 0 or any(x.ndim != 1 or x.shape[0] == 0 for x in xs):
+        raise ValueError("normals must be non-empty 1-D arrays")
+    if len(colours) != len(xs):
+        raise ValueError("one colour per utterance")
+    counts = np.array([len(x) for x in xs], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    B, nmax = len(xs), int(counts.max())
+    L = _lib.lib()
+    x_d = torch.from_numpy(np.concatenate(xs)).to(dev)
+    o_d = torch.from_numpy(offs[:-1].copy()).to(dev)
+    c_d = torch.from_numpy(counts).to(dev)
+    col_d = torch.from_numpy(np.asarray(colours, dtype=np.float64)).to(dev)
+    out = torch.empty(int(offs[-1]), dtype=torch.float32, device=dev)
+    nbytes = L.asrk_color_noise_workspace_bytes(B, nmax)
+    ws = features.workspace(nbytes, dev, "cnoise")
+    st = L.asrk_color_noise_run(_lib.ptr(x_d), _lib.ptr(o_d), _lib.ptr(c_d), _lib.ptr(col_d), B, nmax,
+                                _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(st, "asrk_color_noise_run")
+    return out, offs
+
+
+def color_noise(len_noise, type_noise):
+    """noise.py:17-34: one coloured noise of ``len_noise`` samples, float32, zero mean,
+    maximum 1.  The deviates come from ``np.random.normal(0, 1, len_noise)`` like in the
+    reference, so the same ``np.random.seed`` gives the same noise."""
+    x_random = np.random.normal(0, 1, len_noise)
+    out, _ = color_noise_batch([x_random], [float(type_noise)])
+    return out.cpu().numpy()
 
 
 def _pack_pair(signal, noise, dev, torch):

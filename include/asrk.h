@@ -188,6 +188,18 @@ int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long lon
  *                           against truth[b][0..truth_len[b]) (truth_stride <= 64), divided by truth_len when
  *                           normalize != 0 (empty truth: +inf for a non-empty hypothesis, else 0).
  * ------------------------------------------------------------------------ */
+/*   asrk_color_noise_run    replaces util/noise.py:17-34 color_noise after the draw of the normal deviates
+ *                           (`normals`, float64, ragged like the PCM: utterance b owns counts[b] values at
+ *                           offsets[b]; numpy's global generator is not reproducible on the device, the Python
+ *                           surface draws them exactly like the reference): length-N FFT, bins 0..floor(N/2)
+ *                           scaled by (k+1)^colour[b], Hermitian rebuild, real inverse FFT, minus the mean,
+ *                           divided by the MAXIMUM (not the absolute maximum), float32.  Any N (Bluestein). */
+size_t asrk_color_noise_workspace_bytes(int batch, long long max_count);
+int asrk_color_noise_run(const double* normals, const long long* offsets, const long long* counts,
+                         const double* colour /* device float64 [B] */, int batch, long long max_count,
+                         float* out /* device float32, ragged like normals */,
+                         void* workspace, size_t workspace_bytes, asrk_stream_t stream);
+
 /*   asrk_logfbank_run       replaces util/wav_util.py:22-31 compute_fbank_from_api =
  *                           python_speech_features.logfbank(signal, fs, nfilt) + sklearn scale (the feature
  *                           call of the live loaders, lm_and_am/data_loader.py:129): float64 samples (as

@@ -1,0 +1,55 @@
+"""GPU parity: coloured-noise generation (util/noise.py:17-34) vs the golden vectors made by the
+reference's own color_noise and vs the oracle restatement, given the same normal deviates."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fbank_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-6          # float32 output in [-a, 1]: a couple of ulps of 1
+
+
+def test_golden_color_noise(golden_dir):
+    from asr_dfcnn_transformer_b200 import noise
+    files = sorted(glob.glob(os.path.join(golden_dir, "noise_case*.npz")))
+    assert files
+    for f in files:
+        d = np.load(f)
+        out, offs = noise.color_noise_batch([d["x_random"]], [float(d["colour"])])
+        got = out.cpu().numpy()
+        assert got.dtype == np.float32 and got.shape == d["noise"].shape
+        assert np.abs(got - d["noise"]).max() <= TOL, (f, np.abs(got - d["noise"]).max())
+        assert got.max() == 1.0                                   # divided by the maximum, not the abs-maximum
+
+
+def test_ragged_batch_any_length_vs_oracle():
+    from asr_dfcnn_transformer_b200 import noise
+    rng = np.random.default_rng(5)
+    lens = [2, 3, 5, 16, 17, 1000, 1001, 4096, 10007, 80000, 65536, 65537, 37123]
+    cols = [0.0, -1.0, 1.0, 0.3, -0.7, 0.5, -0.5, 1.0, -1.0, 0.1, 0.9, -0.9, 0.0]
+    xs = [rng.standard_normal(n) for n in lens]
+    out, offs = noise.color_noise_batch(xs, cols)
+    got = out.cpu().numpy()
+    for i, (x, c) in enumerate(zip(xs, cols)):
+        ref = fbank_ref.color_noise_from_normal(x, c)
+        g = got[offs[i]:offs[i + 1]]
+        assert np.abs(g - ref).max() <= TOL * max(1.0, np.abs(ref).max()), (lens[i], c, np.abs(g - ref).max())
+
+
+def test_drop_in_surface_reproduces_the_reference_stream():
+    """Same np.random.seed -> the same draw as the reference's color_noise -> the same noise."""
+    from asr_dfcnn_transformer_b200 import noise
+    np.random.seed(1234)
+    got = noise.color_noise(24001, -0.6)
+    np.random.seed(1234)
+    ref = fbank_ref.color_noise_from_normal(np.random.normal(0, 1, 24001), -0.6)
+    assert got.dtype == np.float32 and np.abs(got - ref).max() <= TOL
+    # and the full augmentation chain on the device: noise -> SNR2K -> mix
+    sig = (0.3 * np.sin(np.arange(24001) * 0.05)).astype(np.float32)
+    mixed = noise.mix(sig, got, 7)
+    refm = fbank_ref.mix_noise(sig, got, 7)
+    assert np.array_equal(mixed, refm)
