@@ -85,15 +85,65 @@ def mix(signal, noise, dB):
     return (s + torch.tensor(K, dtype=torch.float32, device=dev) * n).cpu().numpy()
 
 
-def add_noise(signals, noises, dB="random", rng=None):
-    """In-memory branch of noise.py:70-128 (``out_path=None``) with the signals
-    already decoded and the coloured noise supplied: returns (list of float32
-    arrays, name list).  Draws the SNR like noise.py:95-96 when dB == 'random'."""
+def _load_signal(item, sample_rate):
+    """librosa.load(file, sr=sample_rate) for the cases that need no resampling: 16-bit / float
+    PCM wavs at ``sample_rate`` -> mono float32 in [-1, 1].  Arrays pass through."""
+    if isinstance(item, str):
+        import scipy.io.wavfile as wavfile
+        fs, sig = wavfile.read(item)
+        if fs != sample_rate:
+            raise ValueError("resampling is not part of this path: %s is %d Hz" % (item, fs))
+        sig = np.asarray(sig)
+        if sig.ndim == 2:
+            sig = sig.mean(axis=1)
+        if sig.dtype == np.int16:
+            return (sig.astype(np.float32) / 32768.0).astype(np.float32)
+        return sig.astype(np.float32)
+    return np.ascontiguousarray(item, dtype=np.float32)
+
+
+def add_noise(signal_path, n_to_add=1, sample_rate=16000, out_path=None, dB="random", type_noise="random",
+              keep_bits=False):
+    """noise.py:70-128.  ``signal_path``: a list of wav files (or of decoded float32 signals), or a
+    directory.  For every signal and every copy: SNR ~ randint(5, 10) and colour ~ randint(-10, 10)/10
+    from ``random`` (same draws, same order as the reference), coloured noise of the signal's length,
+    gain from the SNR, ``(signal + K * noise).astype(float32)`` -- noise, gain and mix on the device.
+    Returns (list of mixed signals, list of written file names); bad arguments print and return 0
+    like the reference."""
+    import os
     import random
+    if isinstance(signal_path, (list, tuple)):
+        if len(signal_path) == 0 or (isinstance(signal_path[0], str) and not os.path.isfile(signal_path[0])):
+            print("Error signal_path!")
+            return 0
+        items = list(signal_path)
+    elif isinstance(signal_path, str) and os.path.isdir(signal_path):
+        items = [os.path.join(signal_path, f) for f in os.listdir(signal_path)]
+    else:
+        print("Error signal_path!")
+        return 0
     out, names = [], []
-    for s, n in zip(signals, noises):
-        snr_dB = random.randint(5, 10) if dB == "random" else int(dB)
-        out.append(mix(s, n, snr_dB))
+    for l, item in enumerate(items):
+        signal = _load_signal(item, sample_rate)
+        for n in range(n_to_add):
+            snr_dB = random.randint(5, 10) if dB == "random" else int(dB)
+            if type_noise == "random":
+                type_n = random.randint(-10, 10) / 10
+            else:
+                type_n = float(type_noise)
+                if abs(type_n) > 1:
+                    print("Error noise type! Please given a float belongs to [-1, 1] !")
+                    return 0
+            nz = color_noise(len(signal), type_n)
+            mixed = mix(signal, nz, snr_dB)
+            if out_path is not None:
+                import scipy.io.wavfile as wavfile
+                path = out_path + "/" + str(l) + "_" + str(n) + "_" + str(type_n) + "_" + str(snr_dB) + "_dB.wav"
+                names.append(path)
+                y = mixed / np.abs(mixed).max() if np.abs(mixed).max() > 1 else mixed     # noise.py:115-119
+                wavfile.write(path, sample_rate, y.astype(np.float32))
+            else:
+                out.append(mixed)
     return out, names
 
 

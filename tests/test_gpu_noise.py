@@ -53,3 +53,29 @@ def test_drop_in_surface_reproduces_the_reference_stream():
     mixed = noise.mix(sig, got, 7)
     refm = fbank_ref.mix_noise(sig, got, 7)
     assert np.array_equal(mixed, refm)
+
+
+def test_add_noise_in_memory_branch(tmp_path):
+    """noise.py:70-128 with out_path=None: same random draws in the same order as the reference
+    (random.randint for SNR and colour, np.random.normal for the deviates)."""
+    import random
+    import scipy.io.wavfile as wavfile
+    from asr_dfcnn_transformer_b200 import noise
+    t = np.arange(16000)
+    pcm = np.round(9000 * np.sin(t * 0.03)).astype(np.int16)
+    path = str(tmp_path / "a.wav")
+    wavfile.write(path, 16000, pcm)
+    random.seed(3)
+    np.random.seed(3)
+    out, names = noise.add_noise([path], n_to_add=2)
+    assert names == [] and len(out) == 2 and out[0].dtype == np.float32 and out[0].shape == (16000,)
+    random.seed(3)
+    np.random.seed(3)
+    sig = (pcm.astype(np.float32) / 32768.0).astype(np.float32)
+    for k in range(2):
+        snr = random.randint(5, 10)
+        col = random.randint(-10, 10) / 10
+        nz = fbank_ref.color_noise_from_normal(np.random.normal(0, 1, 16000), col)
+        ref = fbank_ref.mix_noise(sig, nz, snr)
+        assert np.abs(out[k] - ref).max() <= 1e-5
+    assert noise.add_noise("/nonexistent/dir") == 0 and noise.add_noise([path], type_noise="3") == 0
