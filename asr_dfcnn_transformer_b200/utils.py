@@ -74,13 +74,9 @@ def label_error_rate(hyp, hyp_len, truth, truth_len):
 
 
 def GetEditDistance(str1, str2):
-    """utils.py:43-53: cost of the difflib opcodes (a 'replace' block costs the longer side)."""
-    leven_cost = 0
-    for tag, i1, i2, j1, j2 in difflib.SequenceMatcher(None, str1, str2).get_opcodes():
-        if tag == "replace":
-            leven_cost += max(i2 - i1, j2 - j1)
-        elif tag == "insert":
-            leven_cost += j2 - j1
-        elif tag == "delete":
-            leven_cost += i2 - i1
-    return leven_cost
+    """utils.py:43-53: NOT a Levenshtein distance but the cost of difflib's opcode blocks -- a
+    'replace' block costs its longer side, 'insert' the inserted length, 'delete' the deleted one."""
+    cost = {"replace": lambda di, dj: max(di, dj), "insert": lambda di, dj: dj, "delete": lambda di, dj: di,
+            "equal": lambda di, dj: 0}
+    ops = difflib.SequenceMatcher(None, str1, str2).get_opcodes()
+    return sum(cost[tag](i2 - i1, j2 - j1) for tag, i1, i2, j1, j2 in ops)

@@ -115,20 +115,16 @@ def mix_noise(signal, noise, dB):
 
 
 def color_noise_from_normal(x_random, type_noise):
-    """noise.py:17-34 with the N(0,1) draw passed in (the reference uses the
-    global numpy RNG at :18; parity is defined given the same draw)."""
-    len_noise = len(x_random)
-    mid_frame = int(np.ceil((len_noise + 1) / 2))
-    x_fft = np.fft.fft(x_random)
-    x_fft_half = x_fft[:mid_frame]
-    n = np.arange(1, mid_frame + 1)
-    x_fft_half = x_fft_half * (n ** type_noise)
-    if len_noise % 2 == 0:
-        x_fft_half_ = np.conj(x_fft_half[-2:0:-1])
-    else:
-        x_fft_half_ = np.conj(x_fft_half[-1:0:-1])
-    noise = np.concatenate([x_fft_half, x_fft_half_])
-    noise = np.real(np.fft.ifft(noise))
-    noise = noise - np.mean(noise)
-    noise = noise / np.max(noise)
-    return noise.astype(np.float32)
+    """noise.py:17-34 with the N(0,1) draw passed in (the reference uses the global numpy RNG at
+    :18; parity is defined given the same draw).  Same numpy operations in the same order (the
+    result is compared bit for bit with the golden vectors): full FFT, bins 0..floor(N/2) times
+    (k+1)^colour (:19-23), the upper bins rebuilt as conjugates of the lower ones -- without the
+    Nyquist bin when N is even (:24-27) -- real part of the inverse FFT, minus the mean, divided by
+    the maximum (:28-31), float32 (:33)."""
+    N = len(x_random)
+    keep = int(np.ceil((N + 1) / 2))
+    lower = np.fft.fft(x_random)[:keep] * (np.arange(1, keep + 1) ** type_noise)
+    mirror = lower[-2:0:-1] if N % 2 == 0 else lower[-1:0:-1]
+    y = np.real(np.fft.ifft(np.concatenate([lower, np.conj(mirror)])))
+    y = y - np.mean(y)
+    return (y / np.max(y)).astype(np.float32)

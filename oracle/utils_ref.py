@@ -1,6 +1,6 @@
 """ORACLE (test infrastructure only): restatement of the helpers next to the hot path.
 
-  build_LFR_features   /root/reference/util/utils.py:7-31, followed line by line
+  build_LFR_features   /root/reference/util/utils.py:7-31 (restated as an index gather)
   edit_distance        tf.edit_distance semantics (tensorflow/core/kernels/edit_distance_op.cc,
                        lib/gtl/edit_distance.h: Levenshtein; normalize divides by the truth
                        length; empty truth -> inf for a non-empty hypothesis, 0 otherwise)
@@ -12,19 +12,14 @@ import numpy as np
 
 
 def build_LFR_features(inputs, m, n):
-    LFR_inputs = []
+    """Restated as one gather: output row i stacks the input rows i*n .. i*n+m-1, and a row index
+    past the end is replaced by the LAST row (utils.py:20-30: the tail is padded by repeating
+    inputs[-1]); ceil(T/n) output rows (utils.py:21)."""
+    inputs = np.asarray(inputs)
     T = inputs.shape[0]
-    T_lfr = int(np.ceil(T / n))
-    for i in range(T_lfr):
-        if m <= T - i * n:
-            LFR_inputs.append(np.hstack(inputs[i * n:i * n + m]))
-        else:
-            num_padding = m - (T - i * n)
-            frame = np.hstack(inputs[i * n:])
-            for _ in range(num_padding):
-                frame = np.hstack((frame, inputs[-1]))
-            LFR_inputs.append(frame)
-    return np.vstack(LFR_inputs)
+    rows = -(-T // n)
+    src = np.minimum(np.arange(rows)[:, None] * n + np.arange(m)[None, :], T - 1)     # [rows, m]
+    return inputs[src].reshape(rows, m * inputs.shape[1])
 
 
 def levenshtein(hyp, truth):
