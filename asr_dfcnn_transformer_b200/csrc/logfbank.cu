@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(kWarps * 32) logfbank_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw = reinterpret_cast<cd*>(smem_raw);                     // W512^k, k <= 256
     int* bins = reinterpret_cast<int*>(tw + kSpec);               // [kMaxFilt + 2]
-    cd* zbuf = reinterpret_cast<cd*>(bins + kMaxFilt + 4);         // [kWarps][256]
+    double* inv_up = reinterpret_cast<double*>(bins + kMaxFilt + 4);   // [kMaxFilt] 1 / (bin j+1 - bin j)
+    double* inv_dn = inv_up + kMaxFilt;                            // [kMaxFilt] 1 / (bin j+2 - bin j+1)
+    cd* zbuf = reinterpret_cast<cd*>(inv_dn + kMaxFilt);           // [kWarps][256]
     double* pbuf = reinterpret_cast<double*>(zbuf + kWarps * kHalf);   // [kWarps][260]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = tid; k < kSpec; k += blockDim.x) {
@@ -51,6 +53,11 @@ __global__ void __launch_bounds__(kWarps * 32) logfbank_kernel(Params p) {
         tw[k] = cd{c, -s};
     }
     for (int k = tid; k < p.nfilt + 2; k += blockDim.x) bins[k] = p.mel_bins[k];
+    for (int j = tid; j < p.nfilt; j += blockDim.x) {
+        const int d1 = p.mel_bins[j + 1] - p.mel_bins[j], d2 = p.mel_bins[j + 2] - p.mel_bins[j + 1];
+        inv_up[j] = d1 > 0 ? 1.0 / (double)d1 : 0.0;
+        inv_dn[j] = d2 > 0 ? 1.0 / (double)d2 : 0.0;
+    }
     __syncthreads();
     cd* z = zbuf + warp * kHalf;
     double* ps = pbuf + warp * 260;
@@ -88,12 +95,23 @@ __global__ void __launch_bounds__(kWarps * 32) logfbank_kernel(Params p) {
         for (int st = 1; st <= 8; ++st) {
             const int half = 1 << (st - 1);
             const int tstep = kNfft >> st;                 // W256^(j * 128/half) = W512^(j * 256/half)
-            for (int q = lane; q < 128; q += 32) {
+            // four butterflies per lane: all loads first, so that their latencies overlap
+            cd a[4], b[4], w[4];
+            int idx[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int q = lane + 32 * e;
                 const int j = q & (half - 1);
-                const int i0 = ((q >> (st - 1)) << st) + j;
-                const cd a = z[i0], bb = cmul(z[i0 + half], tw[j * tstep]);
-                z[i0] = cd{a.x + bb.x, a.y + bb.y};
-                z[i0 + half] = cd{a.x - bb.x, a.y - bb.y};
+                idx[e] = ((q >> (st - 1)) << st) + j;
+                a[e] = z[idx[e]];
+                b[e] = z[idx[e] + half];
+                w[e] = tw[j * tstep];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const cd bb = cmul(b[e], w[e]);
+                z[idx[e]] = cd{a[e].x + bb.x, a[e].y + bb.y};
+                z[idx[e] + half] = cd{a[e].x - bb.x, a[e].y - bb.y};
             }
             __syncwarp();
         }
@@ -111,11 +129,16 @@ __global__ void __launch_bounds__(kWarps * 32) logfbank_kernel(Params p) {
         const long long row = (p.out_row_offsets ? p.out_row_offsets[b] : p.frame_offsets[b]) + fidx;
         for (int j = lane; j < p.nfilt; j += 32) {
             const int b0 = bins[j], b1 = bins[j + 1], b2 = bins[j + 2];
+            const double iu = inv_up[j], id = inv_dn[j];
             double feat = 0.0;
-            for (int i = b0; i < b1; ++i) feat += ps[i] * ((double)(i - b0) / (double)(b1 - b0));
-            for (int i = b1; i < b2; ++i) feat += ps[i] * ((double)(b2 - i) / (double)(b2 - b1));
+            for (int i = b0; i < b1; ++i) feat += ps[i] * ((double)(i - b0) * iu);
+            for (int i = b1; i < b2; ++i) feat += ps[i] * ((double)(b2 - i) * id);
             if (feat == 0.0) feat = 2.220446049250313e-16;   // np.finfo(float).eps
-            p.out[row * p.nfilt + j] = (float)log(feat);
+            // log(feat) = log(m) + e ln 2 with feat = m 2^e, m in [0.5, 1): fp32 log of the mantissa (the
+            // double range of a power spectrum does not fit a float), error ~1e-7 absolute
+            int e;
+            const double mant = frexp(feat, &e);
+            p.out[row * p.nfilt + j] = logf((float)mant) + (float)e * 0.6931471805599453f;
         }
         __syncwarp();
     }
@@ -182,6 +205,7 @@ extern "C" int asrk_logfbank_run(const double* samples, const long long* sample_
     p.batch = batch; p.nfilt = nfilt; p.frame_len = frame_len; p.frame_step = frame_step;
     p.total_frames = total_frames; p.out = out; p.preemph = preemph;
     const size_t smem = sizeof(lfb::cd) * lfb::kSpec + sizeof(int) * (lfb::kMaxFilt + 4) +
+                        sizeof(double) * 2 * lfb::kMaxFilt +
                         sizeof(lfb::cd) * lfb::kWarps * lfb::kHalf + sizeof(double) * lfb::kWarps * 260;
     cudaFuncSetAttribute(lfb::logfbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long blocks = (total_frames + lfb::kWarps - 1) / lfb::kWarps;
