@@ -420,7 +420,7 @@ __device__ __forceinline__ float warp_max_redux(float v) {
 // The logits cross HBM once in and the gradient once out; alpha, beta and the
 // gathered log-probabilities never leave shared memory.
 template <int NV4>
-__global__ void __launch_bounds__(kRowWarps * 32) fused_small_kernel(Params p) {
+__global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ double s_fin;
     const int b = blockIdx.x;

@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256) stats_kernel(Params p) {
 // ---------------------------------------------------------------------------
 // z-score: out = (y - mean) / std, in place; grid (x, utterance), pure streaming
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) normalize_kernel(Params p) {
+__global__ void __launch_bounds__(128) normalize_kernel(Params p) {
     const int b = blockIdx.y;
     __shared__ __align__(16) float s_stat[3 * kBins];
     for (int k = threadIdx.x; k < 3 * kBins; k += blockDim.x) s_stat[k] = p.stats[(size_t)b * 3 * kBins + k];
@@ -653,7 +653,7 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         }
         if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE)) {
             stats_kernel<<<nb, 256, 0, stream>>>(p);
-            normalize_kernel<<<dim3(16, nb), 256, 0, stream>>>(p);
+            normalize_kernel<<<dim3(32, nb), 128, 0, stream>>>(p);   // small CTAs: they fit next to the CTC kernel
         }
     }
     return launch_status();

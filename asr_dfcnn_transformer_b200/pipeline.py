@@ -1,9 +1,12 @@
 """The fused training-side step of the hot path: spectrogram features of a batch
 and CTC loss + gradient of a batch, issued on two CUDA streams.
 
-The feature kernel is bound by the fp64 pipe, the CTC kernels by HBM bandwidth, so
-they overlap well: the persistent feature kernel is capped to ``feature_ctas`` SMs
-and the CTC kernels fill the rest.  Nothing here synchronises with the host.
+The persistent feature kernel (enqueued first, on a side stream) owns every SM while it
+runs; the CTC kernels (main stream) fill the SMs as its CTAs retire, and the small z-score
+CTAs fit next to the CTC kernel's two CTAs per SM.  Measured both ways round: features
+first is 1-2 % faster than CTC first.  Nothing here synchronises with the host.
+``shard_bounds`` / ``all_reduce_loss`` are the multi-GPU plumbing: contiguous batch shards,
+one SUM all-reduce of [sum loss, n] per step.
 """
 from . import _lib, ctc, features
 
