@@ -957,6 +957,34 @@ __global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const 
     if (threadIdx.x == 0) { out2[0] = s_sum[0]; out2[1] = (double)s_cnt[0]; }
 }
 
+// Host -> device staging of the logits without their padding: rows t < input_len[b] only are pulled
+// straight out of (mapped, pinned) host memory by the SMs with 16-byte loads and written to the device
+// tensor; rows t >= input_len[b] are never read (the CTC kernels never look at them).  One warp per
+// row, grid-stride; every warp keeps several 16-byte requests per lane in flight to cover the PCIe
+// round trip.
+__global__ void __launch_bounds__(256) stage_logits_kernel(const float* src, long long sst, long long ssb,
+                                                           float* dst, long long dst_t, long long dst_b,
+                                                           const int* input_len, int T, int B, int V) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)T * B;
+    const int V4 = V >> 2;
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+        const int t = (int)(row / B), b = (int)(row % B);
+        if (t >= input_len[b]) continue;
+        const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)t * sst + (size_t)b * ssb);
+        float4* d4 = reinterpret_cast<float4*>(dst + (size_t)t * dst_t + (size_t)b * dst_b);
+        for (int i0 = lane; i0 < V4; i0 += 32 * 6) {
+            float4 v[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e)
+                if (i0 + 32 * e < V4) v[e] = ldg_stream(s4 + i0 + 32 * e);
+#pragma unroll
+            for (int e = 0; e < 6; ++e)
+                if (i0 + 32 * e < V4) d4[i0 + 32 * e] = v[e];
+        }
+    }
+}
+
 static int pick_nv4(const Params& p, const void* a, long long st, long long sb, const void* g,
                     long long gt, long long gb) {
     // vector path: V % 4 == 0, 16-byte aligned bases and strides, V <= 2048
@@ -1152,5 +1180,18 @@ extern "C" int asrk_ctc_loss_sum_run(const float* loss, const int* row_status, i
                                      asrk_stream_t stream_) {
     if (B < 0 || !out2 || (B > 0 && !loss)) return ASRK_E_BADARG;
     loss_sum_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(loss, row_status, B, out2);
+    return launch_status();
+}
+
+extern "C" int asrk_ctc_stage_logits_run(const float* src, long long src_stride_t, long long src_stride_b,
+                                         float* dst, long long dst_stride_t, long long dst_stride_b,
+                                         const int* input_len, int T, int B, int V, asrk_stream_t stream_) {
+    if (T < 0 || B < 0 || V < 1) return ASRK_E_BADARG;
+    if (T == 0 || B == 0) return ASRK_OK;
+    if (!src || !dst || !input_len) return ASRK_E_BADARG;
+    if (V % 4 != 0 || (src_stride_t % 4) || (src_stride_b % 4) || (dst_stride_t % 4) || (dst_stride_b % 4)) return ASRK_E_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return ASRK_E_ALIGN;
+    stage_logits_kernel<<<sm_count() * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+        src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, T, B, V);
     return launch_status();
 }

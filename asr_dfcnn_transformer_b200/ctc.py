@@ -19,6 +19,8 @@ the logits is produced by the same kernel pass as the loss.
 """
 from collections import namedtuple
 
+import ctypes
+
 import numpy as np
 
 from . import _lib
@@ -100,6 +102,25 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
                                          int(phases))
     _lib.check(rc, "asrk_ctc_loss_grad_run")
     return CtcResult(loss, grad, status, tokens, tlen, nsl)
+
+
+def stage_logits(host_logits, input_len, out=None, layout="tbv", stream=None):
+    """Host -> device copy of the logits WITHOUT their padding: ``host_logits`` is a pinned host
+    tensor ([T,B,V] or [B,T,V]); only the rows t < input_len[b] cross PCIe (the SMs read the
+    mapped host memory directly).  ``input_len``: int32 device tensor.  Returns the device tensor
+    (rows past input_len are left as they were: the CTC kernels never read them)."""
+    torch = _lib.require_cuda()
+    if not host_logits.is_pinned():
+        raise ValueError("stage_logits needs pinned (page-locked) host memory")
+    dev = input_len.device
+    if out is None:
+        out = torch.empty(host_logits.shape, dtype=torch.float32, device=dev)
+    T, B, V, st, sb = _strides(host_logits, layout)
+    _, _, _, dt, db = _strides(out, layout)
+    rc = _lib.lib().asrk_ctc_stage_logits_run(ctypes.c_void_p(host_logits.data_ptr()), st, sb, _lib.ptr(out), dt, db,
+                                              _lib.ptr(input_len), T, B, V, _lib.stream_ptr(stream))
+    _lib.check(rc, "asrk_ctc_stage_logits_run")
+    return out
 
 
 def loss_sum(loss, row_status=None, out=None, stream=None):

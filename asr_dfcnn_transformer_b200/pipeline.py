@@ -52,6 +52,20 @@ class HotPathStep:
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
 
+    def from_host(self, h_samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
+                  h_logits, h_labels, label_len, input_len, blank=None, logits_dev=None, **kw):
+        """The same step with the per-step inputs in PINNED HOST memory: PCM and labels are copied
+        host -> device, the logits are staged without their padding (``ctc.stage_logits``: only rows
+        t < input_len[b] cross PCIe), then the kernels run.  Lengths / offsets are device tensors.
+        Returns (features, CtcResult, h2d_bytes)."""
+        torch = self.torch
+        samples = h_samples.to(self.device, non_blocking=True)
+        labels = h_labels.to(self.device, non_blocking=True)
+        logits = ctc.stage_logits(h_logits, input_len, out=logits_dev, layout=kw.get("layout", "tbv"))
+        feats, res = self(samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames, logits, labels,
+                          label_len, input_len, blank, **kw)
+        return feats, res, samples.numel() * samples.element_size() + labels.numel() * labels.element_size()
+
     def __call__(self, samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
                  logits, labels, label_len, input_len, blank=None, feat_out=None, grad_out=None,
                  grad_scale=None, mode="fbank", decode=False, layout="tbv"):

@@ -427,15 +427,14 @@ def main():
     h2d = d2h = 0
 
     def e2e_step(db):
+        # the public host-buffer entry point: PCM + labels host -> device, logits staged without
+        # their padding (only rows t < input_len cross PCIe), kernels, loss back to the host
         nonlocal h2d, d2h
-        samples = db.h_samples.to(dev, non_blocking=True)
-        logits = db.h_logits.to(dev, non_blocking=True)
-        labels = db.h_labels.to(dev, non_blocking=True)
-        features.spectrogram_device(samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat)
-        r = ctc.ctc_loss_grad(logits, labels, db.label_len, db.input_len, V - 1, grad_scale=db.grad_scale,
-                              grad_out=db.grad)
+        _, r, nbytes = hot_path(dev).from_host(db.h_samples, db.so, db.sc, db.fo, db.B, db.total_frames, db.h_logits,
+                                               db.h_labels, db.label_len, db.input_len, V - 1, logits_dev=db.logits,
+                                               feat_out=db.feat, grad_out=db.grad, grad_scale=db.grad_scale)
         loss_host = r.loss.cpu()          # device -> host read of the step's result (synchronises)
-        h2d = db.h_samples.numel() * 2 + db.h_logits.numel() * 4 + db.h_labels.numel() * 4
+        h2d = nbytes + 4 * V * int(db.hb["input_len"].astype(np.int64).sum())
         d2h = loss_host.numel() * 4
         return loss_host
 

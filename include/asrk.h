@@ -149,6 +149,16 @@ int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long st
                            float* neg_sum_logits,               /* device float32 [B] or NULL     */
                            void* workspace, size_t workspace_bytes, asrk_stream_t stream);
 
+/* Host -> device staging of the logits without their padding.  `src` is the caller's logits in pinned
+ * (page-locked, device-mapped) HOST memory, `dst` the device tensor the CTC entry points will read;
+ * element (t,b,v) sits at t*stride_t + b*stride_b + v on both sides (so [T,B,V] and [B,T,V] both work,
+ * and the two sides may differ).  Only rows t < input_len[b] are transferred -- the padding of a
+ * [T,B,V] batch (28 % of an AISHELL-shaped one) never crosses PCIe.  V % 4 == 0, 16-byte aligned. */
+int asrk_ctc_stage_logits_run(const float* src, long long src_stride_t, long long src_stride_b,
+                              float* dst, long long dst_stride_t, long long dst_stride_b,
+                              const int* input_len /* device int32 [B] */, int T, int B, int V,
+                              asrk_stream_t stream);
+
 /* Batch reduction feeding the path's only collective (tf.reduce_mean(self.loss),
  * acoustic_model2.py:83): out2[0] = sum of loss[b] over the rows with row_status[b] ==
  * ASRK_ROW_OK (all rows when row_status == NULL), out2[1] = their number, float64,

@@ -241,3 +241,22 @@ def test_full_size_c3_long_utterance_batch_properties():
     assert_ctc_grad_close(r.grad[:, b:b + 1].cpu().numpy(), rg, x[:, b:b + 1], il[b:b + 1])
     ref_tok, _ = ctc_ref.greedy_decode(x[:, :8], il[:8])
     assert ctc.tokens_to_lists(r.tokens, r.token_len)[:8] == ref_tok
+
+
+def test_stage_logits_copies_only_valid_rows():
+    import torch
+    from asr_dfcnn_transformer_b200 import ctc
+    rng = np.random.default_rng(12)
+    for layout, shape in (("tbv", (9, 5, 64)), ("btv", (5, 9, 64))):
+        h = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).pin_memory()
+        il = torch.tensor([9, 1, 4, 7, 2], dtype=torch.int32, device="cuda")
+        out = torch.full(shape, -7.0, dtype=torch.float32, device="cuda")
+        ctc.stage_logits(h, il, out=out, layout=layout)
+        got, ref = out.cpu().numpy(), h.numpy()
+        if layout == "btv":
+            got, ref = got.transpose(1, 0, 2), ref.transpose(1, 0, 2)
+        for b, n in enumerate([9, 1, 4, 7, 2]):
+            assert np.array_equal(got[:n, b], ref[:n, b])
+            assert np.all(got[n:, b] == -7.0)              # padding rows never touched
+    with pytest.raises(ValueError):
+        ctc.stage_logits(torch.zeros(2, 2, 4), il[:2])
