@@ -220,12 +220,24 @@ __device__ __forceinline__ void lds_row(const float4* rb, int V4, int lane, RowR
         else r.v[k] = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
     }
 }
-// start the copy of one row into the warp's buffer: 16-byte LDGSTS through L2 only, with
-// an L2 eviction priority (first read: keep the row for the gradient pass; second: drop it)
-__device__ __forceinline__ void issue_row(float4* rb, const float* row, int V4, int lane, uint64_t policy) {
-    const float4* x4 = reinterpret_cast<const float4*>(row);
-    for (int i = lane; i < V4; i += 32) cp_async16_hint(rb + i, x4 + i, policy);
-    cp_async_commit();
+// start the copy of one row into the warp's buffer: ONE TMA bulk copy (cp.async.bulk) issued by
+// lane 0 and completed on the warp's mbarrier, with an L2 eviction priority (first read: keep the
+// row for the gradient pass; second read: drop it)
+__device__ __forceinline__ void issue_row(float4* rb, const float* row, int V4, int lane, uint64_t policy,
+                                          uint64_t* bar) {
+    if (lane == 0) tma_load_1d(rb, row, (unsigned)V4 * 16u, bar, policy);
+}
+// The bulk copy writes through the async proxy, which is not ordered after shared-memory LOADS
+// that were merely issued: before the buffer is handed back, every lane consumes what it loaded
+// (a register dependence on all of its LDS results), then the warp converges.  Measured: without
+// this a few rows in 10^4 were overwritten under the reader in the L2-hit gradient pass.
+template <int NV4>
+__device__ __forceinline__ void release_row(const float4 (&v)[NV4]) {
+    unsigned dep = 0;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) dep |= __float_as_uint(v[k].w);
+    asm volatile("" ::"r"(dep) : "memory");
+    __syncwarp();
 }
 
 // first maximum over the row: strict '>' scan order == lowest index among equals
@@ -465,15 +477,22 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     // ---- A: row statistics + gather -----------------------------------------
     const int gc = (lane == 0) ? p.blank : ((lane < W) ? eff[lane - 1] : 0);   // class gathered by this lane
     const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
-    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, keep);
+    __shared__ uint64_t s_bar[kRowWarps];          // one mbarrier per warp: the warp's row has landed
+    uint64_t* bar = s_bar + warp;
+    unsigned parity = 0;
+    if (lane == 0) mbar_init(bar, 1);
+    mbar_fence_init();
+    __syncwarp();
+    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, keep, bar);
     for (int t = warp; t < T; t += kRowWarps) {
-        cp_async_wait<0>();
-        __syncwarp();
+        mbar_wait(bar, parity);
+        parity ^= 1;
         RowRegs<NV4> r;
         lds_row(rb, V4, lane, r);
-        const float xg = reinterpret_cast<const float*>(rb)[gc];
-        __syncwarp();
-        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane, keep);
+        float xg = reinterpret_cast<const float*>(rb)[gc];
+        asm volatile("" : "+f"(xg));
+        release_row(r.v);
+        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane, keep, bar);
         float m;
         int am;
         row_argmax(r, lane, m, am);
@@ -634,7 +653,7 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     const unsigned same = __match_any_sync(0xffffffffu, my_lab);
     const bool owner = (lane < L) && ((int)__ffs(same) - 1 == lane) && (my_lab != p.blank);
     const bool is_blank_lab = (lane < L) && (my_lab == p.blank);
-    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, drop);      // L2 hits: read a moment ago
+    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, drop, bar);      // L2 hits: read a moment ago
     for (int t = warp; t < p.T; t += kRowWarps) {
         float* g = p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b;
         float4* g4 = reinterpret_cast<float4*>(g);
@@ -644,16 +663,16 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             continue;
         }
         const float nlse2 = -slse[t] * kLog2e;
-        cp_async_wait<0>();
-        __syncwarp();
+        mbar_wait(bar, parity);
+        parity ^= 1;
         float4 v[NV4];
 #pragma unroll
         for (int k = 0; k < NV4; ++k) {
             const int idx = lane + 32 * k;
-            if (idx < V4) v[k] = rb[idx];
+            v[k] = (idx < V4) ? rb[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncwarp();
-        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane, drop);
+        release_row(v);
+        if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane, drop, bar);
 #pragma unroll
         for (int k = 0; k < NV4; ++k) {
             const int idx = lane + 32 * k;
