@@ -12,11 +12,12 @@ LIB_PATH = os.path.join(_PKG_DIR, "libasrk.so")
 
 OK = 0
 E_BADARG, E_SHAPE, E_ALIGN, E_WORKSPACE, E_CUDA = -1, -2, -3, -4, -5
-ROW_OK, ROW_INFEASIBLE, ROW_NOT_ENOUGH_TIME, ROW_BAD_LENGTH = 0, 1, 2, 3
+ROW_OK, ROW_INFEASIBLE, ROW_NOT_ENOUGH_TIME, ROW_BAD_LENGTH, ROW_NOT_SMALL = 0, 1, 2, 3, 4
 SPEC_FBANK, SPEC_ASRT, SPEC_FBANK_RAW = 0, 1, 2
 DTYPE_I16, DTYPE_F32 = 0, 1
 LABELS_BY_LENGTH, LABELS_DROP_ZEROS = 0, 1
 PHASE_ALL = 0xffff
+CTC_SMALL_ONLY = 0x10000
 PHASE_SPEC_SETUP, PHASE_SPEC_MAIN, PHASE_SPEC_NORMALIZE = 1, 2, 4
 PHASE_CTC_PREP, PHASE_CTC_ROWS, PHASE_CTC_LATTICE, PHASE_CTC_GRAD, PHASE_CTC_COLLAPSE = 1, 2, 4, 8, 16
 PHASE_CTC_FUSED = 32
@@ -31,6 +32,7 @@ SIGNATURES = {
                                   _vp]),
     "asrk_snr2k_run": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "asrk_ctc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "asrk_ctc_fits_fused": (_i, [_i, _i]),
     "asrk_ctc_loss_grad_run": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp,
                                     _ll, _ll, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "asrk_spectrogram_run_phases": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp, _vp,

@@ -75,6 +75,8 @@ struct Params {
     int* need_generic;   // [1] set by prep when some utterance does not fit the fused kernel
     int Ls;              // label_stride
     int fused;           // 1: utterances with a small lattice are done by fused_small_kernel
+    int prep_fused;      // 1: fused_small_kernel prepares its own utterance (no prep_kernel launch)
+    int small_only;      // 1: the caller bounded the batch (ASRK_CTC_SMALL_ONLY): no generic kernels follow
 };
 
 // Utterances whose lattice fits one warp (L <= 31 labels -> 32 state pairs) and whose
@@ -112,30 +114,31 @@ static WsLayout ws_layout(int T, int B, int Ls) {
 // ---------------------------------------------------------------------------
 // prep
 // ---------------------------------------------------------------------------
-// One CTA per utterance, one thread per label slot.
-__global__ void __launch_bounds__(1024) prep_kernel(Params p) {
-    extern __shared__ int sh[];            // [Ls] effective labels, then [33] scan scratch
-    const int b = blockIdx.x;
+// One CTA per utterance, one thread per label slot (the CTA has >= label_stride threads);
+// `sh` holds label_stride + 40 ints.  Every thread returns (row status, effective length).
+struct PrepOut {
+    int status, L;
+};
+__device__ __forceinline__ PrepOut prep_body(const Params& p, int b, int* sh) {
     const int j = threadIdx.x;
     const int Ls = p.label_stride;
-    int* seff = sh;
-    int* scr = sh + (Ls > 0 ? Ls : 1);
-    __shared__ int s_status;
+    int* seff = sh;                        // [Ls] effective labels
+    int* scr = sh + (Ls > 0 ? Ls : 1);     // [33] scan scratch, [34] status, [35] L
     const int* lab = p.labels + (size_t)b * p.label_stride;
     int* eff = p.eff_labels + (size_t)b * p.Ls;
     int* nxt = p.chain_next + (size_t)b * p.Ls;
     int* fst = p.chain_first + (size_t)b * p.Ls;
     const int tl = p.input_len[b];
-    if (j == 0) s_status = (tl < 1 || tl > p.T) ? ASRK_ROW_BAD_LENGTH : ASRK_ROW_OK;
+    if (j == 0) scr[34] = (tl < 1 || tl > p.T) ? ASRK_ROW_BAD_LENGTH : ASRK_ROW_OK;
     int Lby = 0;
     if (p.label_mode == ASRK_LABELS_BY_LENGTH) {
         Lby = p.label_len[b];
         if (Lby < 0 || Lby > Ls) Lby = -1;
     }
     __syncthreads();
-    if (Lby < 0) {
+    if (Lby < 0) {                         // uniform over the CTA
         if (j == 0) { p.eff_len[b] = 0; p.row_status[b] = ASRK_ROW_BAD_LENGTH; }
-        return;
+        return PrepOut{ASRK_ROW_BAD_LENGTH, 0};
     }
     // keep flag: by length (Keras) or every non-zero entry (dense_to_sparse, acoustic_model2.py:71)
     const int v = (j < Ls) ? lab[j] : 0;
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(1024) prep_kernel(Params p) {
     const int L = scr[32];
     if (keep) {
         int c = v;
-        if (c < 0 || c >= p.V) { atomicExch(&s_status, ASRK_ROW_BAD_LENGTH); c = 0; }
+        if (c < 0 || c >= p.V) { atomicExch(&scr[34], ASRK_ROW_BAD_LENGTH); c = 0; }
         seff[scr[warp] + within] = c;
     }
     __syncthreads();
@@ -181,12 +184,26 @@ __global__ void __launch_bounds__(1024) prep_kernel(Params p) {
     }
     const int repeats = __syncthreads_count(rep);
     if (j == 0) {
-        int status = s_status;
+        int status = scr[34];
         if (status == ASRK_ROW_OK && tl < L + repeats) status = ASRK_ROW_NOT_ENOUGH_TIME;
-        p.eff_len[b] = (status == ASRK_ROW_BAD_LENGTH) ? 0 : L;
+        const int Le = (status == ASRK_ROW_BAD_LENGTH) ? 0 : L;
+        if (status != ASRK_ROW_BAD_LENGTH && !small_lattice(L, tl < p.T ? tl : p.T)) {
+            // a bounded batch (no generic kernels behind this one) must not hold such a row
+            if (p.small_only) status = ASRK_ROW_NOT_SMALL;
+            else atomicOr(p.need_generic, 1);
+        }
+        p.eff_len[b] = Le;
         p.row_status[b] = status;
-        if (status != ASRK_ROW_BAD_LENGTH && !small_lattice(L, tl < p.T ? tl : p.T)) atomicOr(p.need_generic, 1);
+        scr[34] = status;
+        scr[35] = Le;
     }
+    __syncthreads();
+    return PrepOut{scr[34], scr[35]};
+}
+
+__global__ void __launch_bounds__(1024) prep_kernel(Params p) {
+    extern __shared__ int sh[];
+    prep_body(p, blockIdx.x, sh);
 }
 
 // ---------------------------------------------------------------------------
@@ -438,11 +455,36 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int status = p.row_status[b];
-    const int L = p.eff_len[b];
     const int T = p.input_len[b];
+    const int V4 = p.V >> 2;
+    // one row buffer per warp behind the lattice region, filled by TMA bulk copies on the warp's
+    // mbarrier: the next row of the warp arrives while the current one is reduced, so HBM / L2
+    // latency is off the chain.  The first rows are requested before anything else is known about
+    // the utterance (the label preparation below runs under their latency).
+    float4* rb = reinterpret_cast<float4*>(sm + kSmallSmemFloats) + (size_t)warp * V4;
+    const float* xb = p.logits + (size_t)b * p.stride_b;
+    const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+    __shared__ uint64_t s_bar[kRowWarps];
+    uint64_t* bar = s_bar + warp;
+    unsigned parity = 0;
+    if (lane == 0) mbar_init(bar, 1);
+    mbar_fence_init();
+    __syncwarp();
+    const bool prefetched = (T >= 1 && T <= p.T && warp < T);
+    if (prefetched) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, keep, bar);
+    int status, L;
+    if (p.prep_fused) {
+        __shared__ int s_prep[kRowWarps * 32 + 40];
+        const PrepOut po = prep_body(p, b, s_prep);
+        status = po.status;
+        L = po.L;
+    } else {
+        status = p.row_status[b];
+        L = p.eff_len[b];
+    }
     const double ninf = (double)kNegInf;
-    if (status == ASRK_ROW_BAD_LENGTH) {
+    if (status == ASRK_ROW_BAD_LENGTH || status == ASRK_ROW_NOT_SMALL) {
+        if (prefetched) mbar_wait(bar, 0);      // no bulk copy may be in flight when the CTA exits
         if (tid == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
         if (p.tokens && tid == 0) { p.token_len[b] = 0; if (p.neg_sum_logits) p.neg_sum_logits[b] = 0.f; }
         if (p.grad) {   // keep the gradient defined: zeros
@@ -453,7 +495,10 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         }
         return;
     }
-    if (!small_lattice(L, T)) return;          // generic path
+    if (!small_lattice(L, T)) {                 // generic path
+        if (prefetched) mbar_wait(bar, 0);
+        return;
+    }
     const int W = L + 1;                        // row width of the gathered log-probs
     const int Ub = 2 * L + 1;                   // lattice states
     double* sC = reinterpret_cast<double*>(sm); // [T] sum_{s<=t} log c_s
@@ -468,22 +513,9 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     float* sal = slp + T * W;                   // [T][Ub]
     float* sbe = sal + T * Ub;                  // [T][Ub]
     const int* eff = p.eff_labels + (size_t)b * p.Ls;
-    const int V4 = p.V >> 2;
-    // one row buffer per warp behind the lattice region: the next row of the warp arrives
-    // by cp.async while the current one is reduced, so HBM / L2 latency is off the chain
-    float4* rb = reinterpret_cast<float4*>(sm + kSmallSmemFloats) + (size_t)warp * V4;
-    const float* xb = p.logits + (size_t)b * p.stride_b;
 
     // ---- A: row statistics + gather -----------------------------------------
     const int gc = (lane == 0) ? p.blank : ((lane < W) ? eff[lane - 1] : 0);   // class gathered by this lane
-    const uint64_t keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
-    __shared__ uint64_t s_bar[kRowWarps];          // one mbarrier per warp: the warp's row has landed
-    uint64_t* bar = s_bar + warp;
-    unsigned parity = 0;
-    if (lane == 0) mbar_init(bar, 1);
-    mbar_fence_init();
-    __syncwarp();
-    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, keep, bar);
     for (int t = warp; t < T; t += kRowWarps) {
         mbar_wait(bar, parity);
         parity ^= 1;
@@ -1074,6 +1106,10 @@ extern "C" size_t asrk_ctc_workspace_bytes(int T, int B, int label_stride) {
     return ws_layout(T, B, label_stride < 1 ? 1 : label_stride).total;
 }
 
+extern "C" int asrk_ctc_fits_fused(int max_input_len, int max_label_len) {
+    return (max_input_len >= 0 && max_label_len >= 0 && small_lattice(max_label_len, max_input_len)) ? 1 : 0;
+}
+
 extern "C" size_t asrk_ctc_decode_workspace_bytes(int T, int B) {
     if (T <= 0 || B <= 0) return 0;
     return ws_layout(T, B, 1).total;
@@ -1133,14 +1169,23 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
 
     const int nv4 = pick_nv4(p, logits, stride_t, stride_b, grad, gstride_t, gstride_b);
     p.fused = (nv4 > 0) ? 1 : 0;
+    // the fused kernel prepares its own utterance when both phases are asked for in one call
+    p.prep_fused = (p.fused && (phases & ASRK_PHASE_CTC_PREP) && (phases & ASRK_PHASE_CTC_FUSED) &&
+                    Ls <= kRowWarps * 32) ? 1 : 0;
+    // a batch the caller bounded to small lattices needs none of the generic kernels
+    p.small_only = (p.fused && (phases & ASRK_CTC_SMALL_ONLY)) ? 1 : 0;
     if (phases & ASRK_PHASE_CTC_PREP) {
-        if (cudaMemsetAsync(p.need_generic, 0, sizeof(int), stream) != cudaSuccess) return ASRK_E_CUDA;
-        const int pt = ((label_stride > 0 ? label_stride : 1) + 31) / 32 * 32;
-        prep_kernel<<<B, pt, sizeof(int) * (Ls + 40), stream>>>(p);
+        if (!p.small_only && cudaMemsetAsync(p.need_generic, 0, sizeof(int), stream) != cudaSuccess)
+            return ASRK_E_CUDA;
+        if (!p.prep_fused) {
+            const int pt = ((label_stride > 0 ? label_stride : 1) + 31) / 32 * 32;
+            prep_kernel<<<B, pt, sizeof(int) * (Ls + 40), stream>>>(p);
+        }
     }
     // utterances with a small lattice: one fused CTA each; the row-parallel kernels
     // below skip them and handle the long ones
     if (p.fused && (phases & ASRK_PHASE_CTC_FUSED)) launch_fused(p, nv4, stream);
+    if (p.small_only) return launch_status();
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
     if (phases & ASRK_PHASE_CTC_LATTICE)

@@ -55,10 +55,16 @@ def _i32(x, dev, torch):
 
 def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="by_length",
                   layout="tbv", grad_scale=None, want_grad=True, decode=False, grad_out=None,
-                  stream=None, phases=_lib.PHASE_ALL, outputs=None):
+                  stream=None, phases=_lib.PHASE_ALL, outputs=None, bounds=None):
     """Raw op: one fused pass.  logits float32 CUDA tensor ``[T,B,V]`` ('tbv') or
     ``[B,T,V]`` ('btv'); labels int32 ``[B,Lmax]``.  Returns CtcResult of device
-    tensors (no synchronisation, statuses are NOT checked here)."""
+    tensors (no synchronisation, statuses are NOT checked here).
+
+    ``bounds = (max input_len, max label_len)`` of the batch, when the host knows them (the
+    reference's loader builds both length vectors on the host, data_loader.py:132-148): a batch
+    whose largest lattice fits the fused kernel is then ONE launch -- the three generic kernels
+    that would otherwise be launched to find nothing to do are skipped.  Lengths given as host
+    arrays are bounded here; a row that breaks the promise gets row_status ROW_NOT_SMALL."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     if logits.dtype != torch.float32 or not logits.is_cuda:
@@ -71,6 +77,13 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
         torch.as_tensor(np.asarray(labels).astype(np.int32)).to(dev)
     labels = labels.reshape(B, -1).contiguous()
     Ls = labels.shape[1]
+    if bounds is None and not isinstance(input_len, torch.Tensor) and np.size(input_len):
+        lmax = Ls if (label_len is None or isinstance(label_len, torch.Tensor) or not np.size(label_len)) \
+            else int(np.max(label_len))
+        bounds = (int(np.max(input_len)), lmax)
+    if bounds is not None and phases == _lib.PHASE_ALL and \
+            L.asrk_ctc_fits_fused(max(int(bounds[0]), 0), max(int(bounds[1]), 0)):
+        phases = phases | _lib.CTC_SMALL_ONLY
     input_len = _i32(input_len, dev, torch)
     label_len = _i32(label_len, dev, torch) if label_len is not None else None
     mode = _lib.LABELS_BY_LENGTH if label_mode == "by_length" else _lib.LABELS_DROP_ZEROS
@@ -145,6 +158,10 @@ def _raise_on_status(status):
     if len(bad):
         raise InvalidArgumentError("sequence_length / label_length / label value out of range in "
                                    "batch rows %s" % bad.tolist())
+    bad = np.nonzero(st == _lib.ROW_NOT_SMALL)[0]
+    if len(bad):
+        raise ValueError("ctc_loss_grad(bounds=...) promised small lattices, batch rows %s are larger"
+                         % bad.tolist())
 
 
 def _make_fn():

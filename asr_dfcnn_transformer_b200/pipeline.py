@@ -68,7 +68,7 @@ class HotPathStep:
 
     def __call__(self, samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
                  logits, labels, label_len, input_len, blank=None, feat_out=None, grad_out=None,
-                 grad_scale=None, mode="fbank", decode=False, layout="tbv"):
+                 grad_scale=None, mode="fbank", decode=False, layout="tbv", ctc_bounds=None):
         """Returns (features, CtcResult).  Both are complete, in stream order, on the
         current stream when this returns (no host synchronisation)."""
         torch = self.torch
@@ -80,6 +80,6 @@ class HotPathStep:
                                                 total_frames, mode, out=feat_out, cta_limit=self.feature_ctas)
             self._ev_join.record(self.side)
         res = ctc.ctc_loss_grad(logits, labels, label_len, input_len, blank, layout=layout,
-                                grad_scale=grad_scale, grad_out=grad_out, decode=decode)
+                                grad_scale=grad_scale, grad_out=grad_out, decode=decode, bounds=ctc_bounds)
         cur.wait_event(self._ev_join)
         return feats, res

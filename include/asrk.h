@@ -44,6 +44,8 @@ typedef void* asrk_stream_t;
 #define ASRK_ROW_NOT_ENOUGH_TIME 2 /* input_len < L + #repeats: TF raises InvalidArgument      */
 #define ASRK_ROW_BAD_LENGTH 3   /* input_len < 1 or > T, label_len < 0 or > label_stride,
                                    or a label outside [0,V)                             */
+#define ASRK_ROW_NOT_SMALL 4    /* the call carried ASRK_CTC_SMALL_ONLY but this row does not
+                                   fit the fused kernel: loss = NaN, gradient rows = 0  */
 
 int asrk_version(void);
 const char* asrk_error_string(int code);
@@ -133,6 +135,15 @@ int asrk_snr2k_run(const float* signal, const float* noise, const long long* sam
 #define ASRK_LABELS_DROP_ZEROS 1
 
 size_t asrk_ctc_workspace_bytes(int T, int B, int label_stride);
+
+/* 1 when an utterance of at most max_input_len frames and max_label_len labels is handled by
+ * the fused CTA-per-utterance kernel (32 state pairs, 60 KB of per-frame scalars).  A host that
+ * knows the batch maxima (the reference's loader builds input_length / label_length on the host,
+ * lm_and_am/data_loader.py:132-148) may then OR ASRK_CTC_SMALL_ONLY into `phases` of
+ * asrk_ctc_loss_grad_run_phases: the three generic kernels behind the fused one are not
+ * launched at all; a row that breaks the promise is reported as ASRK_ROW_NOT_SMALL. */
+int asrk_ctc_fits_fused(int max_input_len, int max_label_len);
+#define ASRK_CTC_SMALL_ONLY 0x10000
 
 int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long stride_b,
                            int T, int B, int V,

@@ -267,3 +267,43 @@ def test_stage_logits_copies_only_valid_rows():
             assert np.all(got[n:, b] == -7.0)              # padding rows never touched
     with pytest.raises(ValueError):
         ctc.stage_logits(torch.zeros(2, 2, 4), il[:2])
+
+
+def test_bounded_batch_is_one_launch_and_matches_the_unbounded_call():
+    """Lengths given as DEVICE tensors leave the host blind: prep + fused + the generic kernels are
+    launched.  With ``bounds`` (or host length vectors) the fused kernel prepares its own utterance
+    and nothing else runs.  Both must give the same bits; a broken promise is reported per row."""
+    import torch
+    from asr_dfcnn_transformer_b200 import _lib, ctc
+    rng = np.random.default_rng(77)
+    il = rng.integers(20, 60, 12).astype(np.int32)
+    x, labels, ll, il = synth.ctc_batch(rng, il, 1424, 4, 20, lmax=64)
+    xs = torch.as_tensor(x).cuda()
+    d = lambda a: torch.as_tensor(a).cuda()
+    a = ctc.ctc_loss_grad(xs, d(labels), d(ll), d(il), 1423, decode=True)               # unbounded
+    b = ctc.ctc_loss_grad(xs, d(labels), d(ll), d(il), 1423, decode=True, bounds=(int(il.max()), int(ll.max())))
+    c = ctc.ctc_loss_grad(xs, labels, ll, il, 1423, decode=True)                        # host vectors
+    for r in (b, c):
+        assert torch.equal(r.loss, a.loss) and torch.equal(r.grad, a.grad)
+        assert torch.equal(r.row_status, a.row_status) and torch.equal(r.token_len, a.token_len)
+        for k in range(len(il)):
+            n = int(a.token_len[k])
+            assert torch.equal(r.tokens[k, :n], a.tokens[k, :n])
+    ref = ctc_ref.ctc_loss_grad_batch(x, labels, ll, il, 1423)
+    assert np.allclose(a.loss.cpu().numpy(), ref[0], rtol=CTC_RTOL, atol=CTC_ATOL)
+    # a promise that does not hold: rows with more than 31 labels cannot take the fused kernel
+    il2 = np.full(4, 120, np.int32)
+    x2, labels2, ll2, il2 = synth.ctc_batch(rng, il2, 1424, 10, 50, lmax=64)
+    ll2[1] = 40
+    labels2[1, :40] = 1 + np.arange(40)
+    r = ctc.ctc_loss_grad(torch.as_tensor(x2).cuda(), d(labels2), d(ll2), d(il2), 1423, bounds=(60, 20))
+    st = r.row_status.cpu().numpy()
+    assert st[1] == _lib.ROW_NOT_SMALL and np.isnan(r.loss.cpu().numpy()[1])
+    assert not r.grad[:, 1].any()
+    with pytest.raises(ValueError):
+        ctc._raise_on_status(r.row_status)
+    # without the promise the same batch goes through the generic kernels
+    r2 = ctc.ctc_loss_grad(torch.as_tensor(x2).cuda(), labels2, ll2, il2, 1423)
+    ref2 = ctc_ref.ctc_loss_grad_batch(x2, labels2, ll2, il2, 1423)
+    assert int(r2.row_status.max()) == 0
+    assert np.allclose(r2.loss.cpu().numpy(), ref2[0], rtol=CTC_RTOL, atol=CTC_ATOL)
