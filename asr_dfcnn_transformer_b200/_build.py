@@ -30,8 +30,15 @@ def _nvcc():
     raise RuntimeError("nvcc not found (set NVCC or put /usr/local/cuda/bin on PATH)")
 
 
+FLAGS_STAMP = os.path.join(PKG_DIR, "build", "flags.txt")
+
+
 def needs_build():
     if not os.path.isfile(LIB_PATH):
+        return True
+    # a library built with other flags (e.g. a -D debug switch through ASRK_EXTRA_NVCC) is stale;
+    # without a stamp (a library that travelled alone) the time stamps decide
+    if os.path.isfile(FLAGS_STAMP) and open(FLAGS_STAMP).read() != " ".join(NVCC_FLAGS):
         return True
     t = os.path.getmtime(LIB_PATH)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
@@ -63,6 +70,7 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout))
     os.replace(tmp, LIB_PATH)
+    open(FLAGS_STAMP, "w").write(" ".join(NVCC_FLAGS))
     return LIB_PATH
 
 

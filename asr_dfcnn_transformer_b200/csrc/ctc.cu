@@ -448,10 +448,20 @@ __device__ __forceinline__ float warp_max_redux(float v) {
 //      ago) and writes softmax minus occupancy once, 16 bytes per lane.
 // The logits cross HBM once in and the gradient once out; alpha, beta and the
 // gathered log-probabilities never leave shared memory.
+#ifdef ASRK_CTC_TIMING
+// SM cycle counter: %globaltimer takes microseconds to read on this part (two adjacent reads were 1.7-5.5 us apart)
+#define ASRK_TICK(i) do { if (threadIdx.x == 0) s_tick[i] = (unsigned long long)clock64(); } while (0)
+#else
+#define ASRK_TICK(i) do { } while (0)
+#endif
 template <int NV4>
 __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ double s_fin;
+#ifdef ASRK_CTC_TIMING
+    __shared__ unsigned long long s_tick[12];
+#endif
+    ASRK_TICK(0);
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -501,14 +511,12 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     }
     const int W = L + 1;                        // row width of the gathered log-probs
     const int Ub = 2 * L + 1;                   // lattice states
-    double* sC = reinterpret_cast<double*>(sm); // [T] sum_{s<=t} log c_s
-    double* sD = sC + T;                        // [T] sum_{s>=t} log d_s
+    double* sC = reinterpret_cast<double*>(sm); // [T] level of alpha column t: everything subtracted up to t
+    double* sD = sC + T;                        // [T] level of beta column t
     float* slse = reinterpret_cast<float*>(sD + T);  // [T]
     float* smax = slse + T;                     // [T]
     int* samax = reinterpret_cast<int*>(smax + T);   // [T]
-    float* slogc = smax + 2 * T;                // [T] alpha column scales c_t
-    float* slogd = slogc + T;                   // [T] beta column scales d_t
-    float* sK = slogd + T;                      // [T] exp(C_t + D_t - log p)
+    float* sK = smax + 2 * T;                   // [T] C_t + D_t - log2 p
     float* slp = sK + T;                        // [T][W] y_t(l'_j)
     float* sal = slp + T * W;                   // [T][Ub]
     float* sbe = sal + T * Ub;                  // [T][Ub]
@@ -534,15 +542,19 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         if (lane < W) slp[t * W + lane] = (xg - lse) * 1.4426950408889634f;   // log2 y_t(l'_j)
     }
     __syncthreads();
+    ASRK_TICK(1);
 
     // ---- B: alpha || beta || greedy collapse ----------------------------------
-    // Log2-domain recursions in fp32, each column stored RELATIVE to its maximum (one
-    // REDUX per frame on order-preserving bit patterns), so stored values are <= 0 and
-    // small in magnitude: no drift with T (the absolute level, ~ -10 T, lives in the
-    // per-frame maxima, prefix-summed in double afterwards) and no underflow of the
-    // states that matter (a linear-domain variant rescaled by the column maximum was
-    // measured 2x faster per step but crushed low-mass terminal states into denormals).
-    //   alpha_t(u) = 2^(ahat_t(u) + sum_{s<=t} c_s),  beta_t(u) (excludes y_t, TF) = 2^(bhat_t(u) + sum_{s>=t} d_s)
+    // Log2-domain recursions in fp32.  Every column is stored relative to a LEVEL kept in
+    // double: column t has the maximum of the stored column t-1 subtracted (one REDUX per
+    // frame on order-preserving bit patterns), so stored values stay within a few tens of
+    // 0 -- no drift with T, no underflow of the states that matter (a linear-domain variant
+    // rescaled by the column maximum was 2x faster per step but crushed low-mass terminal
+    // states into denormals).  Using the PREVIOUS column's maximum takes the reduction off
+    // the recursion's dependency chain (shuffle -> log-sum-exp -> subtract): it runs beside
+    // the next step's log-sum-exp.  The levels are accumulated in the same loop, in double
+    // (T additions of ~10 each: fp32 would lose 1e-2 at T in the hundreds).
+    //   alpha_t(u) = 2^(ahat_t(u) + C_t),  beta_t(u) (excludes y_t, TF) = 2^(bhat_t(u) + D_t)
     const int i = lane;
     const int lab_i = (i < L) ? eff[i] : -1;
     const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
@@ -558,6 +570,8 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         }
         float yb_n = 0.f, yl_n = 0.f;            // log2 y of the next frame, loaded ahead of the chain
         if (T > 1) { yb_n = slp[W]; yl_n = has_lab ? slp[W + 1 + i] : kNegInf; }
+        float m_prev = 0.f;                      // maximum of the stored column t-1
+        double lvl = 0.0;                        // C_t
         for (int t = 0; t < T; ++t) {
             if (t > 0) {
                 const float yb = yb_n, yl = yl_n;
@@ -566,22 +580,24 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
                 if (i == 0) p1 = kNegInf;
                 const float nb = yb + lse2_log2(a_b, p1);
                 const float nl = yl + lse3_log2(a_l, a_b, skip ? p1 : kNegInf);
-                a_b = has_blank ? nb : kNegInf;
-                a_l = nl;
+                a_b = has_blank ? nb - m_prev : kNegInf;
+                a_l = nl - m_prev;
+                lvl += (double)m_prev;
             }
-            const float c = warp_max_redux(fmaxf(a_b, a_l));
-            const float sub = (c == kNegInf) ? 0.f : c;      // all -inf: no valid prefix
-            a_b -= sub;
-            a_l -= sub;
             float* o = sal + t * Ub;
             if (has_blank) o[2 * i] = a_b;
             if (has_lab) o[2 * i + 1] = a_l;
-            if (lane == 0) slogc[t] = c;
+            if (lane == 0) sC[t] = lvl;
+            const float c = warp_max_redux(fmaxf(a_b, a_l));
+            m_prev = (c == kNegInf) ? 0.f : c;   // all -inf: no valid prefix
         }
-        // mass of the two terminal states at T-1 (relative to the last column maximum)
+        // mass of the two terminal states at T-1 (relative to the last column's level)
         const float fb = __shfl_sync(0xffffffffu, a_b, L);
         const float fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : kNegInf;
         if (lane == 0) s_fin = (double)lse2_log2(fb, fl);
+#ifdef ASRK_CTC_TIMING
+        if (lane == 0) s_tick[8] = (unsigned long long)clock64();
+#endif
     } else if (warp == 1) {
         if (p.grad != nullptr) {
             // beta: pair (label 2i-1, blank 2i); excludes y_t
@@ -593,6 +609,8 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             }
             float yb_n = 0.f, yl_n = 0.f;
             if (T > 1) { yb_n = slp[(T - 1) * W]; yl_n = has_lab ? slp[(T - 1) * W + i] : kNegInf; }
+            float m_prev = 0.f;
+            double lvl = 0.0;                    // D_t
             for (int t = T - 1; t >= 0; --t) {
                 if (t < T - 1) {
                     const float yb = yb_n, yl = yl_n;
@@ -603,19 +621,21 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
                     if (i == 31) n1 = kNegInf;
                     const float nbb = lse2_log2(e_b, n1);
                     const float nbl = lse3_log2(e_l, e_b, skip ? n1 : kNegInf);
-                    b_b = has_blank ? nbb : kNegInf;
-                    b_l = has_lab ? nbl : kNegInf;
+                    b_b = has_blank ? nbb - m_prev : kNegInf;
+                    b_l = has_lab ? nbl - m_prev : kNegInf;
+                    lvl += (double)m_prev;
                 }
-                const float d = warp_max_redux(fmaxf(b_b, b_l));
-                const float sub = (d == kNegInf) ? 0.f : d;
-                b_b -= sub;
-                b_l -= sub;
                 float* o = sbe + t * Ub;
                 if (has_blank) o[2 * i] = b_b;
                 if (has_lab) o[2 * i - 1] = b_l;
-                if (lane == 0) slogd[t] = d;
+                if (lane == 0) sD[t] = lvl;
+                const float d = warp_max_redux(fmaxf(b_b, b_l));
+                m_prev = (d == kNegInf) ? 0.f : d;
             }
         }
+#ifdef ASRK_CTC_TIMING
+        if (lane == 0) s_tick[9] = (unsigned long long)clock64();
+#endif
     } else if (warp == 2 && p.tokens != nullptr) {
         // greedy decode of this utterance: ballot + prefix count over 32-frame chunks
         int* out = p.tokens + (size_t)b * p.token_stride;
@@ -640,28 +660,14 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             p.token_len[b] = count < p.token_stride ? count : p.token_stride;
             if (p.neg_sum_logits) p.neg_sum_logits[b] = (float)(-nsl);
         }
+#ifdef ASRK_CTC_TIMING
+        if (lane == 0) s_tick[10] = (unsigned long long)clock64();
+#endif
     }
     __syncthreads();
-    // prefix sums of the column scales in double (T additions of ~7 each: fp32 would
-    // lose 1e-2 at T in the hundreds): warp 0 forward over log c, warp 1 backward over log d
-    if (warp < 2) {
-        double carry = 0.0;
-        for (int base = 0; base < T; base += 32) {
-            const int k = base + lane;                       // position in sweep order
-            const int t = (warp == 0) ? k : T - 1 - k;
-            double v = 0.0;
-            if (k < T) v = (double)(warp == 0 ? slogc[t] : slogd[t]);
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double n = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += n;
-            }
-            v += carry;
-            if (k < T) (warp == 0 ? sC : sD)[t] = v;
-            carry = __shfl_sync(0xffffffffu, v, 31);
-        }
-    }
-    __syncthreads();
+    ASRK_TICK(2);
+    ASRK_TICK(5);
+    ASRK_TICK(7);
     // log2 p = C_{T-1} + log2(relative mass of the two terminal alphas at T-1)
     const double logp2 = sC[T - 1] + s_fin;
     const double logp = logp2 * 0.6931471805599453;
@@ -675,9 +681,11 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     // ---- C: gradient rows -----------------------------------------------------
     const bool fix = (logp != ninf) && (status == ASRK_ROW_OK);   // TF: no valid path -> dy = y
     // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(ahat_t(u) + bhat_t(u) + K_t)
+    ASRK_TICK(6);
     if (fix)
         for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = (float)(sC[t] + sD[t] - logp2);
     __syncthreads();
+    ASRK_TICK(3);
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
     // lane j < L owns label position j: the positions that carry the same label (one
     // MATCH), so repeated labels are summed in a fixed order without touching memory
@@ -735,6 +743,18 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         ob = warp_sum(ob);
         if (lane == 0) g[p.blank] = (ex2_fast(slp[t * W]) - ob) * scale;
     }
+#ifdef ASRK_CTC_TIMING
+    __syncthreads();
+    ASRK_TICK(4);
+    if (tid == 0 && p.tokens) {       // debug build only: phase times (ns) over the first token slots
+        int* o = p.tokens + (size_t)b * p.token_stride;
+        unsigned sm_id;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_id));
+        o[0] = (int)(s_tick[0] & 0x3fffffffull);
+        for (int i = 1; i <= 4; ++i) o[i] = (int)(s_tick[i] - s_tick[0]);
+        o[5] = (int)sm_id; o[6] = T; o[7] = L; o[8] = (int)(s_tick[5] - s_tick[2]); o[9] = (int)(s_tick[6] - s_tick[5]); o[10] = (int)(s_tick[7] - s_tick[5]); o[11] = (int)(s_tick[8] - s_tick[1]); o[12] = (int)(s_tick[9] - s_tick[1]); o[13] = (int)(s_tick[10] - s_tick[1]);
+    }
+#endif
 }
 
 // One CTA per utterance; thread i owns the state pair

@@ -18,7 +18,7 @@ def main():
     open(os.path.join(P, "r1_launches_step.csv"), "w").writelines(lines)
     rows = list(csv.DictReader(lines))
     ours = [r for r in rows if ("spec::" in r["Kernel Name"] or "ctc::" in r["Kernel Name"])]
-    last = ours[-8:]
+    last = ours[-4:]      # spectrogram, stats, z-score, fused CTC
     tot = sum(float(r["Metric Value"]) for r in last)
     md = ["# One step of the hot path (C2 batch, 256 utterances), ncu --metrics gpu__time_duration.sum --clock-control none",
           "# (cold-cache, serialised launches: compare SHARES, not absolutes). Source: profiles/r1_launches_step.csv",
