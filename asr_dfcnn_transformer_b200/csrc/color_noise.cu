@@ -9,9 +9,13 @@
 //     DFT_N(a)[k] = conj(c_k) * sum_n (a_n conj(c_n)) c_(k-n),   c_n = exp(+i pi n^2 / N)
 // i.e. a cyclic convolution of length M done with radix-2 FFTs (decimation in frequency
 // forward, decimation in time backward: no bit-reversal pass is ever needed).
-// First correct version (round 1): one kernel launch per radix-2 stage over the whole batch in
-// global memory -- HBM-bound at 2 * 16 B * M per utterance and stage; not yet blocked in shared
-// memory.
+// The radix-2 stages are blocked in shared memory (blocked_stages_kernel): a CTA holds 4096
+// complex points (64 KB) and runs up to 12 consecutive stages on them -- the stages whose span is
+// below 4096 on a contiguous block, the others on a tile of 2^S rows x (4096 >> S) consecutive
+// columns -- so a length-2^18 transform crosses HBM twice instead of 18 times.  Same butterflies,
+// same twiddle table and same order of operations as the one-launch-per-stage kernels of the first
+// version (kept below: they still serve transforms shorter than one block's worth of sense and as
+// the reference the blocked kernel was checked against), so the bits are unchanged.
 #include <math.h>
 
 #include "asrk_common.cuh"
@@ -103,6 +107,152 @@ __global__ void dit_inv_stage_kernel(cd* buf, const cd* tw, int log2M, int stage
     const cd a = v[i], b = cmul(v[i + span], conj(tw[j << s]));
     v[i] = cd{a.x + b.x, a.y + b.y};
     v[i + span] = cd{a.x - b.x, a.y - b.y};
+}
+
+// ---------------------------------------------------------------------------
+// S consecutive radix-2 stages [s0, s0 + S) of the length-2^L transform on 4096-point tiles in
+// shared memory.  Tile element (a, c), a < 2^S, c < C = 4096 >> S, is the global point
+//     i = h 2^(L - s0) + a 2^(L - s0 - S) + c0 + c
+// (for the last stages, L - s0 - S = 0 and C = 2^(L - s0 - S): the tile is a contiguous block).
+// Global stage s pairs points that differ in bit L - 1 - s, i.e. bit (s0 + S - 1 - s) of a.
+// INVERSE = false: decimation in frequency, stages in increasing order;
+// INVERSE = true : decimation in time of the inverse transform, stages in DEcreasing order.
+// ---------------------------------------------------------------------------
+constexpr int kTileLog2 = 12, kTile = 1 << kTileLog2;
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(256) blocked_stages_kernel(cd* buf, const cd* __restrict__ tw, int L, int s0, int S) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* t = reinterpret_cast<cd*>(smem_raw);
+    const int low = L - s0 - S;                         // bits of the global index below the active ones
+    const int cb = kTileLog2 - S;                       // log2 of the tile's column count (<= low)
+    const long long M = 1LL << L;
+    cd* v = buf + (size_t)blockIdx.y * M;
+    // tile id -> (h, c0)
+    const long long tiles_per_h = 1LL << (low - cb);
+    const long long h = (long long)blockIdx.x / tiles_per_h;
+    const long long c0 = ((long long)blockIdx.x % tiles_per_h) << cb;
+    const long long base = (h << (L - s0)) + c0;
+    const int C = 1 << cb;
+    for (int e = threadIdx.x; e < kTile; e += blockDim.x) {
+        const int a = e >> cb, c = e & (C - 1);
+        t[e] = v[base + ((long long)a << low) + c];
+    }
+    __syncthreads();
+    // twiddle index of the butterfly whose first point is tile element i0, at global stage s, when the
+    // paired bit is bit `abits` of a: the global index below bit L - 1 - s is (low bits of a, column)
+    auto tw_of = [&](int i0, int abits, int s) -> cd {
+        const long long j = ((long long)((i0 >> cb) & ((1 << abits) - 1)) << low) + c0 + (i0 & (C - 1));
+        const double2 w = __ldg(reinterpret_cast<const double2*>(tw) + (j << s));
+        return cd{w.x, w.y};
+    };
+    // two stages per round on four points held in registers (half the shared-memory traffic and
+    // barriers of one stage per round); a leftover single stage when S is odd.  k counts stages in
+    // processing order: forward s = s0 + k (paired a-bit S-1-k, going down), inverse s = s0+S-1-k
+    // (paired a-bit k, going up).
+    int k = 0;
+    while (k < S) {
+        if (S - k >= 2) {
+            const int bit_first = INVERSE ? k : (S - 1 - k);              // a-bit paired by the round's first stage
+            const int bit_hi = INVERSE ? k + 1 : bit_first, bit_lo = bit_hi - 1;
+            const int pb_lo = cb + bit_lo, pb_hi = pb_lo + 1;
+            const int s_hi = s0 + S - 1 - bit_hi, s_lo = s_hi + 1;        // global stages that pair bit_hi / bit_lo
+#pragma unroll 4
+            for (int q = threadIdx.x; q < kTile / 4; q += blockDim.x) {
+                const int lo = q & ((1 << pb_lo) - 1);
+                const int i00 = ((q >> pb_lo) << (pb_lo + 2)) | lo;
+                const int i01 = i00 | (1 << pb_lo), i10 = i00 | (1 << pb_hi), i11 = i10 | (1 << pb_lo);
+                cd e0 = t[i00], e1 = t[i01], e2 = t[i10], e3 = t[i11];
+                const cd w_lo = tw_of(i00, bit_lo, s_lo);                 // (e0,e1) and (e2,e3)
+                const cd w_h0 = tw_of(i00, bit_hi, s_hi);                 // (e0,e2)
+                const cd w_h1 = tw_of(i01, bit_hi, s_hi);                 // (e1,e3)
+                if (!INVERSE) {
+                    cd a = e0, b = e2;
+                    e0 = cd{a.x + b.x, a.y + b.y};
+                    e2 = cmul(cd{a.x - b.x, a.y - b.y}, w_h0);
+                    a = e1; b = e3;
+                    e1 = cd{a.x + b.x, a.y + b.y};
+                    e3 = cmul(cd{a.x - b.x, a.y - b.y}, w_h1);
+                    a = e0; b = e1;
+                    e0 = cd{a.x + b.x, a.y + b.y};
+                    e1 = cmul(cd{a.x - b.x, a.y - b.y}, w_lo);
+                    a = e2; b = e3;
+                    e2 = cd{a.x + b.x, a.y + b.y};
+                    e3 = cmul(cd{a.x - b.x, a.y - b.y}, w_lo);
+                } else {
+                    cd a = e0, b = cmul(e1, conj(w_lo));
+                    e0 = cd{a.x + b.x, a.y + b.y};
+                    e1 = cd{a.x - b.x, a.y - b.y};
+                    a = e2; b = cmul(e3, conj(w_lo));
+                    e2 = cd{a.x + b.x, a.y + b.y};
+                    e3 = cd{a.x - b.x, a.y - b.y};
+                    a = e0; b = cmul(e2, conj(w_h0));
+                    e0 = cd{a.x + b.x, a.y + b.y};
+                    e2 = cd{a.x - b.x, a.y - b.y};
+                    a = e1; b = cmul(e3, conj(w_h1));
+                    e1 = cd{a.x + b.x, a.y + b.y};
+                    e3 = cd{a.x - b.x, a.y - b.y};
+                }
+                t[i00] = e0; t[i01] = e1; t[i10] = e2; t[i11] = e3;
+            }
+            k += 2;
+        } else {
+            const int abits = INVERSE ? k : (S - 1 - k);
+            const int s = s0 + S - 1 - abits;
+            const int pb = cb + abits;
+            for (int q = threadIdx.x; q < kTile / 2; q += blockDim.x) {
+                const int lo = q & ((1 << pb) - 1);
+                const int i0 = ((q >> pb) << (pb + 1)) | lo, i1 = i0 | (1 << pb);
+                const cd w = tw_of(i0, abits, s);
+                if (!INVERSE) {
+                    const cd a = t[i0], b = t[i1];
+                    t[i0] = cd{a.x + b.x, a.y + b.y};
+                    t[i1] = cmul(cd{a.x - b.x, a.y - b.y}, w);
+                } else {
+                    const cd a = t[i0], b = cmul(t[i1], conj(w));
+                    t[i0] = cd{a.x + b.x, a.y + b.y};
+                    t[i1] = cd{a.x - b.x, a.y - b.y};
+                }
+            }
+            k += 1;
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < kTile; e += blockDim.x) {
+        const int a = e >> cb, c = e & (C - 1);
+        v[base + ((long long)a << low) + c] = t[e];
+    }
+}
+
+// all L stages of one transform over the batch: blocked when the transform has at least one tile
+template <bool INVERSE>
+static void run_fft(cd* buf, const cd* tw, int L, int batch, cudaStream_t stream) {
+    const long long M = 1LL << L;
+    if (L < kTileLog2) {
+        const dim3 gH((unsigned)((M / 2 + 255) / 256), batch);
+        for (int s = 0; s < L; ++s) {
+            if (INVERSE) dit_inv_stage_kernel<<<gH, 256, 0, stream>>>(buf, tw, L, s);
+            else dif_stage_kernel<<<gH, 256, 0, stream>>>(buf, tw, L, s);
+        }
+        return;
+    }
+    const size_t smem = sizeof(cd) * kTile;
+    cudaFuncSetAttribute(blocked_stages_kernel<INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const dim3 grid((unsigned)(M >> kTileLog2), batch);
+    // stage groups in forward order: the top L - 12 stages in strided passes of <= 6, then the last 12
+    int starts[8], counts[8], n = 0;
+    int top = L - kTileLog2;
+    for (int s0 = 0; s0 < top;) {
+        const int S = (top - s0) < 6 ? (top - s0) : 6;
+        starts[n] = s0; counts[n] = S; ++n;
+        s0 += S;
+    }
+    starts[n] = top; counts[n] = kTileLog2; ++n;
+    if (!INVERSE) {
+        for (int g = 0; g < n; ++g) blocked_stages_kernel<false><<<grid, 256, smem, stream>>>(buf, tw, L, starts[g], counts[g]);
+    } else {
+        for (int g = n - 1; g >= 0; --g) blocked_stages_kernel<true><<<grid, 256, smem, stream>>>(buf, tw, L, starts[g], counts[g]);
+    }
 }
 
 __global__ void pointwise_kernel(cd* A, const cd* Bc, int log2M) {
@@ -254,17 +404,15 @@ extern "C" int asrk_color_noise_run(const double* normals, const long long* offs
     const dim3 gM((unsigned)((M + 255) / 256), batch), gH((unsigned)((M / 2 + 255) / 256), batch);
     twiddle_kernel<<<(unsigned)((M / 2 + 255) / 256), 256, 0, stream>>>(p.tw, log2M);
     init_kernel<<<gM, 256, 0, stream>>>(p);
-    for (int s = 0; s < log2M; ++s) {
-        dif_stage_kernel<<<gH, 256, 0, stream>>>(p.A, p.tw, log2M, s);
-        dif_stage_kernel<<<gH, 256, 0, stream>>>(p.Bc, p.tw, log2M, s);
-    }
+    run_fft<false>(p.A, p.tw, log2M, batch, stream);
+    run_fft<false>(p.Bc, p.tw, log2M, batch, stream);
     pointwise_kernel<<<gM, 256, 0, stream>>>(p.A, p.Bc, log2M);
-    for (int s = 0; s < log2M; ++s) dit_inv_stage_kernel<<<gH, 256, 0, stream>>>(p.A, p.tw, log2M, s);
+    run_fft<true>(p.A, p.tw, log2M, batch, stream);
     shape_kernel<<<gM, 256, 0, stream>>>(p);
     restage_kernel<<<gM, 256, 0, stream>>>(p);
-    for (int s = 0; s < log2M; ++s) dif_stage_kernel<<<gH, 256, 0, stream>>>(p.A, p.tw, log2M, s);
+    run_fft<false>(p.A, p.tw, log2M, batch, stream);
     pointwise_kernel<<<gM, 256, 0, stream>>>(p.A, p.Bc, log2M);
-    for (int s = 0; s < log2M; ++s) dit_inv_stage_kernel<<<gH, 256, 0, stream>>>(p.A, p.tw, log2M, s);
+    run_fft<true>(p.A, p.tw, log2M, batch, stream);
     double* yreal = p.y;     // the staging buffer is free again: [B][M] doubles fit in its first half
     finish_real_kernel<<<gM, 256, 0, stream>>>(p, yreal);
     mean_max_kernel<<<batch, 1024, 0, stream>>>(p, yreal);
