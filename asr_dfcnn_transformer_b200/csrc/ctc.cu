@@ -587,7 +587,7 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             float* o = sal + t * Ub;
             if (has_blank) o[2 * i] = a_b;
             if (has_lab) o[2 * i + 1] = a_l;
-            if (lane == 0) sC[t] = lvl;
+            sC[t] = lvl;                           // every lane, same value
             const float c = warp_max_redux(fmaxf(a_b, a_l));
             m_prev = (c == kNegInf) ? 0.f : c;   // all -inf: no valid prefix
         }
@@ -628,7 +628,7 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
                 float* o = sbe + t * Ub;
                 if (has_blank) o[2 * i] = b_b;
                 if (has_lab) o[2 * i - 1] = b_l;
-                if (lane == 0) sD[t] = lvl;
+                sD[t] = lvl;                       // every lane, same value: no divergent branch in the chain
                 const float d = warp_max_redux(fmaxf(b_b, b_l));
                 m_prev = (d == kNegInf) ? 0.f : d;
             }
