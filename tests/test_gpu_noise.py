@@ -40,6 +40,21 @@ def test_ragged_batch_any_length_vs_oracle():
         assert np.abs(g - ref).max() <= TOL * max(1.0, np.abs(ref).max()), (lens[i], c, np.abs(g - ref).max())
 
 
+@pytest.mark.parametrize("n", [700, 1500, 3000, 10000, 40001, 300000])
+def test_every_transform_length_class(n):
+    """One call per length so that the power-of-two transform length changes: 2^11 (one launch per
+    radix-2 stage), 2^12 (one contiguous block), 2^13 / 2^15 / 2^17 (one strided pass of 1, 3, 5 stages:
+    odd counts end with a single-stage round), 2^20 (two strided passes)."""
+    from asr_dfcnn_transformer_b200 import noise
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    for c in (-1.0, 0.3):
+        out, offs = noise.color_noise_batch([x], [c])
+        ref = fbank_ref.color_noise_from_normal(x, c)
+        g = out.cpu().numpy()
+        assert np.abs(g - ref).max() <= TOL * max(1.0, np.abs(ref).max()), (n, c, np.abs(g - ref).max())
+
+
 def test_drop_in_surface_reproduces_the_reference_stream():
     """Same np.random.seed -> the same draw as the reference's color_noise -> the same noise."""
     from asr_dfcnn_transformer_b200 import noise
