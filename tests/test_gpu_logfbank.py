@@ -54,3 +54,21 @@ def test_zscored_vs_oracle_and_surface(tmp_path):
     ref_raw = psf_ref.logfbank(pcm.astype(np.float64))
     live = ref_raw.std(axis=0) > 1e-9
     assert feature_err(got[:, live], ref[:, live]) <= 5 * FEATURE_TOL
+
+
+@pytest.mark.parametrize("fs,nfilt", [(8000, 40), (16000, 26), (20000, 200), (11025, 64)])
+def test_other_sample_rates_and_filter_counts(fs, nfilt):
+    """frame length 200 / 400 / 500 / 276 samples (round-half-up of 25 ms) inside the 512-point
+    transform, and filter banks that are not 200 wide: the kernel's group counts, bin tables and lane
+    loops are all derived from these."""
+    from asr_dfcnn_transformer_b200 import wav_util
+    rng = np.random.default_rng(fs + nfilt)
+    sigs = [synth.g2_voiced(rng, 3 * fs).astype(np.float64) / 32768.0,
+            synth.g1_white(rng, fs // 2 + 7).astype(np.float64) / 32768.0]
+    fb = wav_util.compute_fbank_from_api_batch(sigs, fs, nfilt, normalise=False)
+    out = fb.features.cpu().numpy()
+    for i, s in enumerate(sigs):
+        ref = psf_ref.logfbank(s, fs, nfilt)
+        got = out[fb.frame_offsets[i]:fb.frame_offsets[i + 1]]
+        assert got.shape == ref.shape, (i, got.shape, ref.shape)
+        assert feature_err(got, ref) <= FEATURE_TOL, (fs, nfilt, i, feature_err(got, ref))
