@@ -48,6 +48,15 @@ def ncu_traffic(kernel):
         return None
 
 
+def ncu_fp64_pct(kernel):
+    """fp64 pipe utilisation of that kernel in the same capture (the spectrogram kernel is bound by the
+    fp64 pipe and its feeding, not by HBM: the HBM fraction alone would misread it)."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["fp64_pipe_pct"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -492,7 +501,7 @@ def main():
                              % (POOL, (step_alg + bc / 2) / 1e6)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg,
+                         "algorithmic_bytes_per_launch": alg, "fp64_pipe_pct_ncu": ncu_fp64_pct(dom),
                          "step_frac": (step_alg / (ms / args.steps * 1e-3) / 1e9) / peak / world},
             "kernel_ms": kms,
             "loss_mean": float(loss_check[0] / max(float(loss_check[1]), 1.0)),
