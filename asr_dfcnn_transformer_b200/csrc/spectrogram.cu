@@ -525,7 +525,8 @@ __global__ void __launch_bounds__(256) stats_kernel(Params p) {
 // z-score: out = (y - mean) / std, in place; grid (x, utterance), pure streaming
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) normalize_kernel(Params p) {
-    const int b = blockIdx.y;
+    // newest utterances first: their rows are the ones the main kernel's evict-last stores still hold in L2
+    const int b = (int)gridDim.y - 1 - (int)blockIdx.y;
     __shared__ __align__(16) float s_stat[3 * kBins];
     for (int k = threadIdx.x; k < 3 * kBins; k += blockDim.x) s_stat[k] = p.stats[(size_t)b * 3 * kBins + k];
     __syncthreads();
