@@ -10,13 +10,16 @@
 // Launches per call (DESIGN.md "CTC kernels"):
 //   prep    : one CTA per utterance -- effective label list (by length / drop zeros),
 //             feasibility, chains of repeated labels, and the flag that tells the generic
-//             kernels whether any utterance needs them.
+//             kernels whether any utterance needs them.  When prep and fused are asked for in
+//             one call, the fused kernel does this for its own utterance (no launch).
 //   fused   : one CTA per utterance whose lattice fits a warp and 60 KB of shared memory
-//             (every AISHELL-shaped utterance): rows streamed through per-warp cp.async
-//             buffers (max / first arg-max / log-sum-exp / gather), alpha and beta on two
-//             warps concurrently in the fp32 log2 domain relative to the column maxima,
-//             greedy collapse on a third, then the rows again from L2 for softmax minus
-//             occupancy, written once.  Logits cross HBM once in, the gradient once out.
+//             (every AISHELL-shaped utterance): rows streamed through per-warp buffers filled
+//             by TMA bulk copies on per-warp mbarriers (max / first arg-max / log-sum-exp /
+//             gather), alpha and beta on two warps concurrently in the fp32 log2 domain
+//             relative to levels kept in double, greedy collapse on a third, then the rows
+//             again from L2 for softmax minus occupancy, written once.  Logits cross HBM once
+//             in, the gradient once out.  A caller that bounds the batch (ASRK_CTC_SMALL_ONLY)
+//             gets exactly this one launch.
 //   generic path for long lattices (T in the thousands, hundreds of labels), skipped by a
 //   device flag when every utterance was fused:
 //   rows    : one WARP per (t,b) row, grid-stride -- max, first arg-max, log-sum-exp and the
