@@ -82,3 +82,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_python_constants_match_the_header():
+    """Every numeric ASRK_* #define of include/asrk.h that the Python side mirrors has the same value there."""
+    import re
+    from asr_dfcnn_transformer_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "asrk.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+ASRK_(\w+)\s+\(?(-?(?:0x[0-9a-fA-F]+|\d+))\)?", text)}
+    mirrored = 0
+    for name, value in defs.items():
+        for cand in (name, name.replace("PHASE_CTC_", "PHASE_CTC_"), name.replace("SPEC_", "MODE_")):
+            if hasattr(_lib, cand):
+                assert getattr(_lib, cand) == value, (name, getattr(_lib, cand), value)
+                mirrored += 1
+                break
+    assert mirrored >= 15, mirrored
+    assert _lib.CTC_SMALL_ONLY == defs["CTC_SMALL_ONLY"] and _lib.ROW_NOT_SMALL == defs["ROW_NOT_SMALL"]
