@@ -44,26 +44,6 @@ struct Params {
     double preemph;
 };
 
-// forward 16-point DFT in place (kernel exp(-2 pi i nk/16)): n = 4 n1 + n2, k = k1 + 4 k2;
-// on return X[k1 + 4 k2] sits in a[4 k1 + k2]
-__device__ __forceinline__ void dft16(cd (&a)[16]) {
-    constexpr double C = 0.92387953251128675613, S = 0.38268343236508977173, R = 0.70710678118654752440;
-#pragma unroll
-    for (int n2 = 0; n2 < 4; ++n2) dft4(a[n2], a[4 + n2], a[8 + n2], a[12 + n2]);     // a[4 k1 + n2]
-    // twiddles W16^(n2 k1)
-    a[5] = cmul(a[5], cd{C, -S});                                  // (1,1): W^1
-    a[6] = cd{R * (a[6].x + a[6].y), R * (a[6].y - a[6].x)};       // (k1=1,n2=2): W^2
-    a[7] = cmul(a[7], cd{S, -C});                                  // (1,3): W^3
-    a[9] = cd{R * (a[9].x + a[9].y), R * (a[9].y - a[9].x)};       // (2,1): W^2
-    a[10] = cd{a[10].y, -a[10].x};                                 // (2,2): W^4 = -i
-    a[11] = cd{R * (a[11].y - a[11].x), -R * (a[11].x + a[11].y)}; // (2,3): W^6 = (-R, -R)
-    a[13] = cmul(a[13], cd{S, -C});                                // (3,1): W^3
-    a[14] = cd{R * (a[14].y - a[14].x), -R * (a[14].x + a[14].y)}; // (3,2): W^6
-    a[15] = cmul(a[15], cd{-C, S});                                // (3,3): W^9 = -W^1
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) dft4(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
-}
-
 __global__ void __launch_bounds__(kWarps * 32, 1) logfbank_kernel(Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* tw512 = reinterpret_cast<cd*>(smem_raw);                   // W512^k, k <= 256 (real-input split)

@@ -99,3 +99,21 @@ def test_python_constants_match_the_header():
                 break
     assert mirrored >= 15, mirrored
     assert _lib.CTC_SMALL_ONLY == defs["CTC_SMALL_ONLY"] and _lib.ROW_NOT_SMALL == defs["ROW_NOT_SMALL"]
+
+
+def test_dft16_and_the_16x16_split_on_host(tmp_path):
+    """The mel front end's 256-point complex transform: two passes of the dft16 codelet with the W256
+    twiddle between them, index maps exactly as in csrc/logfbank.cu, against numpy."""
+    exe = str(tmp_path / "fft16")
+    subprocess.check_call(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tests", "host", "fft16x16_host.cpp")])
+    rng = np.random.default_rng(16)
+    for trial in range(3):
+        z = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+        if trial == 2:
+            z = np.exp(2j * np.pi * 37 * np.arange(256) / 256) * 1e3 + 1e-6 * z
+        text = "\n".join("%r %r" % (float(v.real), float(v.imag)) for v in z)
+        out = subprocess.run([exe], input=text, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = np.array([float(s) for s in out.stdout.split()]).reshape(256, 2)
+        ref = np.fft.fft(z)
+        assert np.abs(got[:, 0] + 1j * got[:, 1] - ref).max() <= 1e-12 * np.abs(ref).max()
