@@ -343,6 +343,16 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # started by hand with --gpus N: become the launch the driver uses (one rank per GPU, NCCL, loopback)
+        import socket
+        with socket.socket() as so:
+            so.bind(("127.0.0.1", 0))
+            port = so.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                                  str(args.gpus), "--master-addr", "127.0.0.1", "--master-port", str(port),
+                                  os.path.abspath(__file__)] + sys.argv[1:])
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
