@@ -74,3 +74,23 @@ def test_shard_bounds():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         pipeline.shard_bounds(4, 2, 2)
+
+
+def test_reference_arm_under_the_multi_rank_launch():
+    """`bench.py --impl reference --gpus 2` (CPU only): started by hand it relaunches itself under
+    torch.distributed.run; rank 0 alone times the reference algorithm and prints the line, rank 1 exits 0."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--gpus", "2", "--impl", "reference",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                   # one line, from rank 0
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
