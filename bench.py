@@ -401,6 +401,8 @@ def main():
         # the path's only collective: all-reduce of [sum loss, n] (one tiny kernel fills
         # the operand), on a side stream so that it overlaps the next step
         from asr_dfcnn_transformer_b200 import ctc, pipeline
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(side)      # the previous step's all-reduce is done with `red`
         ctc.loss_sum(r.loss, r.row_status, out=red)
         if world > 1:
             pipeline.all_reduce_loss(red, stream=side)
