@@ -6,5 +6,5 @@ through the reference's own Python call surface.  No CPU fallback.
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["features", "wav_util", "noise", "ctc", "data_loader", "parallel"]
+__all__ = ["features", "wav_util", "noise", "ctc", "data_loader", "pipeline", "utils"]
 __version__ = "0.1.0"

@@ -12,9 +12,11 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libasrk.so")
+# ASRK_LIB_SUFFIX builds / loads a variant library next to the default one (experiments: other -D switches)
+SUFFIX = os.environ.get("ASRK_LIB_SUFFIX", "")
+LIB_PATH = os.path.join(PKG_DIR, "libasrk%s.so" % SUFFIX)
 SOURCES = ["asrk_api.cu", "spectrogram.cu", "noise.cu", "ctc.cu", "post.cu", "logfbank.cu", "color_noise.cu"]
-HEADERS = ["asrk_common.cuh", "asrk_fft.cuh", os.path.join("..", "..", "include", "asrk.h")]
+HEADERS = ["asrk_common.cuh", "asrk_fft.cuh", "asrk_tables.inc", os.path.join("..", "..", "include", "asrk.h")]
 NVCC_FLAGS = (os.environ.get("ASRK_EXTRA_NVCC", "").split()) + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -30,7 +32,7 @@ def _nvcc():
     raise RuntimeError("nvcc not found (set NVCC or put /usr/local/cuda/bin on PATH)")
 
 
-FLAGS_STAMP = os.path.join(PKG_DIR, "build", "flags.txt")
+FLAGS_STAMP = os.path.join(PKG_DIR, "build" + SUFFIX, "flags.txt")
 
 
 def needs_build():
@@ -50,7 +52,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = _nvcc()
     objs = []
-    obj_dir = os.path.join(PKG_DIR, "build")
+    obj_dir = os.path.join(PKG_DIR, "build" + SUFFIX)
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for s in SOURCES:

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libasrk.so")
+LIB_PATH = os.path.join(_PKG_DIR, "libasrk%s.so" % os.environ.get("ASRK_LIB_SUFFIX", ""))
 
 OK = 0
 E_BADARG, E_SHAPE, E_ALIGN, E_WORKSPACE, E_CUDA = -1, -2, -3, -4, -5

@@ -36,19 +36,25 @@ ASRK_HD cplx cmul(cplx a, cplx b) {
 #define ASRK_S1 0.95105651629515357212
 #define ASRK_S2 0.58778525229247312917
 
-// forward 5-point DFT (kernel exp(-2 pi i nk/5)), in place.
+// forward 5-point DFT (kernel exp(-2 pi i nk/5)), in place.  32 fp64 instructions: the sine
+// terms are folded into the output FMAs (a1 = m1 - i s1 as two chained FMAs per component) and
+// the mirrored output is formed as 2 m1 - a1 (one FMA), which saves the separate s1 / s2 values.
+#if defined(__CUDACC__)
+#define ASRK_FMA(a, b, c) fma((a), (b), (c))
+#else
+#define ASRK_FMA(a, b, c) __builtin_fma((a), (b), (c))
+#endif
 ASRK_HD void dft5(cplx& a0, cplx& a1, cplx& a2, cplx& a3, cplx& a4) {
-    cplx t1 = cadd(a1, a4), t2 = cadd(a2, a3);
-    cplx t3 = csub(a1, a4), t4 = csub(a2, a3);
-    cplx m1{a0.x + ASRK_C1 * t1.x + ASRK_C2 * t2.x, a0.y + ASRK_C1 * t1.y + ASRK_C2 * t2.y};
-    cplx m2{a0.x + ASRK_C2 * t1.x + ASRK_C1 * t2.x, a0.y + ASRK_C2 * t1.y + ASRK_C1 * t2.y};
-    cplx s1{ASRK_S1 * t3.x + ASRK_S2 * t4.x, ASRK_S1 * t3.y + ASRK_S2 * t4.y};
-    cplx s2{ASRK_S2 * t3.x - ASRK_S1 * t4.x, ASRK_S2 * t3.y - ASRK_S1 * t4.y};
+    const cplx t1 = cadd(a1, a4), t2 = cadd(a2, a3);
+    const cplx t3 = csub(a1, a4), t4 = csub(a2, a3);
+    const cplx m1{ASRK_FMA(ASRK_C2, t2.x, ASRK_FMA(ASRK_C1, t1.x, a0.x)), ASRK_FMA(ASRK_C2, t2.y, ASRK_FMA(ASRK_C1, t1.y, a0.y))};
+    const cplx m2{ASRK_FMA(ASRK_C1, t2.x, ASRK_FMA(ASRK_C2, t1.x, a0.x)), ASRK_FMA(ASRK_C1, t2.y, ASRK_FMA(ASRK_C2, t1.y, a0.y))};
     a0 = cplx{a0.x + t1.x + t2.x, a0.y + t1.y + t2.y};
-    a1 = cplx{m1.x + s1.y, m1.y - s1.x};   // m1 - i s1
-    a4 = cplx{m1.x - s1.y, m1.y + s1.x};   // m1 + i s1
-    a2 = cplx{m2.x + s2.y, m2.y - s2.x};
-    a3 = cplx{m2.x - s2.y, m2.y + s2.x};
+    // s1 = S1 t3 + S2 t4, s2 = S2 t3 - S1 t4;  a1 = m1 - i s1, a4 = m1 + i s1, a2 = m2 - i s2, a3 = m2 + i s2
+    a1 = cplx{ASRK_FMA(ASRK_S2, t4.y, ASRK_FMA(ASRK_S1, t3.y, m1.x)), ASRK_FMA(-ASRK_S2, t4.x, ASRK_FMA(-ASRK_S1, t3.x, m1.y))};
+    a4 = cplx{ASRK_FMA(2.0, m1.x, -a1.x), ASRK_FMA(2.0, m1.y, -a1.y)};
+    a2 = cplx{ASRK_FMA(-ASRK_S1, t4.y, ASRK_FMA(ASRK_S2, t3.y, m2.x)), ASRK_FMA(ASRK_S1, t4.x, ASRK_FMA(-ASRK_S2, t3.x, m2.y))};
+    a3 = cplx{ASRK_FMA(2.0, m2.x, -a2.x), ASRK_FMA(2.0, m2.y, -a2.y)};
 }
 
 // forward 4-point DFT, in place.
@@ -144,15 +150,17 @@ ASRK_HD void fft200_pass1(const cplx (&z)[20], const cplx* tw, cplx (&y)[20]) {
     for (int k1 = 1; k1 < 20; ++k1) y[k1] = cmul(y[k1], tw[k1]);
 }
 
-// |X|^2 * 4 for the bin pair (k, 200-k)
+// |X|^2 * 4 for the bin pair (k, 200-k): 2 X[k] = E + O, 2 conj(X[200-k]) = E - O with
+// E = A + conj(Zm), O = P (A - conj(Zm)).  14 fp64 instructions: O is never formed, E + O is
+// two chained FMAs per component and E - O = 2 E - (E + O) one.
 ASRK_HD void split_pair(cplx A, cplx Zm, cplx P, double& pk, double& pm) {
-    cplx B{Zm.x, -Zm.y};
-    cplx E = cadd(A, B), D = csub(A, B);
-    cplx O = cmul(P, D);
-    double ex = E.x + O.x, ey = E.y + O.y;
-    double fx = E.x - O.x, fy = E.y - O.y;
-    pk = ex * ex + ey * ey;
-    pm = fx * fx + fy * fy;
+    const double Ex = A.x + Zm.x, Ey = A.y - Zm.y;
+    const double Dx = A.x - Zm.x, Dy = A.y + Zm.y;
+    const double ex = ASRK_FMA(P.x, Dx, ASRK_FMA(-P.y, Dy, Ex));
+    const double ey = ASRK_FMA(P.x, Dy, ASRK_FMA(P.y, Dx, Ey));
+    const double fx = ASRK_FMA(2.0, Ex, -ex), fy = ASRK_FMA(2.0, Ey, -ey);
+    pk = ASRK_FMA(ex, ex, ey * ey);
+    pm = ASRK_FMA(fx, fx, fy * fy);
 }
 
 // LoadY(k1, n2) -> cplx ; P[k] = -i W400^k = (-sin(2 pi k/400), -cos(2 pi k/400));

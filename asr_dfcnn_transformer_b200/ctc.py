@@ -106,7 +106,7 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
     if grad_scale is not None:
         grad_scale = grad_scale.to(device=dev, dtype=torch.float32).contiguous()
     nbytes = L.asrk_ctc_workspace_bytes(T, B, Ls)
-    ws = workspace(nbytes, dev, "ctc")
+    ws = workspace(nbytes, dev, "ctc", stream)
     rc = L.asrk_ctc_loss_grad_run_phases(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(labels), Ls,
                                          _lib.ptr(label_len), _lib.ptr(input_len), int(blank), mode,
                                          _lib.ptr(grad_scale), _lib.ptr(loss), _lib.ptr(grad), gt, gb,
@@ -241,7 +241,7 @@ def greedy_decode(logits, input_len, blank=None, merge_repeated=True, layout="tb
     tlen = torch.empty(B, dtype=torch.int32, device=dev)
     nsl = torch.empty(B, dtype=torch.float32, device=dev)
     nbytes = L.asrk_ctc_decode_workspace_bytes(max(T, 1), B)
-    ws = workspace(nbytes, dev, "ctc")
+    ws = workspace(nbytes, dev, "ctc", stream)
     rc = L.asrk_ctc_greedy_decode_run(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(input_len), int(blank),
                                       1 if merge_repeated else 0, _lib.ptr(tokens), max(T, 1),
                                       _lib.ptr(tlen), _lib.ptr(nsl), _lib.ptr(ws), ws.numel(),

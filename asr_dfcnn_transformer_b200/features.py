@@ -45,13 +45,18 @@ def _check_frames(n, n_samples):
 _workspaces = {}
 
 
-def workspace(nbytes, device, tag="spec"):
-    """grow-only scratch tensor per (device, tag, stream)."""
+def workspace(nbytes, device, tag="spec", stream=None):
+    """grow-only scratch tensor per (device, tag, LAUNCH stream): the stream the kernels are
+    enqueued on (``stream``; torch's current stream when None) owns the buffer, so two calls on
+    two explicit streams never share scratch memory, and a grown buffer is allocated -- and its
+    predecessor released -- under the stream that uses it."""
     torch = _lib.require_cuda()
-    key = (str(device), tag, torch.cuda.current_stream(device).cuda_stream)
+    s = torch.cuda.current_stream(device) if stream is None else stream
+    key = (str(device), tag, s.cuda_stream)
     w = _workspaces.get(key)
     if w is None or w.numel() < nbytes:
-        w = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        with torch.cuda.stream(s):
+            w = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = w
     return w
 
@@ -120,7 +125,7 @@ def spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, ba
     if out is None:
         out = torch.empty((max(total_frames, 1), N_BINS), dtype=torch.float32, device=dev)[:total_frames]
     nbytes = L.asrk_spectrogram_workspace_bytes(batch, total_frames)
-    ws = workspace(nbytes, dev, "spec")
+    ws = workspace(nbytes, dev, "spec", stream)
     st = L.asrk_spectrogram_run_phases(_lib.ptr(samples), dt, _lib.ptr(noise), _lib.ptr(gain),
                                        _lib.ptr(snr_db), _lib.ptr(sample_offsets), _lib.ptr(sample_counts),
                                        _lib.ptr(frame_offsets), _lib.ptr(out_row_offsets), batch,
