@@ -80,6 +80,8 @@ struct Params {
     int fused;           // 1: utterances with a small lattice are done by fused_small_kernel
     int prep_fused;      // 1: fused_small_kernel prepares its own utterance (no prep_kernel launch)
     int small_only;      // 1: the caller bounded the batch (ASRK_CTC_SMALL_ONLY): no generic kernels follow
+    int prob;            // 1: `logits` holds PROBABILITIES p (Keras' softmax output); the op's input is log(p + eps)
+    float eps;           //    (K.ctc_batch_cost: eps = 1e-7) and `grad` is the gradient w.r.t. p
 };
 
 // Utterances whose lattice fits one warp (L <= 31 labels -> 32 state pairs) and whose
@@ -312,6 +314,18 @@ __device__ __forceinline__ float row_sumexp(const RowRegs<NV4>& r, float m) {
     return warp_sum(s);
 }
 
+// PROB input: the op's input is x = log(p + eps), so softmax(x) = (p + eps) / sum(p + eps): no exponentials.
+// Sum of (p + eps) over the row (tail lanes of the register image are not part of the row).
+template <int NV4>
+__device__ __forceinline__ float row_sum_eps(const RowRegs<NV4>& r, int V4, int lane, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+        if (lane + 32 * k < V4) s += ((r.v[k].x + eps) + (r.v[k].y + eps)) + ((r.v[k].z + eps) + (r.v[k].w + eps));
+    }
+    return warp_sum(s);
+}
+
 // generic (unaligned / V % 4 != 0 / very large V) row pass: two sweeps
 __device__ __forceinline__ void row_stats_generic(const float* row, int V, int lane, float& m, int& am,
                                                   float& s) {
@@ -343,13 +357,19 @@ __device__ __forceinline__ void rows_body(const Params& p, long long row, int la
     const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
     float m, s = 0.f;
     int am;
+    const bool prob = WANT_LSE && p.prob;
     if constexpr (NV4 > 0) {
         RowRegs<NV4> r;
         load_row(x, p.V >> 2, lane, r);
         row_argmax(r, lane, m, am);
-        if (WANT_LSE) s = row_sumexp(r, m);
+        if (WANT_LSE) s = prob ? row_sum_eps(r, p.V >> 2, lane, p.eps) : row_sumexp(r, m);
     } else {
         row_stats_generic(x, p.V, lane, m, am, s);
+        if (prob) {
+            s = 0.f;
+            for (int i = lane; i < p.V; i += 32) s += x[i] + p.eps;
+            s = warp_sum(s);
+        }
     }
     const size_t bt = (size_t)b * p.T + t;
     if (lane == 0) {
@@ -357,14 +377,15 @@ __device__ __forceinline__ void rows_body(const Params& p, long long row, int la
         p.argmax[bt] = am;
     }
     if (WANT_LSE) {
-        const float lse = m + __logf(s);
+        // log of the softmax denominator of the op's input: log sum exp(x), or log sum (p + eps)
+        const float lse = prob ? __logf(s) : m + __logf(s);
         if (lane == 0) p.lse[bt] = lse;
         const int L = p.eff_len[b];
         const int* eff = p.eff_labels + (size_t)b * p.Ls;
         float* dst = p.lpl + bt * (size_t)(p.Ls + 1);
         for (int j = lane; j <= L; j += 32) {
             const int c = (j == 0) ? p.blank : eff[j - 1];
-            dst[j] = x[c] - lse;
+            dst[j] = (prob ? __logf(x[c] + p.eps) : x[c]) - lse;
         }
     }
 }

@@ -9,8 +9,7 @@
 //     high-dynamic-range audio, so the 400-point transform runs in fp64 -- B200
 //     has a half-rate fp64 pipe (64 lanes/SM/clk), which is the bound of this
 //     kernel; everything after |X|^2 (sqrt, log, z-score) is fp32.
-//   * ONE persistent kernel, one CTA per SM: kTeams independent teams of five warps
-//     that transform, plus ONE z-score warp that only moves memory.
+//   * ONE persistent kernel, one CTA per SM: kTeams independent teams of five warps.
 //     A team transforms 16 consecutive frames at a time: lane = (frame, role half), the
 //     two half-warps of warp q own roles q and q + 5 of the 20 x 10 Cooley-Tukey split
 //     of the 200-point complex DFT (400-point real DFT = 200-point complex DFT + real-
@@ -34,10 +33,13 @@
 //     in fp64, fixed order: reproducible, no float atomics).  The team that completes an
 //     utterance (release fence one unit late + per-utterance counter: the fence then has
 //     nothing to wait for) turns the unit sums into mean / 1/std and queues the
-//     utterance's units; the z-score warps of all CTAs take tickets from that queue and
-//     pull 16 rows at a time (L2 hits: written microseconds ago) through shared memory
-//     with TMA bulk copies, normalise them there and bulk-store them back.  The raw
-//     rows never make a second HBM round trip and no kernel trails the transform.
+//     utterance's units.  Every team takes tickets from that queue and, next to each of
+//     its own sub-tiles, normalises ONE 16-row chunk of a finished utterance: the rows
+//     come in through shared memory as one TMA bulk copy issued a pass ahead (L2 hits:
+//     written microseconds ago), are normalised by the copy-out lanes and go back as one
+//     bulk store.  The z-score work is thereby spread over all warps and schedulers (a
+//     dedicated z-score warp per CTA could not keep up: profiles/r2_spectrogram.md), the
+//     raw rows never make a second HBM round trip and no kernel trails the transform.
 #include <math.h>
 #include <stdlib.h>
 
@@ -102,7 +104,7 @@ struct Params {
     // workspace
     int* counters;           // [0] next unit, [1] queue tail, [2] queue head   (zeroed per launch)
     int* done;               // [B] published units per utterance               (zeroed per launch)
-    int* queue;              // [units] unit + 1 in completion order, 0 = empty (zeroed per launch)
+    unsigned long long* queue;   // [units] packed (valid | utterance | rows | first row) in completion order, 0 = empty
     int* tile_off_g;         // [B + 1] first unit of every utterance (written by CTA 0)
     double2* partials;       // [units][200]: per-unit column sums (sum y, sum y^2)
     float* stats;            // [B][3][200]: mean (hi, lo), 1/std
@@ -122,7 +124,7 @@ static WsLayout ws_layout(int batch, long long total_frames) {
     // counters | done | queue are contiguous: one memset per launch
     l.counters = o;  o = align_up(o + sizeof(int) * 4, 256);
     l.done = o;      o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
-    l.queue = o;     o = align_up(o + sizeof(int) * max_units(batch, total_frames), 256);
+    l.queue = o;     o = align_up(o + sizeof(unsigned long long) * max_units(batch, total_frames), 256);
     l.zero_bytes = o;
     l.tile_off = o;  o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
     l.gains = o;     o = align_up(o + sizeof(float) * (size_t)batch, 256);
@@ -143,6 +145,12 @@ static WsLayout ws_layout(int batch, long long total_frames) {
 //      x w = d w - (2^20 + 2^15) w is ONE DFMA with the constant tabulated next to the window.
 #ifndef ASRK_SPEC_CONV
 #define ASRK_SPEC_CONV 1
+#endif
+#ifndef ASRK_SPEC_TWGEN
+#define ASRK_SPEC_TWGEN 0
+#endif
+#ifndef ASRK_SPEC_PGEN
+#define ASRK_SPEC_PGEN 0
 #endif
 #if ASRK_SPEC_CONV == 0
 constexpr double kMagic = 1081344.0;                 // 2^20 + 2^15
@@ -166,13 +174,17 @@ __device__ __forceinline__ void stg4_hint(float* p, float4 v, uint64_t policy) {
                  "f"(v.z), "f"(v.w), "l"(policy)
                  : "memory");
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed(int* p, int v) {
-    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// queue entry of one finished unit: bit 63 valid | utterance (16 bits) | rows 1..32 (6 bits) | first output row (40 bits)
+__device__ __forceinline__ unsigned long long pack_entry(int b, int rows, long long grow) {
+    return (1ull << 63) | ((unsigned long long)b << 46) | ((unsigned long long)rows << 40) | (unsigned long long)grow;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // shared -> global bulk store (TMA), tracked by the issuing thread's bulk async-group
@@ -335,14 +347,29 @@ struct Cfg {
     static constexpr int kPcmWords = kSubHopRows * (F32 ? kHopWordsF32 : kHopWordsI16);
     static constexpr int kExchBytes = 200 * kSub * 16;                       // 51 200
     static constexpr int kOutBytes = kSepOut ? kSub * kOutStride * 4 : 0;    // 13 056
-    static constexpr int kTeamBytes = kExchBytes + kPcmWords * 4 + kOutBytes;
-    // the float32 staging of three teams leaves room for one z-score buffer only
-    static constexpr int kZBufs = (F32 && kTeams == 3) ? 1 : 2;
-    static constexpr int kThreads = kTeams * kTeamThreads + 32;
+    // one z-score chunk buffer per team; the float32 (noise-mix) staging leaves no room for it next to
+    // three exchange buffers: that path z-scores with the trailing kernels
+    static constexpr bool kZ = !(F32 && kTeams == 3);
+    static constexpr int kTeamBytes = kExchBytes + kPcmWords * 4 + kOutBytes + (kZ ? kZBytes : 0);
+    static constexpr int kThreads = kTeams * kTeamThreads;
     static constexpr size_t smem_bytes() {
-        return (size_t)(200 * 32 + 3200 + 3200) + sizeof(int) * (kMaxBatch + 1) + (size_t)kZBufs * kZBytes +
-               (size_t)kTeams * kTeamBytes + 16;
+        return (size_t)(200 * 32 + 3200 + 3200) + sizeof(int) * (kMaxBatch + 1) + (size_t)kTeams * kTeamBytes + 16;
     }
+};
+
+// z-score state of one team (shared memory; written by the team's first thread only)
+struct ZState {
+    unsigned long long ent;   // polled queue entry of ticket `tkt` (0: not there yet)
+    long long cur_row;        // next output row of the unit being cut into chunks
+    long long grow;           // first output row of the chunk in the buffer
+    int tkt;                  // ticket held (-1: none)
+    int exhausted;            // every ticket has been handed out
+    int cur_left;             // rows left in the unit being cut
+    int cur_b;
+    int loaded;               // 1: a chunk is in the buffer (bulk load issued), waiting to be normalised / stored
+    int rows, b;              // ... its rows and utterance
+    int nproc;                // chunks processed so far (phase parity of the buffer's mbarrier)
+    int finished;             // drain: nothing left
 };
 
 __device__ __forceinline__ void team_bar(int team) {
@@ -350,120 +377,11 @@ __device__ __forceinline__ void team_bar(int team) {
 }
 
 // ---------------------------------------------------------------------------
-// the z-score warp: tickets -> units of completed utterances -> 16-row chunks through smem
-// ---------------------------------------------------------------------------
-template <int kZBufs>
-__device__ void zscore_warp(const Params& p, const int* tile_off, int total_units, float* zbuf, uint64_t* zbar,
-                            int lane) {
-    const bool act = lane < 25;                 // lane owns float4 columns lane and lane + 25 of every row
-    float4 mhA, mlA, ivA, mhB, mlB, ivB;
-    mhA = mlA = ivA = mhB = mlB = ivB = make_float4(0.f, 0.f, 0.f, 0.f);
-    int stat_b = -1;
-    const uint64_t drop = l2_policy_evict_first();
-    // current unit being cut into chunks
-    int u_b = -1, u_rows_left = 0;
-    long long u_row = 0;
-    struct Chunk {
-        int rows, b;
-        long long grow;
-    };
-    auto get = [&](Chunk& c) -> bool {
-        if (u_rows_left <= 0) {
-            int e = 0;
-            if (lane == 0) {
-                const int ticket = atomicAdd(p.counters + 2, 1);
-                if (ticket < total_units) {
-                    while ((e = ld_acquire(p.queue + ticket)) == 0) __nanosleep(256);
-                } else {
-                    e = -1;
-                }
-            }
-            e = __shfl_sync(0xffffffffu, e, 0);
-            if (e < 0) return false;
-            const int unit = e - 1;
-            const int b = find_utterance(tile_off, p.batch, unit);
-            const long long fo = p.frame_offsets[b];
-            const long long nfr = p.frame_offsets[b + 1] - fo;
-            const long long row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
-            const int f0 = (unit - tile_off[b]) * kUnit;
-            const long long rem = nfr - f0;
-            u_b = b;
-            u_rows_left = rem < kUnit ? (int)rem : kUnit;
-            u_row = row0 + f0;
-        }
-        c.b = u_b;
-        c.rows = u_rows_left < kZRows ? u_rows_left : kZRows;
-        c.grow = u_row;
-        u_rows_left -= c.rows;
-        u_row += c.rows;
-        return true;
-    };
-    unsigned parity[2] = {0, 0};
-    auto issue = [&](const Chunk& c, int buf) {
-        if (lane == 0) {
-            tma_store_wait_read();               // the bulk store that last read this buffer has drained it
-            fence_proxy_async();                 // rows written by other SMs (generic proxy) -> async-proxy read
-            tma_load_1d(zbuf + (size_t)buf * (kZBytes / 4), p.out + (size_t)c.grow * kBins, (unsigned)c.rows * kBins * 4,
-                        zbar + buf, drop);
-        }
-    };
-    Chunk cur, nxt;
-    bool have = get(cur);
-    int k = 0;
-    if (have) issue(cur, 0);
-    while (have) {
-        const int buf = (kZBufs == 2) ? (k & 1) : 0;
-        bool have_next = false;
-        if (kZBufs == 2) {
-            have_next = get(nxt);
-            if (have_next) issue(nxt, buf ^ 1);
-        }
-        if (cur.b != stat_b) {
-            stat_b = cur.b;
-            if (act) {
-                const float4* st = reinterpret_cast<const float4*>(p.stats + (size_t)stat_b * 3 * kBins);
-                mhA = __ldcg(st + lane);       mhB = __ldcg(st + lane + 25);
-                mlA = __ldcg(st + 50 + lane);  mlB = __ldcg(st + 75 + lane);
-                ivA = __ldcg(st + 100 + lane); ivB = __ldcg(st + 125 + lane);
-            }
-        }
-        mbar_wait(zbar + buf, parity[buf]);
-        parity[buf] ^= 1;
-        float4* rows = reinterpret_cast<float4*>(zbuf + (size_t)buf * (kZBytes / 4));
-        if (act) {
-#pragma unroll 4
-            for (int r = 0; r < cur.rows; ++r) {
-                float4 a = rows[r * 50 + lane], b4 = rows[r * 50 + 25 + lane];
-                a.x = ((a.x - mhA.x) - mlA.x) * ivA.x;   a.y = ((a.y - mhA.y) - mlA.y) * ivA.y;
-                a.z = ((a.z - mhA.z) - mlA.z) * ivA.z;   a.w = ((a.w - mhA.w) - mlA.w) * ivA.w;
-                b4.x = ((b4.x - mhB.x) - mlB.x) * ivB.x; b4.y = ((b4.y - mhB.y) - mlB.y) * ivB.y;
-                b4.z = ((b4.z - mhB.z) - mlB.z) * ivB.z; b4.w = ((b4.w - mhB.w) - mlB.w) * ivB.w;
-                rows[r * 50 + lane] = a;
-                rows[r * 50 + 25 + lane] = b4;
-            }
-        }
-        fence_proxy_async();                     // generic-proxy writes of the rows -> async-proxy (bulk store) reads
-        __syncwarp();
-        if (lane == 0) {
-            tma_store_1d(p.out + (size_t)cur.grow * kBins, rows, (unsigned)cur.rows * kBins * 4);
-            tma_store_commit();
-        }
-        if (kZBufs == 1) {
-            have_next = get(nxt);
-            if (have_next) issue(nxt, 0);
-        }
-        cur = nxt;
-        have = have_next;
-        ++k;
-    }
-    if (lane == 0) tma_store_wait_all();         // no bulk copy may be in flight when the CTA exits
-}
-
-// ---------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------
 template <bool F32, int kTeams, bool kSepOut>
-__global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spectrogram_kernel(Params p) {
+__global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads)) __maxnreg__(kTeams == 3 ? 136 : 184)
+spectrogram_kernel(Params p) {
     using C = Cfg<F32, kTeams, kSepOut>;
     constexpr int kPcmWords = C::kPcmWords;
     constexpr int kThreads = C::kThreads;
@@ -473,11 +391,11 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     cplx16* tabTall = reinterpret_cast<cplx16*>(tabW + 800);                  // [10][20]
     cplx16* tabP = tabTall + 200;                                             // [200]
     int* tile_off = reinterpret_cast<int*>(tabP + 200);                       // [kMaxBatch + 1]
-    float* zbuf = reinterpret_cast<float*>(tile_off + kMaxBatch + 1);         // [kZBufs][16][200]
-    unsigned char* team_base = reinterpret_cast<unsigned char*>(zbuf) + (size_t)C::kZBufs * kZBytes;
+    unsigned char* team_base = reinterpret_cast<unsigned char*>(tile_off + kMaxBatch + 1);
     __shared__ Meta meta[kTeams][2];
     __shared__ int s_fin[kTeams];
-    __shared__ uint64_t s_zbar[2];
+    __shared__ ZState s_z[kTeams];
+    __shared__ uint64_t s_zbar[kTeams];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -489,11 +407,13 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
         tabW[4 * m + 2 + e] = -kMagic * w;
     }
     for (int i = tid; i < 800; i += kThreads) reinterpret_cast<double*>(tabTall)[i] = g_tab[400 + i];
-    if (tid == 0) {
-        mbar_init(s_zbar, 1);
-        mbar_init(s_zbar + 1, 1);
-        mbar_fence_init();
+    if (tid < kTeams) {
+        mbar_init(s_zbar + tid, 1);
+        ZState& z = s_z[tid];
+        z.ent = 0; z.cur_row = 0; z.grow = 0; z.tkt = -1; z.exhausted = 0; z.cur_left = 0; z.cur_b = 0;
+        z.loaded = 0; z.rows = 0; z.b = 0; z.nproc = 0; z.finished = 0;
     }
+    if (tid == 0) mbar_fence_init();
     if (warp == 0) {
         // exclusive scan of ceil(n_frames / kUnit) over the utterances
         int carry = 0;
@@ -519,14 +439,9 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     __syncthreads();
     const int total_tiles = tile_off[p.batch];
     const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
-    const bool zin = want_stats && p.zscore_in_kernel;
+    const bool zin = C::kZ && want_stats && p.zscore_in_kernel;
     if (blockIdx.x == 0 && want_stats)
         for (int i = tid; i <= p.batch; i += kThreads) p.tile_off_g[i] = tile_off[i];
-
-    if (warp == kTeams * kTeamWarps) {
-        if (zin) zscore_warp<C::kZBufs>(p, tile_off, total_tiles, zbuf, s_zbar, lane);
-        return;
-    }
 
     const int team = warp / kTeamWarps, q = warp - team * kTeamWarps;
     const int tt = tid - team * kTeamThreads;
@@ -534,6 +449,9 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     uint32_t* pcm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(exch) + C::kExchBytes);
     // out tile [16][204]: its own buffer, or aliased onto the exchange (then two more team barriers guard it)
     float* ot = kSepOut ? reinterpret_cast<float*>(pcm + kPcmWords) : reinterpret_cast<float*>(exch);
+    float* zbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(pcm + kPcmWords) + C::kOutBytes);   // [16][200]
+    ZState& zs = s_z[team];
+    uint64_t* zbar = s_zbar + team;
 
     // lane -> (frame of the sub-tile, role): the two half-warps of warp q own roles q, q + 5
     const int f = lane & 15;
@@ -544,8 +462,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     const double2* tabW2 = reinterpret_cast<const double2*>(tabW);
     const cplx16* tabT = tabTall + r * 20;
     const bool mix = (p.noise != nullptr);
-    // the un-normalised rows are read again by the z-score: keep them in L2
-    const uint64_t keep = want_stats ? l2_policy_evict_last() : l2_policy_evict_first();
     // copy-out geometry: lane -> (float4 column 10 q + lane / 3, row phase lane % 3)
     const bool co_act = lane < 30;
     const int co_c4 = 10 * q + (co_act ? lane / 3 : 0);
@@ -574,7 +490,7 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     };
     // publication of a finished unit, one unit late (the fence then finds every store of the unit
     // acknowledged): the team's first thread counts the unit on its utterance; whoever completes the
-    // utterance makes its statistics (whole team) and queues its units for the z-score warps
+    // utterance makes its statistics (whole team) and queues its units for the z-score
     int pub_b = -1, pub_nt = 0;      // (thread 0) utterance / unit count of the unit to publish
     auto publish_count = [&]() {     // thread 0, after a team barrier that follows the unit's last store
         if (tt == 0) {
@@ -590,23 +506,84 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     };
     auto publish_queue = [&](int fin) {   // thread 0, after a team barrier that follows finalize_stats
         if (tt == 0 && fin >= 0) {
+            const long long fo = p.frame_offsets[fin];
+            const long long nfr = p.frame_offsets[fin + 1] - fo;
+            const long long row0 = p.out_row_offsets ? p.out_row_offsets[fin] : fo;
             __threadfence();
-            const int t0 = tile_off[fin], nt = tile_off[fin + 1] - t0;
+            const int nt = tile_off[fin + 1] - tile_off[fin];
             const int slot = atomicAdd(p.counters + 1, nt);
-            for (int c = 0; c < nt; ++c) st_relaxed(p.queue + slot + c, t0 + c + 1);
+            for (int c = 0; c < nt; ++c) {
+                const long long left = nfr - (long long)c * kUnit;
+                st_relaxed(p.queue + slot + c, pack_entry(fin, left < kUnit ? (int)left : kUnit, row0 + (long long)c * kUnit));
+            }
         }
+    };
+    // ---- z-score steps (all no-ops unless zin) ----------------------------------------------------
+    // thread 0, right after a "P" barrier: the chunk normalised during the previous copy-out goes home
+    auto z_store = [&]() {
+        if (zin && tt == 0 && zs.loaded) {
+            tma_store_1d(p.out + (size_t)zs.grow * kBins, zbuf, (unsigned)zs.rows * kBins * 4);
+            tma_store_commit();
+            zs.loaded = 0;
+            zs.nproc = zs.nproc + 1;
+        }
+    };
+    // thread 0: adopt a polled entry as the unit to cut ...
+    auto z_adopt = [&]() {
+        if (zs.cur_left == 0 && zs.ent != 0) {
+            const unsigned long long e = zs.ent;
+            zs.cur_row = (long long)(e & ((1ull << 40) - 1));
+            zs.cur_left = (int)((e >> 40) & 63);
+            zs.cur_b = (int)((e >> 46) & 0xffff);
+            zs.ent = 0;
+            zs.tkt = -1;
+        }
+    };
+    // ... and start the bulk load of its next chunk into the (free) buffer
+    auto z_issue = [&]() {
+        if (!zs.loaded && zs.cur_left > 0) {
+            const int rows = zs.cur_left < kZRows ? zs.cur_left : kZRows;
+            tma_store_wait_read();               // the bulk store that last read the buffer has drained it
+            fence_proxy_async();                 // rows written through the generic proxy -> async-proxy read
+            tma_load_1d(zbuf, p.out + (size_t)zs.cur_row * kBins, (unsigned)rows * kBins * 4, zbar, l2_policy_evict_first());
+            zs.grow = zs.cur_row;
+            zs.rows = rows;
+            zs.b = zs.cur_b;
+            zs.cur_row += rows;
+            zs.cur_left -= rows;
+            zs.loaded = 1;
+        }
+    };
+    // all threads, in the copy-out phase: normalise the chunk in the buffer (lane = (4 bins, row phase))
+    auto z_process = [&](const float4& mh, const float4& ml, const float4& iv, int zrows, unsigned zpar) {
+        mbar_wait(zbar, zpar);
+        if (co_act) {
+            float4* rows = reinterpret_cast<float4*>(zbuf) + co_c4;
+            for (int row = co_ph; row < zrows; row += 3) {
+                float4 a = rows[row * 50];
+                a.x = ((a.x - mh.x) - ml.x) * iv.x;
+                a.y = ((a.y - mh.y) - ml.y) * iv.y;
+                a.z = ((a.z - mh.z) - ml.z) * iv.z;
+                a.w = ((a.w - mh.w) - ml.w) * iv.w;
+                rows[row * 50] = a;
+            }
+        }
+        fence_proxy_async();                     // generic-proxy writes of the rows -> async-proxy (bulk store) reads
     };
 
     prepare_meta(0);
     if (tt == 0) { cp_async_commit(); cp_async_wait<0>(); }
     team_bar(team);
     if (meta[team][0].valid) stage(meta[team][0], meta[team][0].f0);
+    // the un-normalised rows are read again by the z-score: keep them in L2
+    const uint64_t keep = want_stats ? l2_policy_evict_last() : l2_policy_evict_first();
     for (int u = 0;; ++u) {
         const Meta& m = meta[team][u & 1];
         if (!m.valid) break;
         const Meta& mnext = meta[team][(u + 1) & 1];
         cp_async_wait<0>();
         team_bar(team);                         // P: the first sub-tile's PCM and the unit's constants are in place
+        z_store();
         const long long m_nfr = m.fo1 - m.fo;
         const int m_nf = (m_nfr - m.f0) < kUnit ? (int)(m_nfr - m.f0) : kUnit;
         const long long m_row0 = p.out_row_offsets ? m.row0 : m.fo;
@@ -619,6 +596,7 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
             if (sub > 0) {
                 cp_async_wait<0>();
                 team_bar(team);                 // P: the sub-tile's PCM is in place; the previous copy-out is over
+                z_store();
             } else {
                 prepare_meta((u + 1) & 1);      // (flags visible to the team after the next barrier)
                 if (zin) publish_count();
@@ -653,12 +631,26 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
                 }
                 dft20(z, y);
                 exch[r * kSub + f] = cplx16{y[0].x, y[0].y};
+#if ASRK_SPEC_TWGEN
+                // twiddles W200^(r k1) by recurrence from W200^r: 72 fp64 instructions instead of 18 more
+                // 16-byte table broadcasts (the kernel is shared-memory-wavefront bound before it is fp64 bound)
+                const cplx16 t1l = tabT[1];
+                const cplx t1{t1l.x, t1l.y};
+                cplx tk = t1;
+#pragma unroll
+                for (int k1 = 1; k1 < 20; ++k1) {
+                    const cplx v = cmul(y[k1], tk);
+                    exch[(k1 * 10 + r) * kSub + f] = cplx16{v.x, v.y};
+                    if (k1 < 19) tk = cmul(tk, t1);
+                }
+#else
 #pragma unroll
                 for (int k1 = 1; k1 < 20; ++k1) {
                     const cplx16 t = tabT[k1];
                     const cplx v = cmul(y[k1], cplx{t.x, t.y});
                     exch[(k1 * 10 + r) * kSub + f] = cplx16{v.x, v.y};
                 }
+#endif
             }
             team_bar(team);                     // A: pass-1 stores -> pass-2 loads; the PCM has been read
             if (zin && sub == 0) fin = s_fin[team];
@@ -666,6 +658,16 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
             if (sub + 1 < nsub) stage(m, m.f0 + (sub + 1) * kSub);
             else if (mnext.valid) stage(mnext, mnext.f0);
             if (fin >= 0 && sub == 0) finalize_stats(p, tile_off, fin, tt);
+            // z-score, thread 0: start the bulk load of this sub-tile's chunk; ask for the next ticket or poll
+            // its entry -- the answers are consumed after pass 2 (nobody stalls on them)
+            int z_tkt = -2;
+            unsigned long long z_ent = 0;
+            if (zin && tt == 0) {
+                z_adopt();
+                z_issue();
+                if (zs.tkt < 0) { if (!zs.exhausted) z_tkt = atomicAdd(p.counters + 2, 1); }
+                else if (zs.ent == 0) z_ent = ld_acquire(p.queue + zs.tkt);
+            }
             // ---------------- pass 2: DFT10 of rows j and 20-j, split, log ----------------
             {
                 cplx ia[10], ib[10], za[10], zb[10];
@@ -700,10 +702,25 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
                     };
                     split_lane(j0, za, zb, loadP, emit);
                 } else {
+#if ASRK_SPEC_PGEN
+                    const cplx16 p0l = tabP[r];
+                    const cplx p0{p0l.x, p0l.y};
+#endif
 #pragma unroll
                     for (int s = 0; s < 10; ++s) {
                         const int k = r + 20 * s;
+#if ASRK_SPEC_PGEN
+                        // P[r + 20 s] = P[r] W20^s with W20^s a compile-time constant (constant-bank operands)
+                        constexpr double kC20[10] = {1.0, 0.95105651629515357212, 0.80901699437494742410, 0.58778525229247312917,
+                                                     0.30901699437494742410, 0.0, -0.30901699437494742410,
+                                                     -0.58778525229247312917, -0.80901699437494742410, -0.95105651629515357212};
+                        constexpr double kS20[10] = {0.0, -0.30901699437494742410, -0.58778525229247312917, -0.80901699437494742410,
+                                                     -0.95105651629515357212, -1.0, -0.95105651629515357212,
+                                                     -0.80901699437494742410, -0.58778525229247312917, -0.30901699437494742410};
+                        const cplx t = (s == 0) ? p0 : cmul(p0, cplx{kC20[s], kS20[s]});
+#else
                         const cplx16 t = tabP[k];
+#endif
                         double pk, pm;
                         split_pair(za[s], zb[9 - s], cplx{t.x, t.y}, pk, pm);
                         orow[200 - k] = log_mag((float)pm, hm);
@@ -713,6 +730,16 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
             }
             team_bar(team);                     // C: the out tile is complete
             if (sub == 0) publish_queue(fin);
+            // z-score: the statistics of the chunk's utterance are requested now and used after the copy-out
+            const int zrows = zin ? (zs.loaded ? zs.rows : 0) : 0;
+            float4 zmh, zml, ziv;
+            zmh = zml = ziv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (zrows > 0 && co_act) {
+                const float4* st = reinterpret_cast<const float4*>(p.stats + (size_t)zs.b * 3 * kBins) + co_c4;
+                zmh = __ldcg(st);
+                zml = __ldcg(st + 50);
+                ziv = __ldcg(st + 100);
+            }
             // ---------------- copy-out (16-byte accesses) + column sums ----------------
             {
                 const int rows = (m_nf - sub * kSub) < kSub ? (m_nf - sub * kSub) : kSub;
@@ -728,6 +755,14 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
                     d = y.z - cS.z; sS.z += d; qS.z = fmaf(d, d, qS.z);
                     d = y.w - cS.w; sS.w += d; qS.w = fmaf(d, d, qS.w);
                 }
+            }
+            if (zrows > 0) z_process(zmh, zml, ziv, zrows, (unsigned)zs.nproc & 1u);
+            if (zin && tt == 0) {
+                if (z_tkt != -2) {
+                    if (z_tkt < total_tiles) zs.tkt = z_tkt;
+                    else zs.exhausted = 1;
+                }
+                if (z_ent != 0) zs.ent = z_ent;
             }
         }
         if (want_stats) {
@@ -755,14 +790,48 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
         }
     }
     if (zin) {
-        // drain: the team's last unit is published here
+        // drain: the team's last unit is published here ...
         team_bar(team);
+        z_store();
         publish_count();
         team_bar(team);
         const int fin = s_fin[team];
         if (fin >= 0) finalize_stats(p, tile_off, fin, tt);
         team_bar(team);
         publish_queue(fin);
+        // ... and the team keeps normalising queued chunks until every ticket has been handed out
+        for (;;) {
+            if (tt == 0 && !zs.loaded) {
+                while (zs.cur_left == 0 && !zs.finished) {
+                    if (zs.ent == 0) {
+                        if (zs.tkt < 0) {
+                            const int t = zs.exhausted ? total_tiles : atomicAdd(p.counters + 2, 1);
+                            if (t >= total_tiles) { zs.exhausted = 1; zs.finished = 1; break; }
+                            zs.tkt = t;
+                        }
+                        unsigned long long e;
+                        while ((e = ld_acquire(p.queue + zs.tkt)) == 0) __nanosleep(200);
+                        zs.ent = e;
+                    }
+                    z_adopt();
+                }
+                z_issue();
+            }
+            team_bar(team);
+            if (!zs.loaded) break;               // (finished, and nothing in the buffer)
+            float4 zmh, zml, ziv;
+            zmh = zml = ziv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (co_act) {
+                const float4* st = reinterpret_cast<const float4*>(p.stats + (size_t)zs.b * 3 * kBins) + co_c4;
+                zmh = __ldcg(st);
+                zml = __ldcg(st + 50);
+                ziv = __ldcg(st + 100);
+            }
+            z_process(zmh, zml, ziv, zs.rows, (unsigned)zs.nproc & 1u);
+            team_bar(team);
+            z_store();
+        }
+        if (tt == 0) tma_store_wait_all();       // no bulk copy may be in flight when the CTA exits
     }
 }
 
@@ -917,8 +986,10 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
     // the z-score runs inside the main kernel when both phases are asked for in one call (the normal
     // case); a harness that times the phases one by one gets the separate kernels
     const bool both = (phases & ASRK_PHASE_SPEC_MAIN) && (phases & ASRK_PHASE_SPEC_NORMALIZE);
-    const int zin = (mode == ASRK_SPEC_FBANK && both && cfg_zscore_in_kernel()) ? 1 : 0;
     const int teams = cfg_teams();
+    // (the float32 / noise-mix staging of three teams leaves no shared memory for the z-score buffers)
+    const bool z_fits = !(sample_dtype == ASRK_DTYPE_F32 && teams == 3);
+    const int zin = (mode == ASRK_SPEC_FBANK && both && z_fits && cfg_zscore_in_kernel()) ? 1 : 0;
 
     // the kernel locates units through a prefix array in shared memory: at most
     // kMaxBatch utterances per launch, larger batches go in slices
@@ -938,7 +1009,7 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         p.out = out;
         p.counters = reinterpret_cast<int*>(ws + l.counters);
         p.done = reinterpret_cast<int*>(ws + l.done);
-        p.queue = reinterpret_cast<int*>(ws + l.queue);
+        p.queue = reinterpret_cast<unsigned long long*>(ws + l.queue);
         p.tile_off_g = reinterpret_cast<int*>(ws + l.tile_off);
         p.partials = reinterpret_cast<double2*>(ws + l.partials);
         p.stats = reinterpret_cast<float*>(ws + l.stats) + (size_t)b0 * 3 * kBins;

@@ -89,7 +89,7 @@ def logfbank_frames(n_samples, frame_len=400, frame_step=160):
 
 
 def compute_fbank_from_api_batch(signals, sample_rate=16000, nfilt=200, normalise=True, padded_rows=None,
-                                 device=None):
+                                 device=None, preemph=0.97):
     """Batched mel front end on the device: list of 1-D signals (any real dtype, e.g. the
     float64 in [-1, 1] that soundfile returns) -> FeatureBatch with a float32 device tensor,
     ragged ``[sum n_frames, nfilt]`` or zero-padded ``[B, padded_rows, nfilt]``."""
@@ -123,7 +123,7 @@ def compute_fbank_from_api_batch(signals, sample_rate=16000, nfilt=200, normalis
     else:
         out = torch.empty((int(fo[-1]), nfilt), dtype=torch.float32, device=dev)
     st = _lib.lib().asrk_logfbank_run(_lib.ptr(samples), _lib.ptr(so), _lib.ptr(sc), _lib.ptr(fo_d), _lib.ptr(oro),
-                                      _lib.ptr(bins), B, int(fo[-1]), int(nfilt), frame_len, frame_step, 0.97,
+                                      _lib.ptr(bins), B, int(fo[-1]), int(nfilt), frame_len, frame_step, float(preemph),
                                       1 if normalise else 0, _lib.ptr(out), _lib.stream_ptr(None))
     _lib.check(st, "asrk_logfbank_run")
     return features.FeatureBatch(out, fo, nfr)
@@ -133,9 +133,15 @@ def compute_fbank_from_api(signal, sample_rate, nfilt=200):
     """wav_util.py:22-31: ``logfbank(signal, sample_rate, nfilt)`` + per-filter z-score.
     Returns float64 ``[n_frames, nfilt]`` like the reference."""
     sig = np.asarray(signal)
-    if sig.ndim == 2:                       # read_wav_data returns [channels, samples]
-        sig = sig[0]
-    fb = compute_fbank_from_api_batch([sig], sample_rate, nfilt)
+    preemph = 0.97
+    if sig.ndim == 2:
+        # read_wav_data returns [channels, samples] (compute_fbank_from_file without sf_flag, :13-19), and
+        # python_speech_features' preemphasis is ``np.append(signal[0], signal[1:] - 0.97 * signal[:-1])``:
+        # on a 2-D array that is row 0 UNCHANGED followed by the row differences -- for a mono file the
+        # samples as they are, with no pre-emphasis at all.  Reproduced here.
+        sig = np.append(sig[0], sig[1:] - 0.97 * sig[:-1])
+        preemph = 0.0
+    fb = compute_fbank_from_api_batch([sig], sample_rate, nfilt, preemph=preemph)
     return fb.features.cpu().numpy().astype(np.float64)
 
 

@@ -83,3 +83,43 @@ def load():
     assert os.path.realpath(wav_util.__file__).startswith(os.path.realpath(REFERENCE_ROOT))
     _cache["mods"] = (wav_util, noise)
     return _cache["mods"]
+
+
+def _wave_sf_read(path):
+    """What soundfile.read returns for a 16-bit PCM wav: float64 in [-1, 1] and the sample rate."""
+    import wave
+    w = wave.open(path, "rb")
+    n, ch, fs = w.getnframes(), w.getnchannels(), w.getframerate()
+    raw = w.readframes(n)
+    w.close()
+    a = np.frombuffer(raw, dtype=np.int16).astype(np.float64) / 32768.0
+    return (a if ch == 1 else a.reshape(-1, ch)), fs
+
+
+def load_data_loader():
+    """Return the reference's ``lm_and_am.data_loader`` module, unmodified, for generating the loader
+    golden vectors (tools/make_golden_loader.py).  keras / tensorflow are stubbed (the loader only imports
+    them), ``soundfile.read`` is a wave-module reader, and ``python_speech_features.logfbank`` -- absent
+    and un-installable here -- is the restatement in oracle/psf_ref.py: the loader's CONTROL LOGIC (shapes,
+    lengths, label ids, reject rules, row deletion) is pinned to the reference's own code, the mel features
+    inside remain "parity unpinned"."""
+    if "loader" in _cache:
+        return _cache["loader"]
+    wav_util, _ = load()
+    from oracle import psf_ref
+    sys.modules["soundfile"].read = _wave_sf_read
+    sys.modules["python_speech_features"].logfbank = \
+        lambda signal, samplerate=16000, nfilt=26, **kw: psf_ref.logfbank(signal, samplerate, nfilt=nfilt)
+    wav_util.sf.read = _wave_sf_read
+    wav_util.logfbank = sys.modules["python_speech_features"].logfbank
+    keras = _stub("keras")
+    ku = _stub("keras.utils", Sequence=object)
+    kb = _stub("keras.backend")
+    keras.utils, keras.backend = ku, kb
+    _stub("tensorflow")
+    for k in [k for k in sys.modules if k == "lm_and_am" or k.startswith("lm_and_am.")]:
+        del sys.modules[k]
+    mod = importlib.import_module("lm_and_am.data_loader")
+    assert os.path.realpath(mod.__file__).startswith(os.path.realpath(REFERENCE_ROOT))
+    _cache["loader"] = mod
+    return mod

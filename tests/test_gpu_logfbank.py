@@ -50,10 +50,19 @@ def test_zscored_vs_oracle_and_surface(tmp_path):
     path = str(tmp_path / "a.wav")
     wavfile.write(path, 16000, pcm)
     got = wav_util.compute_fbank_from_file(path, 200)
-    ref = psf_ref.compute_fbank_from_api(pcm.astype(np.float64), 16000)
-    ref_raw = psf_ref.logfbank(pcm.astype(np.float64))
+    # the oracle gets what the reference passes on: read_wav_data's [1, N] int16 array -- for which the
+    # library's pre-emphasis expression leaves the samples unchanged (no pre-emphasis on this path)
+    wd, fr = wav_util.read_wav_data(path)
+    assert wd.shape == (1, len(pcm)) and fr == 16000
+    ref = psf_ref.compute_fbank_from_api(wd, 16000)
+    ref_raw = psf_ref.logfbank(wd)
+    assert np.array_equal(psf_ref.preemphasis(np.asarray(wd, dtype=np.float64)), pcm.astype(np.float64))
     live = ref_raw.std(axis=0) > 1e-9
-    assert feature_err(got[:, live], ref[:, live]) <= 5 * FEATURE_TOL
+    assert feature_err(got[:, live], ref[:, live]) <= FEATURE_TOL
+    # soundfile route (sf_flag=True): 1-D float64 in [-1, 1], pre-emphasis 0.97 applies
+    got = wav_util.compute_fbank_from_file(path, 200, sf_flag=True)
+    ref = psf_ref.compute_fbank_from_api(pcm.astype(np.float64) / 32768.0, 16000)
+    assert feature_err(got[:, live], ref[:, live]) <= FEATURE_TOL
 
 
 @pytest.mark.parametrize("fs,nfilt", [(8000, 40), (16000, 26), (20000, 200), (11025, 64)])

@@ -14,7 +14,7 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 pool = [bench.DeviceBatch(bench.make_batch(2000 + i, batch=batch), dev, torch) for i in range(3)]
-for mode in ("fbank", "fbank_raw", "asrt"):
+for mode in os.environ.get("ASRK_TIME_MODES", "fbank,fbank_raw,asrt").split(","):
     for it in range(3):
         db = pool[it % 3]
         features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, mode, out=db.feat)
