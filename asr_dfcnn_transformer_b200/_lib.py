@@ -18,6 +18,7 @@ DTYPE_I16, DTYPE_F32 = 0, 1
 LABELS_BY_LENGTH, LABELS_DROP_ZEROS = 0, 1
 PHASE_ALL = 0xffff
 CTC_SMALL_ONLY = 0x10000
+CTC_INPUT_PROB = 0x20000
 PHASE_SPEC_SETUP, PHASE_SPEC_MAIN, PHASE_SPEC_NORMALIZE = 1, 2, 4
 PHASE_CTC_PREP, PHASE_CTC_ROWS, PHASE_CTC_LATTICE, PHASE_CTC_GRAD, PHASE_CTC_COLLAPSE = 1, 2, 4, 8, 16
 PHASE_CTC_FUSED = 32
@@ -39,6 +40,8 @@ SIGNATURES = {
                                          _sz, _vp, _i]),
     "asrk_ctc_loss_grad_run_phases": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp,
                                            _vp, _ll, _ll, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _i]),
+    "asrk_ctc_batch_cost_run": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _vp, _vp,
+                                     _sz, _vp, _i]),
     "asrk_ctc_stage_logits_run": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _i, _i, _i, _vp]),
     "asrk_ctc_loss_sum_run": (_i, [_vp, _vp, _i, _vp, _vp]),
     "asrk_color_noise_workspace_bytes": (_sz, [_i, _ll]),

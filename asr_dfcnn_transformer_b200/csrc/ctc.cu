@@ -478,7 +478,7 @@ __device__ __forceinline__ float warp_max_redux(float v) {
 #else
 #define ASRK_TICK(i) do { } while (0)
 #endif
-template <int NV4>
+template <int NV4, bool PROB>
 __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ double s_fin;
@@ -557,13 +557,20 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         asm volatile("" : "+f"(xg));
         release_row(r.v);
         if (t + kRowWarps < T) issue_row(rb, xb + (size_t)(t + kRowWarps) * p.stride_t, V4, lane, keep, bar);
-        float m;
-        int am;
-        row_argmax(r, lane, m, am);
-        const float ssum = row_sumexp(r, m);
-        const float lse = m + __logf(ssum);
-        if (lane == 0) { slse[t] = lse; smax[t] = m; samax[t] = am; }
-        if (lane < W) slp[t * W + lane] = (xg - lse) * 1.4426950408889634f;   // log2 y_t(l'_j)
+        if (PROB) {
+            // the op's input is log(p + eps): y = (p + eps) / sum(p + eps), no exponentials; slse holds 1 / sum
+            const float ssum = row_sum_eps(r, V4, lane, p.eps);
+            if (lane == 0) { slse[t] = __fdividef(1.0f, ssum); smax[t] = 0.f; samax[t] = 0; }
+            if (lane < W) slp[t * W + lane] = lg2_fast(xg + p.eps) - lg2_fast(ssum);   // log2 y_t(l'_j)
+        } else {
+            float m;
+            int am;
+            row_argmax(r, lane, m, am);
+            const float ssum = row_sumexp(r, m);
+            const float lse = m + __logf(ssum);
+            if (lane == 0) { slse[t] = lse; smax[t] = m; samax[t] = am; }
+            if (lane < W) slp[t * W + lane] = (xg - lse) * 1.4426950408889634f;   // log2 y_t(l'_j)
+        }
     }
     __syncthreads();
     ASRK_TICK(1);
@@ -717,13 +724,39 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     const unsigned same = __match_any_sync(0xffffffffu, my_lab);
     const bool owner = (lane < L) && ((int)__ffs(same) - 1 == lane) && (my_lab != p.blank);
     const bool is_blank_lab = (lane < L) && (my_lab == p.blank);
-    if (warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, drop, bar);      // L2 hits: read a moment ago
+    if (!PROB && warp < T) issue_row(rb, xb + (size_t)warp * p.stride_t, V4, lane, drop, bar);   // L2 hits: read a moment ago
     for (int t = warp; t < p.T; t += kRowWarps) {
         float* g = p.grad + (size_t)t * p.gstride_t + (size_t)b * p.gstride_b;
         float4* g4 = reinterpret_cast<float4*>(g);
         if (t >= T) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int k = lane; k < V4; k += 32) stg_evict_first(g4 + k, z);
+            continue;
+        }
+        if (PROB) {
+            // dL/dp = dL/dx / (p + eps) with dL/dx = y - occupancy and y = (p + eps) / S:  scale / S for every
+            // class (the row is not read again), minus scale occupancy / (p + eps) = (scale / S) occupancy / y
+            // for the classes of the lattice
+            const float base = scale * slse[t];
+            const float4 bv = make_float4(base, base, base, base);
+            for (int k = lane; k < V4; k += 32) stg_evict_first(g4 + k, bv);
+            if (!fix) continue;
+            __syncwarp();
+            const float* al = sal + t * Ub;
+            const float* be = sbe + t * Ub;
+            const float Kt = sK[t];
+            float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;
+            if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);
+            if (owner) {
+                float o = 0.f;
+                for (unsigned mset = same; mset; mset &= mset - 1) {
+                    const int k = __ffs(mset) - 1;
+                    o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
+                }
+                g[my_lab] = base * (1.0f - __fdividef(o, ex2_fast(slp[t * W + 1 + lane])));
+            }
+            ob = warp_sum(ob);
+            if (lane == 0) g[p.blank] = base * (1.0f - __fdividef(ob, ex2_fast(slp[t * W])));
             continue;
         }
         const float nlse2 = -slse[t] * kLog2e;
@@ -928,6 +961,39 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
     const float lse = p.lse[bt];
     const float nlse2 = -lse * kLog2e;
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
+    if (p.prob) {
+        // gradient w.r.t. the probabilities (see fused_small_kernel): scale / S everywhere, lattice classes fixed
+        const float base = scale * __expf(-lse);
+        if constexpr (NV4 > 0) {
+            float4* g4 = reinterpret_cast<float4*>(g);
+            const float4 bv = make_float4(base, base, base, base);
+            for (int i = lane; i < (V >> 2); i += 32) stg_stream(g4 + i, bv);
+        } else {
+            for (int i = lane; i < V; i += 32) g[i] = base;
+        }
+        if (status != ASRK_ROW_OK) return;
+        __syncwarp();
+        const int L = p.eff_len[b];
+        const int U = 2 * p.Ls + 1;
+        const float* occ = p.occ + bt * (size_t)U;
+        const float* lpl = p.lpl + bt * (size_t)(p.Ls + 1);
+        const int* eff = p.eff_labels + (size_t)b * p.Ls;
+        const int* nxt = p.chain_next + (size_t)b * p.Ls;
+        const int* fst = p.chain_first + (size_t)b * p.Ls;
+        float ob = 0.f;
+        for (int j = lane; j <= L; j += 32) ob += occ[2 * j];
+        for (int j = lane; j < L; j += 32) {
+            if (eff[j] == p.blank) ob += occ[2 * j + 1];
+            else if (fst[j]) {
+                float o = 0.f;
+                for (int k = j; k >= 0; k = nxt[k]) o += occ[2 * k + 1];
+                g[eff[j]] = base * (1.0f - o / __expf(lpl[1 + j]));
+            }
+        }
+        ob = warp_sum(ob);
+        if (lane == 0) g[p.blank] = base * (1.0f - ob / __expf(lpl[0]));
+        return;
+    }
     if constexpr (NV4 > 0) {
         const float4* x4 = reinterpret_cast<const float4*>(x);
         float4* g4 = reinterpret_cast<float4*>(g);
@@ -1032,6 +1098,15 @@ __global__ void __launch_bounds__(128) collapse_kernel(Params p) {
     }
 }
 
+__global__ void fill_bad_rows_kernel(float* loss, int* row_status, int* token_len, float* nsl, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    loss[b] = __int_as_float(0x7fc00000);
+    row_status[b] = ASRK_ROW_BAD_LENGTH;
+    if (token_len) token_len[b] = 0;
+    if (nsl) nsl[b] = 0.f;
+}
+
 // [sum of the losses of the rows TF would accept, number of such rows] in float64, one
 // CTA, fixed order (reproducible): the operand of the path's only collective.
 __global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const int* row_status, int B, double* out2) {
@@ -1111,10 +1186,15 @@ static void launch_rows(const Params& p, int nv4, cudaStream_t stream) {
 static void launch_fused(const Params& p, int nv4, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (kSmallSmemFloats + (size_t)kRowWarps * p.V);
     switch (nv4) {
-#define ASRK_FUSED_CASE(N)                                                                              \
-    case N:                                                                                             \
-        cudaFuncSetAttribute(fused_small_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        fused_small_kernel<N><<<p.B, kRowWarps * 32, smem, stream>>>(p);                                 \
+#define ASRK_FUSED_CASE(N)                                                                                        \
+    case N:                                                                                                       \
+        if (p.prob) {                                                                                             \
+            cudaFuncSetAttribute(fused_small_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            fused_small_kernel<N, true><<<p.B, kRowWarps * 32, smem, stream>>>(p);                                \
+        } else {                                                                                                  \
+            cudaFuncSetAttribute(fused_small_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            fused_small_kernel<N, false><<<p.B, kRowWarps * 32, smem, stream>>>(p);                               \
+        }                                                                                                         \
         break;
         ASRK_FUSED_CASE(4)
         ASRK_FUSED_CASE(8)
@@ -1185,8 +1265,16 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
                                              size_t workspace_bytes, asrk_stream_t stream_, int phases) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (T < 0 || B < 0 || V < 1 || label_stride < 0) return ASRK_E_BADARG;
-    if (B == 0 || T == 0) return ASRK_OK;
+    if (B == 0) return ASRK_OK;
+    if (T == 0) {
+        // no frames at all: every row is rejected like an input_len outside [1, T] (nothing is left undefined)
+        if (!loss || !row_status) return ASRK_E_BADARG;
+        fill_bad_rows_kernel<<<(B + 255) / 256, 256, 0, stream>>>(loss, row_status, token_len, neg_sum_logits, B);
+        return launch_status();
+    }
     if (!logits || !labels || !input_len || !loss || !row_status || !workspace) return ASRK_E_BADARG;
+    const int prob = (phases & ASRK_CTC_INPUT_PROB) ? 1 : 0;
+    if (prob && tokens) return ASRK_E_BADARG;   // the greedy decode is defined on the op's input, not on p
     if (label_mode != ASRK_LABELS_BY_LENGTH && label_mode != ASRK_LABELS_DROP_ZEROS) return ASRK_E_BADARG;
     if (label_mode == ASRK_LABELS_BY_LENGTH && !label_len) return ASRK_E_BADARG;
     if (blank < 0 || blank >= V) return ASRK_E_BADARG;
@@ -1209,6 +1297,8 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     p.tokens = tokens; p.token_stride = token_stride; p.token_len = token_len;
     p.neg_sum_logits = neg_sum_logits; p.merge_repeated = 1;
     p.Ls = Ls;
+    p.prob = prob;
+    p.eps = 1e-7f;                                       // K.epsilon()
     bind_workspace(p, workspace, l);
 
     const int nv4 = pick_nv4(p, logits, stride_t, stride_b, grad, gstride_t, gstride_b);
@@ -1252,6 +1342,19 @@ extern "C" int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, l
                                          gstride_t, gstride_b, row_status, tokens, token_stride,
                                          token_len, neg_sum_logits, workspace, workspace_bytes, stream_,
                                          ASRK_PHASE_ALL);
+}
+
+extern "C" int asrk_ctc_batch_cost_run(const float* y_pred, long long stride_t, long long stride_b, int T, int B, int V,
+                                       const int* labels, int label_stride, const int* label_len,
+                                       const int* input_len, const float* grad_scale, float* loss, float* grad,
+                                       long long gstride_t, long long gstride_b, int* row_status, void* workspace,
+                                       size_t workspace_bytes, asrk_stream_t stream_, int flags) {
+    // K.ctc_batch_cost: blank = V - 1, labels masked by label_length, input = log(y_pred + 1e-7)
+    return asrk_ctc_loss_grad_run_phases(y_pred, stride_t, stride_b, T, B, V, labels, label_stride, label_len,
+                                         input_len, V - 1, ASRK_LABELS_BY_LENGTH, grad_scale, loss, grad,
+                                         gstride_t, gstride_b, row_status, nullptr, 0, nullptr, nullptr, workspace,
+                                         workspace_bytes, stream_,
+                                         ASRK_PHASE_ALL | ASRK_CTC_INPUT_PROB | (flags & ASRK_CTC_SMALL_ONLY));
 }
 
 extern "C" int asrk_ctc_greedy_decode_run(const float* logits, long long stride_t, long long stride_b,

@@ -380,8 +380,8 @@ __device__ __forceinline__ void team_bar(int team) {
 // main kernel
 // ---------------------------------------------------------------------------
 template <bool F32, int kTeams, bool kSepOut>
-__global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads)) __maxnreg__(kTeams == 3 ? 136 : 184)
-spectrogram_kernel(Params p) {
+// (registers are allocated per warp in units of 512: 480 threads cannot have more than 128 each)
+__global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spectrogram_kernel(Params p) {
     using C = Cfg<F32, kTeams, kSepOut>;
     constexpr int kPcmWords = C::kPcmWords;
     constexpr int kThreads = C::kThreads;

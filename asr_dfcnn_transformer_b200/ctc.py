@@ -55,7 +55,7 @@ def _i32(x, dev, torch):
 
 def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="by_length",
                   layout="tbv", grad_scale=None, want_grad=True, decode=False, grad_out=None,
-                  stream=None, phases=_lib.PHASE_ALL, outputs=None, bounds=None):
+                  stream=None, phases=_lib.PHASE_ALL, outputs=None, bounds=None, input_kind="logits"):
     """Raw op: one fused pass.  logits float32 CUDA tensor ``[T,B,V]`` ('tbv') or
     ``[B,T,V]`` ('btv'); labels int32 ``[B,Lmax]``.  Returns CtcResult of device
     tensors (no synchronisation, statuses are NOT checked here).
@@ -64,7 +64,11 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
     reference's loader builds both length vectors on the host, data_loader.py:132-148): a batch
     whose largest lattice fits the fused kernel is then ONE launch -- the three generic kernels
     that would otherwise be launched to find nothing to do are skipped.  Lengths given as host
-    arrays are bounded here; a row that breaks the promise gets row_status ROW_NOT_SMALL."""
+    arrays are bounded here; a row that breaks the promise gets row_status ROW_NOT_SMALL.
+
+    ``input_kind="prob"``: ``logits`` holds the softmax output p that Keras hands to ``K.ctc_batch_cost``
+    (cnn_ctc.py:149-152); the op's input ``log(p + 1e-7)`` is formed inside the kernel and ``grad`` is the
+    gradient w.r.t. p (no element-wise pass before or after the kernel)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     if logits.dtype != torch.float32 or not logits.is_cuda:
@@ -84,6 +88,12 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
     if bounds is not None and phases == _lib.PHASE_ALL and \
             L.asrk_ctc_fits_fused(max(int(bounds[0]), 0), max(int(bounds[1]), 0)):
         phases = phases | _lib.CTC_SMALL_ONLY
+    if input_kind == "prob":
+        if decode:
+            raise ValueError("the greedy decode is defined on the op's input, not on probabilities")
+        phases = phases | _lib.CTC_INPUT_PROB
+    elif input_kind != "logits":
+        raise ValueError("input_kind must be 'logits' or 'prob'")
     input_len = _i32(input_len, dev, torch)
     label_len = _i32(label_len, dev, torch) if label_len is not None else None
     mode = _lib.LABELS_BY_LENGTH if label_mode == "by_length" else _lib.LABELS_DROP_ZEROS
@@ -168,14 +178,25 @@ def _make_fn():
     torch = _lib.require_cuda()
 
     class _CTCLoss(torch.autograd.Function):
+        """loss = CTC(logits); the gradient w.r.t. the logits comes out of the same kernel pass, already
+        multiplied by ``upstream`` (what the caller states the gradient of the final objective w.r.t. every
+        loss[b] will be: 1 for ``.sum()``, 1/B for ``.mean()``; None = 1).  backward returns that tensor as it
+        is when autograd's upstream gradient is the stated one -- a broadcast scalar is read back from the
+        device (4 bytes, no kernel) to check -- and only otherwise pays an element-wise pass."""
+
         @staticmethod
-        def forward(ctx, logits, labels, label_len, input_len, blank, label_mode, layout, check):
+        def forward(ctx, logits, labels, label_len, input_len, blank, label_mode, layout, check, kind, upstream):
             need = logits.requires_grad
+            B = logits.shape[1] if layout == "tbv" else logits.shape[0]
+            gs = None
+            if upstream is not None and need:
+                gs = torch.full((B,), float(upstream), dtype=torch.float32, device=logits.device)
             r = ctc_loss_grad(logits.detach(), labels, label_len, input_len, blank, label_mode,
-                              layout, want_grad=need)
+                              layout, want_grad=need, grad_scale=gs, input_kind=kind)
             if check:
                 _raise_on_status(r.row_status)
             ctx.layout = layout
+            ctx.upstream = 1.0 if upstream is None else float(upstream)
             if need:
                 ctx.save_for_backward(r.grad)
             return r.loss
@@ -183,11 +204,14 @@ def _make_fn():
         @staticmethod
         def backward(ctx, go):
             (g,) = ctx.saved_tensors
-            if ctx.layout == "tbv":
-                gi = g * go.view(1, -1, 1)
+            go = go.reshape(-1)
+            if go.numel() == 1 or go.stride(0) == 0:
+                c = float(go[0].item()) / ctx.upstream      # broadcast upstream gradient (.sum(), .mean())
+                gi = g if c == 1.0 else g * c
             else:
-                gi = g * go.view(-1, 1, 1)
-            return gi, None, None, None, None, None, None, None
+                w = go / ctx.upstream
+                gi = g * (w.view(1, -1, 1) if ctx.layout == "tbv" else w.view(-1, 1, 1))
+            return gi, None, None, None, None, None, None, None, None, None
 
     return _CTCLoss
 
@@ -208,20 +232,32 @@ def dense_to_sparse(target):
 
 
 def ctc_loss_v2(labels, logits, label_length, logit_length, logits_time_major=True, blank_index=None,
-                check=True):
-    """tf.nn.ctc_loss_v2 (acoustic_model2.py:79-80).  Returns loss ``[B]``."""
+                check=True, upstream=None):
+    """tf.nn.ctc_loss_v2 (acoustic_model2.py:79-80).  Returns loss ``[B]``.  ``blank_index=None`` follows
+    TensorFlow: 0 for dense labels, an error for sparse labels (the reference passes V-1 explicitly).
+    ``upstream``: see ``ctc_batch_cost``."""
     layout = "tbv" if logits_time_major else "btv"
     if isinstance(labels, SparseLabels):
-        return _fn().apply(logits, labels.dense, None, logit_length, blank_index, "drop_zeros", layout, check)
-    return _fn().apply(logits, labels, label_length, logit_length, blank_index, "by_length", layout, check)
+        if blank_index is None:
+            raise ValueError("blank_index must be given when using SparseTensor labels.")
+        return _fn().apply(logits, labels.dense, None, logit_length, int(blank_index), "drop_zeros", layout, check,
+                           "logits", upstream)
+    if blank_index is None:
+        blank_index = 0
+    V = logits.shape[2]
+    if blank_index < 0:
+        blank_index += V
+    return _fn().apply(logits, labels, label_length, logit_length, int(blank_index), "by_length", layout, check,
+                       "logits", upstream)
 
 
-def ctc_batch_cost(y_true, y_pred, input_length, label_length, check=True):
-    """Keras K.ctc_batch_cost (cnn_ctc.py:149-152): ``y_pred`` softmax output
-    ``[B,T,V]``; returns ``[B,1]``."""
-    torch = _lib.require_cuda()
-    x = torch.log(y_pred + 1e-7)     # keras: log(transpose(y_pred) + epsilon); the transpose is a stride swap
-    loss = _fn().apply(x, y_true, label_length, input_length, None, "by_length", "btv", check)
+def ctc_batch_cost(y_true, y_pred, input_length, label_length, check=True, upstream=None):
+    """Keras K.ctc_batch_cost (cnn_ctc.py:149-152): ``y_pred`` softmax output ``[B,T,V]``; returns ``[B,1]``.
+    ONE kernel: ``log(y_pred + 1e-7)`` is formed when a row is loaded (the transpose is a stride swap) and the
+    gradient is written w.r.t. ``y_pred``.  ``upstream`` states the gradient the caller's objective will send
+    back into every loss entry (1 for ``.sum()`` -- the default --, ``1/B`` for Keras' batch mean): the kernel
+    scales by it and ``backward`` hands the tensor on without another pass."""
+    loss = _fn().apply(y_pred, y_true, label_length, input_length, None, "by_length", "btv", check, "prob", upstream)
     return loss.unsqueeze(1)
 
 

@@ -144,6 +144,13 @@ size_t asrk_ctc_workspace_bytes(int T, int B, int label_stride);
  * launched at all; a row that breaks the promise is reported as ASRK_ROW_NOT_SMALL. */
 int asrk_ctc_fits_fused(int max_input_len, int max_label_len);
 #define ASRK_CTC_SMALL_ONLY 0x10000
+/* OR into `phases` of asrk_ctc_loss_grad_run_phases: `logits` holds PROBABILITIES p (the softmax output the
+ * Keras model hands to K.ctc_batch_cost, lm_and_am/model/cnn_ctc.py:149-152); the op's input is formed on
+ * load as log(p + 1e-7) (Keras' epsilon), and `grad` receives the gradient w.r.t. p:
+ *   grad[t,b,v] = grad_scale[b] * (y[v] - occupancy[v]) / (p[v] + 1e-7),   y = (p + 1e-7) / sum_v (p + 1e-7)
+ * -- the three element-wise passes of the Keras glue (log, its backward, the upstream scale) are inside the
+ * kernel.  tokens must be NULL (the greedy decode is defined on the op's input: asrk_ctc_greedy_decode_run). */
+#define ASRK_CTC_INPUT_PROB 0x20000
 
 int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long stride_b,
                            int T, int B, int V,
@@ -159,6 +166,17 @@ int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long st
                            int* token_len,                      /* device int32 [B] (with tokens) */
                            float* neg_sum_logits,               /* device float32 [B] or NULL     */
                            void* workspace, size_t workspace_bytes, asrk_stream_t stream);
+
+/* K.ctc_batch_cost(y_true, y_pred, input_length, label_length) (lm_and_am/model/cnn_ctc.py:149-152;
+ * cnn_rnn_ctc.py:81-84) in one call: y_pred = softmax output, element (t,b,v) at t*stride_t + b*stride_b + v
+ * (Keras' [B,T,V]: stride_t = V, stride_b = T*V), blank = V-1, labels masked by label_len, the op's input
+ * log(y_pred + 1e-7) formed on load, loss[b] = -log p, grad = d(sum_b grad_scale[b] loss[b]) / d y_pred (or NULL).
+ * flags: 0 or ASRK_CTC_SMALL_ONLY. */
+int asrk_ctc_batch_cost_run(const float* y_pred, long long stride_t, long long stride_b, int T, int B, int V,
+                            const int* labels, int label_stride, const int* label_len, const int* input_len,
+                            const float* grad_scale, float* loss, float* grad, long long gstride_t,
+                            long long gstride_b, int* row_status, void* workspace, size_t workspace_bytes,
+                            asrk_stream_t stream, int flags);
 
 /* Host -> device staging of the logits without their padding.  `src` is the caller's logits in pinned
  * (page-locked, device-mapped) HOST memory, `dst` the device tensor the CTC entry points will read;

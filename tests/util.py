@@ -50,3 +50,34 @@ def zscore_feature_err(got, ref_z, ref_raw):
     cond = np.maximum(1.0, 0.05 / np.maximum(sd, 1e-300))
     cond[sd < 10 * np.finfo(np.float64).eps] = 1.0     # constant columns: both sides give 0
     return float(np.max(np.abs(got - ref_z) / np.maximum(np.abs(ref_z), 1.0) / cond[None, :]))
+
+
+def zscore_err_report(got, ref_z, ref_raw):
+    """(un-widened error, widened error, number of columns that needed the 0.05/std allowance, i.e. whose
+    un-widened error exceeds FEATURE_TOL) for one utterance's z-scored features."""
+    got = np.asarray(got, dtype=np.float64)
+    ref_z = np.asarray(ref_z, dtype=np.float64)
+    if got.size == 0:
+        return 0.0, 0.0, 0
+    e = np.abs(got - ref_z) / np.maximum(np.abs(ref_z), 1.0)
+    col = e.max(axis=0)
+    sd = np.asarray(ref_raw, dtype=np.float64).std(axis=0)
+    cond = np.maximum(1.0, 0.05 / np.maximum(sd, 1e-300))
+    cond[sd < 10 * np.finfo(np.float64).eps] = 1.0
+    return float(col.max()), float((col / cond).max()), int((col > FEATURE_TOL).sum())
+
+
+def record_parity(key, values):
+    """Merge one entry into gpurun_out/parity.json (worst errors per config)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "parity.json")
+    try:
+        data = json.load(open(path))
+    except Exception:
+        data = {}
+    data[key] = values
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
