@@ -28,6 +28,7 @@ _vp, _i, _ll, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_s
 SIGNATURES = {
     "asrk_version": (_i, []),
     "asrk_error_string": (ctypes.c_char_p, [_i]),
+    "asrk_launch_count": (ctypes.c_ulonglong, []),
     "asrk_spectrogram_workspace_bytes": (_sz, [_i, _ll]),
     "asrk_spectrogram_run": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _sz,
                                   _vp]),

@@ -1,5 +1,14 @@
 // Version and error strings of the asrk C ABI (include/asrk.h).
+#include <atomic>
+
 #include "asrk_common.cuh"
+
+namespace asrk {
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace asrk
+
+extern "C" unsigned long long asrk_launch_count(void) { return asrk::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int asrk_version(void) { return 100; }   // 0.1.0
 

@@ -131,6 +131,11 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// kernels launched by the library since it was loaded (asrk_launch_count): a measured count for the
+// harnesses, not a claim.  One relaxed atomic increment on the host per launch.
+extern "C" unsigned long long asrk_launch_count(void);
+void note_launch();
+
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? ASRK_OK : ASRK_E_CUDA;

@@ -231,8 +231,8 @@ static void run_fft(cd* buf, const cd* tw, int L, int batch, cudaStream_t stream
     if (L < kTileLog2) {
         const dim3 gH((unsigned)((M / 2 + 255) / 256), batch);
         for (int s = 0; s < L; ++s) {
-            if (INVERSE) dit_inv_stage_kernel<<<gH, 256, 0, stream>>>(buf, tw, L, s);
-            else dif_stage_kernel<<<gH, 256, 0, stream>>>(buf, tw, L, s);
+            if (INVERSE) dit_inv_stage_kernel<<<gH, 256, 0, stream>>>(buf, tw, L, s), asrk::note_launch();
+            else dif_stage_kernel<<<gH, 256, 0, stream>>>(buf, tw, L, s), asrk::note_launch();
         }
         return;
     }
@@ -249,9 +249,9 @@ static void run_fft(cd* buf, const cd* tw, int L, int batch, cudaStream_t stream
     }
     starts[n] = top; counts[n] = kTileLog2; ++n;
     if (!INVERSE) {
-        for (int g = 0; g < n; ++g) blocked_stages_kernel<false><<<grid, 256, smem, stream>>>(buf, tw, L, starts[g], counts[g]);
+        for (int g = 0; g < n; ++g) blocked_stages_kernel<false><<<grid, 256, smem, stream>>>(buf, tw, L, starts[g], counts[g]), asrk::note_launch();
     } else {
-        for (int g = n - 1; g >= 0; --g) blocked_stages_kernel<true><<<grid, 256, smem, stream>>>(buf, tw, L, starts[g], counts[g]);
+        for (int g = n - 1; g >= 0; --g) blocked_stages_kernel<true><<<grid, 256, smem, stream>>>(buf, tw, L, starts[g], counts[g]), asrk::note_launch();
     }
 }
 
@@ -402,20 +402,20 @@ extern "C" int asrk_color_noise_run(const double* normals, const long long* offs
     p.batch = batch; p.log2M = log2M;
     const long long M = 1LL << log2M;
     const dim3 gM((unsigned)((M + 255) / 256), batch), gH((unsigned)((M / 2 + 255) / 256), batch);
-    twiddle_kernel<<<(unsigned)((M / 2 + 255) / 256), 256, 0, stream>>>(p.tw, log2M);
-    init_kernel<<<gM, 256, 0, stream>>>(p);
+    twiddle_kernel<<<(unsigned)((M / 2 + 255) / 256), 256, 0, stream>>>(p.tw, log2M), asrk::note_launch();
+    init_kernel<<<gM, 256, 0, stream>>>(p), asrk::note_launch();
     run_fft<false>(p.A, p.tw, log2M, batch, stream);
     run_fft<false>(p.Bc, p.tw, log2M, batch, stream);
-    pointwise_kernel<<<gM, 256, 0, stream>>>(p.A, p.Bc, log2M);
+    pointwise_kernel<<<gM, 256, 0, stream>>>(p.A, p.Bc, log2M), asrk::note_launch();
     run_fft<true>(p.A, p.tw, log2M, batch, stream);
-    shape_kernel<<<gM, 256, 0, stream>>>(p);
-    restage_kernel<<<gM, 256, 0, stream>>>(p);
+    shape_kernel<<<gM, 256, 0, stream>>>(p), asrk::note_launch();
+    restage_kernel<<<gM, 256, 0, stream>>>(p), asrk::note_launch();
     run_fft<false>(p.A, p.tw, log2M, batch, stream);
-    pointwise_kernel<<<gM, 256, 0, stream>>>(p.A, p.Bc, log2M);
+    pointwise_kernel<<<gM, 256, 0, stream>>>(p.A, p.Bc, log2M), asrk::note_launch();
     run_fft<true>(p.A, p.tw, log2M, batch, stream);
     double* yreal = p.y;     // the staging buffer is free again: [B][M] doubles fit in its first half
-    finish_real_kernel<<<gM, 256, 0, stream>>>(p, yreal);
-    mean_max_kernel<<<batch, 1024, 0, stream>>>(p, yreal);
-    scale_out_kernel<<<gM, 256, 0, stream>>>(p, yreal);
+    finish_real_kernel<<<gM, 256, 0, stream>>>(p, yreal), asrk::note_launch();
+    mean_max_kernel<<<batch, 1024, 0, stream>>>(p, yreal), asrk::note_launch();
+    scale_out_kernel<<<gM, 256, 0, stream>>>(p, yreal), asrk::note_launch();
     return launch_status();
 }

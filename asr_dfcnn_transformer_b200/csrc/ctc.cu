@@ -1175,11 +1175,11 @@ static void launch_rows(const Params& p, int nv4, cudaStream_t stream) {
     const long long cap = (long long)sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     switch (nv4) {
-        case 4: rows_kernel<4, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        case 8: rows_kernel<8, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        case 12: rows_kernel<12, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        case 16: rows_kernel<16, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        default: rows_kernel<0, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 4: rows_kernel<4, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        case 8: rows_kernel<8, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        case 12: rows_kernel<12, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        case 16: rows_kernel<16, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        default: rows_kernel<0, WANT_LSE><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
     }
 }
 
@@ -1190,10 +1190,10 @@ static void launch_fused(const Params& p, int nv4, cudaStream_t stream) {
     case N:                                                                                                       \
         if (p.prob) {                                                                                             \
             cudaFuncSetAttribute(fused_small_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            fused_small_kernel<N, true><<<p.B, kRowWarps * 32, smem, stream>>>(p);                                \
+            fused_small_kernel<N, true><<<p.B, kRowWarps * 32, smem, stream>>>(p), asrk::note_launch();                                \
         } else {                                                                                                  \
             cudaFuncSetAttribute(fused_small_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            fused_small_kernel<N, false><<<p.B, kRowWarps * 32, smem, stream>>>(p);                               \
+            fused_small_kernel<N, false><<<p.B, kRowWarps * 32, smem, stream>>>(p), asrk::note_launch();                               \
         }                                                                                                         \
         break;
         ASRK_FUSED_CASE(4)
@@ -1211,11 +1211,11 @@ static void launch_grad(const Params& p, int nv4, cudaStream_t stream) {
     const long long cap = (long long)sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     switch (nv4) {
-        case 4: grad_kernel<4><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        case 8: grad_kernel<8><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        case 12: grad_kernel<12><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        case 16: grad_kernel<16><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
-        default: grad_kernel<0><<<grid, kRowWarps * 32, 0, stream>>>(p); break;
+        case 4: grad_kernel<4><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        case 8: grad_kernel<8><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        case 12: grad_kernel<12><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        case 16: grad_kernel<16><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
+        default: grad_kernel<0><<<grid, kRowWarps * 32, 0, stream>>>(p), asrk::note_launch(); break;
     }
 }
 
@@ -1269,7 +1269,7 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (T == 0) {
         // no frames at all: every row is rejected like an input_len outside [1, T] (nothing is left undefined)
         if (!loss || !row_status) return ASRK_E_BADARG;
-        fill_bad_rows_kernel<<<(B + 255) / 256, 256, 0, stream>>>(loss, row_status, token_len, neg_sum_logits, B);
+        fill_bad_rows_kernel<<<(B + 255) / 256, 256, 0, stream>>>(loss, row_status, token_len, neg_sum_logits, B), asrk::note_launch();
         return launch_status();
     }
     if (!logits || !labels || !input_len || !loss || !row_status || !workspace) return ASRK_E_BADARG;
@@ -1313,7 +1313,7 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
             return ASRK_E_CUDA;
         if (!p.prep_fused) {
             const int pt = ((label_stride > 0 ? label_stride : 1) + 31) / 32 * 32;
-            prep_kernel<<<B, pt, sizeof(int) * (Ls + 40), stream>>>(p);
+            prep_kernel<<<B, pt, sizeof(int) * (Ls + 40), stream>>>(p), asrk::note_launch();
         }
     }
     // utterances with a small lattice: one fused CTA each; the row-parallel kernels
@@ -1323,9 +1323,9 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
     if (phases & ASRK_PHASE_CTC_LATTICE)
-        lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p);
+        lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p), asrk::note_launch();
     if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
-    if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
+    if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p), asrk::note_launch();
     return launch_status();
 }
 
@@ -1383,14 +1383,14 @@ extern "C" int asrk_ctc_greedy_decode_run(const float* logits, long long stride_
         const int nv4 = pick_nv4(p, logits, stride_t, stride_b, nullptr, 0, 0);
         launch_rows<false>(p, nv4, stream);
     }
-    collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p);
+    collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p), asrk::note_launch();
     return launch_status();
 }
 
 extern "C" int asrk_ctc_loss_sum_run(const float* loss, const int* row_status, int B, double* out2,
                                      asrk_stream_t stream_) {
     if (B < 0 || !out2 || (B > 0 && !loss)) return ASRK_E_BADARG;
-    loss_sum_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(loss, row_status, B, out2);
+    loss_sum_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(loss, row_status, B, out2), asrk::note_launch();
     return launch_status();
 }
 
@@ -1403,6 +1403,6 @@ extern "C" int asrk_ctc_stage_logits_run(const float* src, long long src_stride_
     if (V % 4 != 0 || (src_stride_t % 4) || (src_stride_b % 4) || (dst_stride_t % 4) || (dst_stride_b % 4)) return ASRK_E_SHAPE;
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return ASRK_E_ALIGN;
     stage_logits_kernel<<<sm_count() * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-        src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, T, B, V);
+        src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, T, B, V), asrk::note_launch();
     return launch_status();
 }

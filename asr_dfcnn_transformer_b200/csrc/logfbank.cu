@@ -268,7 +268,7 @@ extern "C" int asrk_logfbank_run(const double* samples, const long long* sample_
     long long blocks = (total_frames + 2 * lfb::kWarps - 1) / (2 * lfb::kWarps);
     const long long cap = (long long)sm_count();
     if (blocks > cap) blocks = cap;
-    lfb::logfbank_kernel<<<(unsigned)blocks, lfb::kWarps * 32, smem, stream>>>(p);
-    if (normalise) lfb::zscore_kernel<<<batch, 1024, 0, stream>>>(p);
+    lfb::logfbank_kernel<<<(unsigned)blocks, lfb::kWarps * 32, smem, stream>>>(p), asrk::note_launch();
+    if (normalise) lfb::zscore_kernel<<<batch, 1024, 0, stream>>>(p), asrk::note_launch();
     return launch_status();
 }

@@ -149,6 +149,6 @@ extern "C" int asrk_snr2k_run(const float* signal, const float* noise, const lon
     const size_t smem = sizeof(float) * 2 * kHeap;
     cudaFuncSetAttribute(snr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     snr2k_kernel<<<batch, kThreads, smem, stream>>>(signal, noise, sample_offsets, sample_counts,
-                                                       snr_db, gain_out);
+                                                       snr_db, gain_out), asrk::note_launch();
     return asrk::launch_status();
 }

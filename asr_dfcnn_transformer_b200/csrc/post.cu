@@ -116,7 +116,7 @@ extern "C" int asrk_lfr_run(const float* in, const long long* in_offsets, float*
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     post::lfr_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-        in, in_offsets, out, out_offsets, batch, dim, m, n);
+        in, in_offsets, out, out_offsets, batch, dim, m, n), asrk::note_launch();
     return launch_status();
 }
 
@@ -128,6 +128,6 @@ extern "C" int asrk_edit_distance_run(const int* hyp, int hyp_stride, const int*
     if (!hyp_len || !truth_len || !out || (hyp_stride > 0 && !hyp) || (truth_stride > 0 && !truth)) return ASRK_E_BADARG;
     if (truth_stride > 64) return ASRK_E_SHAPE;          // two truth positions per lane (data_loader.py: 64 labels)
     post::edit_distance_kernel<<<(batch + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-        hyp, hyp_stride, hyp_len, truth, truth_stride, truth_len, batch, normalize, out);
+        hyp, hyp_stride, hyp_len, truth, truth_stride, truth_len, batch, normalize, out), asrk::note_launch();
     return launch_status();
 }

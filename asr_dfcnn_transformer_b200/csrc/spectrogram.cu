@@ -28,18 +28,19 @@
 //     counter (in utterance order) and stages the PCM of a 16-frame sub-tile with
 //     16-byte cp.async behind the previous sub-tile's second pass (zero-filled past the
 //     end; the noise mix fl32(s + fl32(K n)) is applied on the way in).
-//   * z-score INSIDE the kernel: per-bin sums of every unit are accumulated during the
-//     copy-out (fp32, shifted by the unit's first row so that nothing cancels; un-shifted
-//     in fp64, fixed order: reproducible, no float atomics).  The team that completes an
-//     utterance (release fence one unit late + per-utterance counter: the fence then has
-//     nothing to wait for) turns the unit sums into mean / 1/std and queues the
-//     utterance's units.  Every team takes tickets from that queue and, next to each of
-//     its own sub-tiles, normalises ONE 16-row chunk of a finished utterance: the rows
-//     come in through shared memory as one TMA bulk copy issued a pass ahead (L2 hits:
-//     written microseconds ago), are normalised by the copy-out lanes and go back as one
-//     bulk store.  The z-score work is thereby spread over all warps and schedulers (a
-//     dedicated z-score warp per CTA could not keep up: profiles/r2_spectrogram.md), the
-//     raw rows never make a second HBM round trip and no kernel trails the transform.
+//   * z-score: per-bin sums of every unit are accumulated during the copy-out (fp32,
+//     shifted by the unit's first row so that nothing cancels; un-shifted in fp64, fixed
+//     order: reproducible, no float atomics).  The team that completes an utterance
+//     (release fence one unit late + per-utterance counter: the fence then has nothing to
+//     wait for) turns the unit sums into mean / 1/std inside the kernel; one streaming
+//     kernel with the whole chip's memory parallelism normalises in place behind it
+//     (newest utterances first: their rows are still in L2) and runs next to the CTC
+//     kernel.  Two ways of normalising INSIDE the transform kernel were built and measured
+//     this round (a dedicated z-score warp per CTA fed by TMA bulk copies; one 16-row
+//     chunk per team and sub-tile, also through TMA) -- both parity-green, both slower
+//     than the trailing kernel because the transform is latency bound and every
+//     instruction added to its warps costs more than the HBM round trip it saves
+//     (profiles/r2_spectrogram.md).
 #include <math.h>
 #include <stdlib.h>
 
@@ -102,16 +103,15 @@ struct Params {
     int zscore_in_kernel;
     float* out;
     // workspace
-    int* counters;           // [0] next unit, [1] queue tail, [2] queue head   (zeroed per launch)
+    int* counters;           // [0] next unit                                   (zeroed per launch)
     int* done;               // [B] published units per utterance               (zeroed per launch)
-    unsigned long long* queue;   // [units] packed (valid | utterance | rows | first row) in completion order, 0 = empty
     int* tile_off_g;         // [B + 1] first unit of every utterance (written by CTA 0)
     double2* partials;       // [units][200]: per-unit column sums (sum y, sum y^2)
     float* stats;            // [B][3][200]: mean (hi, lo), 1/std
 };
 
 struct WsLayout {
-    size_t counters, done, queue, zero_bytes, tile_off, gains, stats, partials, total;
+    size_t counters, done, zero_bytes, tile_off, gains, stats, partials, total;
 };
 
 static size_t max_units(int batch, long long total_frames) {
@@ -121,10 +121,9 @@ static size_t max_units(int batch, long long total_frames) {
 static WsLayout ws_layout(int batch, long long total_frames) {
     WsLayout l;
     size_t o = 0;
-    // counters | done | queue are contiguous: one memset per launch
+    // counters | done are contiguous: one memset per launch
     l.counters = o;  o = align_up(o + sizeof(int) * 4, 256);
     l.done = o;      o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
-    l.queue = o;     o = align_up(o + sizeof(unsigned long long) * max_units(batch, total_frames), 256);
     l.zero_bytes = o;
     l.tile_off = o;  o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
     l.gains = o;     o = align_up(o + sizeof(float) * (size_t)batch, 256);
@@ -174,29 +173,6 @@ __device__ __forceinline__ void stg4_hint(float* p, float4 v, uint64_t policy) {
                  "f"(v.z), "f"(v.w), "l"(policy)
                  : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// queue entry of one finished unit: bit 63 valid | utterance (16 bits) | rows 1..32 (6 bits) | first output row (40 bits)
-__device__ __forceinline__ unsigned long long pack_entry(int b, int rows, long long grow) {
-    return (1ull << 63) | ((unsigned long long)b << 46) | ((unsigned long long)rows << 40) | (unsigned long long)grow;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// shared -> global bulk store (TMA), tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // Synchronous staging of the PCM of one sub-tile (unaligned utterances, and the noise mix:
 // fl32(signal + fl32(K * noise)) is formed on the way in).
 template <bool F32>
@@ -347,29 +323,11 @@ struct Cfg {
     static constexpr int kPcmWords = kSubHopRows * (F32 ? kHopWordsF32 : kHopWordsI16);
     static constexpr int kExchBytes = 200 * kSub * 16;                       // 51 200
     static constexpr int kOutBytes = kSepOut ? kSub * kOutStride * 4 : 0;    // 13 056
-    // one z-score chunk buffer per team; the float32 (noise-mix) staging leaves no room for it next to
-    // three exchange buffers: that path z-scores with the trailing kernels
-    static constexpr bool kZ = !(F32 && kTeams == 3);
-    static constexpr int kTeamBytes = kExchBytes + kPcmWords * 4 + kOutBytes + (kZ ? kZBytes : 0);
+    static constexpr int kTeamBytes = kExchBytes + kPcmWords * 4 + kOutBytes;
     static constexpr int kThreads = kTeams * kTeamThreads;
     static constexpr size_t smem_bytes() {
         return (size_t)(200 * 32 + 3200 + 3200) + sizeof(int) * (kMaxBatch + 1) + (size_t)kTeams * kTeamBytes + 16;
     }
-};
-
-// z-score state of one team (shared memory; written by the team's first thread only)
-struct ZState {
-    unsigned long long ent;   // polled queue entry of ticket `tkt` (0: not there yet)
-    long long cur_row;        // next output row of the unit being cut into chunks
-    long long grow;           // first output row of the chunk in the buffer
-    int tkt;                  // ticket held (-1: none)
-    int exhausted;            // every ticket has been handed out
-    int cur_left;             // rows left in the unit being cut
-    int cur_b;
-    int loaded;               // 1: a chunk is in the buffer (bulk load issued), waiting to be normalised / stored
-    int rows, b;              // ... its rows and utterance
-    int nproc;                // chunks processed so far (phase parity of the buffer's mbarrier)
-    int finished;             // drain: nothing left
 };
 
 __device__ __forceinline__ void team_bar(int team) {
@@ -394,8 +352,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     unsigned char* team_base = reinterpret_cast<unsigned char*>(tile_off + kMaxBatch + 1);
     __shared__ Meta meta[kTeams][2];
     __shared__ int s_fin[kTeams];
-    __shared__ ZState s_z[kTeams];
-    __shared__ uint64_t s_zbar[kTeams];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -407,13 +363,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
         tabW[4 * m + 2 + e] = -kMagic * w;
     }
     for (int i = tid; i < 800; i += kThreads) reinterpret_cast<double*>(tabTall)[i] = g_tab[400 + i];
-    if (tid < kTeams) {
-        mbar_init(s_zbar + tid, 1);
-        ZState& z = s_z[tid];
-        z.ent = 0; z.cur_row = 0; z.grow = 0; z.tkt = -1; z.exhausted = 0; z.cur_left = 0; z.cur_b = 0;
-        z.loaded = 0; z.rows = 0; z.b = 0; z.nproc = 0; z.finished = 0;
-    }
-    if (tid == 0) mbar_fence_init();
     if (warp == 0) {
         // exclusive scan of ceil(n_frames / kUnit) over the utterances
         int carry = 0;
@@ -439,7 +388,7 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     __syncthreads();
     const int total_tiles = tile_off[p.batch];
     const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
-    const bool zin = C::kZ && want_stats && p.zscore_in_kernel;
+    const bool zin = want_stats && p.zscore_in_kernel;     // statistics finished inside the kernel
     if (blockIdx.x == 0 && want_stats)
         for (int i = tid; i <= p.batch; i += kThreads) p.tile_off_g[i] = tile_off[i];
 
@@ -449,9 +398,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     uint32_t* pcm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(exch) + C::kExchBytes);
     // out tile [16][204]: its own buffer, or aliased onto the exchange (then two more team barriers guard it)
     float* ot = kSepOut ? reinterpret_cast<float*>(pcm + kPcmWords) : reinterpret_cast<float*>(exch);
-    float* zbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(pcm + kPcmWords) + C::kOutBytes);   // [16][200]
-    ZState& zs = s_z[team];
-    uint64_t* zbar = s_zbar + team;
 
     // lane -> (frame of the sub-tile, role): the two half-warps of warp q own roles q, q + 5
     const int f = lane & 15;
@@ -490,7 +436,7 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     };
     // publication of a finished unit, one unit late (the fence then finds every store of the unit
     // acknowledged): the team's first thread counts the unit on its utterance; whoever completes the
-    // utterance makes its statistics (whole team) and queues its units for the z-score
+    // utterance makes its statistics (whole team)
     int pub_b = -1, pub_nt = 0;      // (thread 0) utterance / unit count of the unit to publish
     auto publish_count = [&]() {     // thread 0, after a team barrier that follows the unit's last store
         if (tt == 0) {
@@ -504,73 +450,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
             s_fin[team] = fin;
         }
     };
-    auto publish_queue = [&](int fin) {   // thread 0, after a team barrier that follows finalize_stats
-        if (tt == 0 && fin >= 0) {
-            const long long fo = p.frame_offsets[fin];
-            const long long nfr = p.frame_offsets[fin + 1] - fo;
-            const long long row0 = p.out_row_offsets ? p.out_row_offsets[fin] : fo;
-            __threadfence();
-            const int nt = tile_off[fin + 1] - tile_off[fin];
-            const int slot = atomicAdd(p.counters + 1, nt);
-            for (int c = 0; c < nt; ++c) {
-                const long long left = nfr - (long long)c * kUnit;
-                st_relaxed(p.queue + slot + c, pack_entry(fin, left < kUnit ? (int)left : kUnit, row0 + (long long)c * kUnit));
-            }
-        }
-    };
-    // ---- z-score steps (all no-ops unless zin) ----------------------------------------------------
-    // thread 0, right after a "P" barrier: the chunk normalised during the previous copy-out goes home
-    auto z_store = [&]() {
-        if (zin && tt == 0 && zs.loaded) {
-            tma_store_1d(p.out + (size_t)zs.grow * kBins, zbuf, (unsigned)zs.rows * kBins * 4);
-            tma_store_commit();
-            zs.loaded = 0;
-            zs.nproc = zs.nproc + 1;
-        }
-    };
-    // thread 0: adopt a polled entry as the unit to cut ...
-    auto z_adopt = [&]() {
-        if (zs.cur_left == 0 && zs.ent != 0) {
-            const unsigned long long e = zs.ent;
-            zs.cur_row = (long long)(e & ((1ull << 40) - 1));
-            zs.cur_left = (int)((e >> 40) & 63);
-            zs.cur_b = (int)((e >> 46) & 0xffff);
-            zs.ent = 0;
-            zs.tkt = -1;
-        }
-    };
-    // ... and start the bulk load of its next chunk into the (free) buffer
-    auto z_issue = [&]() {
-        if (!zs.loaded && zs.cur_left > 0) {
-            const int rows = zs.cur_left < kZRows ? zs.cur_left : kZRows;
-            tma_store_wait_read();               // the bulk store that last read the buffer has drained it
-            fence_proxy_async();                 // rows written through the generic proxy -> async-proxy read
-            tma_load_1d(zbuf, p.out + (size_t)zs.cur_row * kBins, (unsigned)rows * kBins * 4, zbar, l2_policy_evict_first());
-            zs.grow = zs.cur_row;
-            zs.rows = rows;
-            zs.b = zs.cur_b;
-            zs.cur_row += rows;
-            zs.cur_left -= rows;
-            zs.loaded = 1;
-        }
-    };
-    // all threads, in the copy-out phase: normalise the chunk in the buffer (lane = (4 bins, row phase))
-    auto z_process = [&](const float4& mh, const float4& ml, const float4& iv, int zrows, unsigned zpar) {
-        mbar_wait(zbar, zpar);
-        if (co_act) {
-            float4* rows = reinterpret_cast<float4*>(zbuf) + co_c4;
-            for (int row = co_ph; row < zrows; row += 3) {
-                float4 a = rows[row * 50];
-                a.x = ((a.x - mh.x) - ml.x) * iv.x;
-                a.y = ((a.y - mh.y) - ml.y) * iv.y;
-                a.z = ((a.z - mh.z) - ml.z) * iv.z;
-                a.w = ((a.w - mh.w) - ml.w) * iv.w;
-                rows[row * 50] = a;
-            }
-        }
-        fence_proxy_async();                     // generic-proxy writes of the rows -> async-proxy (bulk store) reads
-    };
-
     prepare_meta(0);
     if (tt == 0) { cp_async_commit(); cp_async_wait<0>(); }
     team_bar(team);
@@ -583,7 +462,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
         const Meta& mnext = meta[team][(u + 1) & 1];
         cp_async_wait<0>();
         team_bar(team);                         // P: the first sub-tile's PCM and the unit's constants are in place
-        z_store();
         const long long m_nfr = m.fo1 - m.fo;
         const int m_nf = (m_nfr - m.f0) < kUnit ? (int)(m_nfr - m.f0) : kUnit;
         const long long m_row0 = p.out_row_offsets ? m.row0 : m.fo;
@@ -596,7 +474,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
             if (sub > 0) {
                 cp_async_wait<0>();
                 team_bar(team);                 // P: the sub-tile's PCM is in place; the previous copy-out is over
-                z_store();
             } else {
                 prepare_meta((u + 1) & 1);      // (flags visible to the team after the next barrier)
                 if (zin) publish_count();
@@ -658,16 +535,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
             if (sub + 1 < nsub) stage(m, m.f0 + (sub + 1) * kSub);
             else if (mnext.valid) stage(mnext, mnext.f0);
             if (fin >= 0 && sub == 0) finalize_stats(p, tile_off, fin, tt);
-            // z-score, thread 0: start the bulk load of this sub-tile's chunk; ask for the next ticket or poll
-            // its entry -- the answers are consumed after pass 2 (nobody stalls on them)
-            int z_tkt = -2;
-            unsigned long long z_ent = 0;
-            if (zin && tt == 0) {
-                z_adopt();
-                z_issue();
-                if (zs.tkt < 0) { if (!zs.exhausted) z_tkt = atomicAdd(p.counters + 2, 1); }
-                else if (zs.ent == 0) z_ent = ld_acquire(p.queue + zs.tkt);
-            }
             // ---------------- pass 2: DFT10 of rows j and 20-j, split, log ----------------
             {
                 cplx ia[10], ib[10], za[10], zb[10];
@@ -729,17 +596,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
                 }
             }
             team_bar(team);                     // C: the out tile is complete
-            if (sub == 0) publish_queue(fin);
-            // z-score: the statistics of the chunk's utterance are requested now and used after the copy-out
-            const int zrows = zin ? (zs.loaded ? zs.rows : 0) : 0;
-            float4 zmh, zml, ziv;
-            zmh = zml = ziv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (zrows > 0 && co_act) {
-                const float4* st = reinterpret_cast<const float4*>(p.stats + (size_t)zs.b * 3 * kBins) + co_c4;
-                zmh = __ldcg(st);
-                zml = __ldcg(st + 50);
-                ziv = __ldcg(st + 100);
-            }
             // ---------------- copy-out (16-byte accesses) + column sums ----------------
             {
                 const int rows = (m_nf - sub * kSub) < kSub ? (m_nf - sub * kSub) : kSub;
@@ -755,14 +611,6 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
                     d = y.z - cS.z; sS.z += d; qS.z = fmaf(d, d, qS.z);
                     d = y.w - cS.w; sS.w += d; qS.w = fmaf(d, d, qS.w);
                 }
-            }
-            if (zrows > 0) z_process(zmh, zml, ziv, zrows, (unsigned)zs.nproc & 1u);
-            if (zin && tt == 0) {
-                if (z_tkt != -2) {
-                    if (z_tkt < total_tiles) zs.tkt = z_tkt;
-                    else zs.exhausted = 1;
-                }
-                if (z_ent != 0) zs.ent = z_ent;
             }
         }
         if (want_stats) {
@@ -790,48 +638,12 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
         }
     }
     if (zin) {
-        // drain: the team's last unit is published here ...
+        // drain: the team's last unit is published here
         team_bar(team);
-        z_store();
         publish_count();
         team_bar(team);
         const int fin = s_fin[team];
         if (fin >= 0) finalize_stats(p, tile_off, fin, tt);
-        team_bar(team);
-        publish_queue(fin);
-        // ... and the team keeps normalising queued chunks until every ticket has been handed out
-        for (;;) {
-            if (tt == 0 && !zs.loaded) {
-                while (zs.cur_left == 0 && !zs.finished) {
-                    if (zs.ent == 0) {
-                        if (zs.tkt < 0) {
-                            const int t = zs.exhausted ? total_tiles : atomicAdd(p.counters + 2, 1);
-                            if (t >= total_tiles) { zs.exhausted = 1; zs.finished = 1; break; }
-                            zs.tkt = t;
-                        }
-                        unsigned long long e;
-                        while ((e = ld_acquire(p.queue + zs.tkt)) == 0) __nanosleep(200);
-                        zs.ent = e;
-                    }
-                    z_adopt();
-                }
-                z_issue();
-            }
-            team_bar(team);
-            if (!zs.loaded) break;               // (finished, and nothing in the buffer)
-            float4 zmh, zml, ziv;
-            zmh = zml = ziv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (co_act) {
-                const float4* st = reinterpret_cast<const float4*>(p.stats + (size_t)zs.b * 3 * kBins) + co_c4;
-                zmh = __ldcg(st);
-                zml = __ldcg(st + 50);
-                ziv = __ldcg(st + 100);
-            }
-            z_process(zmh, zml, ziv, zs.rows, (unsigned)zs.nproc & 1u);
-            team_bar(team);
-            z_store();
-        }
-        if (tt == 0) tma_store_wait_all();       // no bulk copy may be in flight when the CTA exits
     }
 }
 
@@ -913,11 +725,11 @@ static void launch_main(const Params& p, int grid, cudaStream_t stream) {
     using C = Cfg<F32, kTeams, kSepOut>;
     const size_t smem = C::smem_bytes();
     cudaFuncSetAttribute(spectrogram_kernel<F32, kTeams, kSepOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spectrogram_kernel<F32, kTeams, kSepOut><<<grid, C::kThreads, smem, stream>>>(p);
+    spectrogram_kernel<F32, kTeams, kSepOut><<<grid, C::kThreads, smem, stream>>>(p), asrk::note_launch();
 }
 
 // Experiment switches (read once): ASRK_SPEC_TEAMS = 2 | 3 teams per CTA, ASRK_SPEC_ZSCORE = kernel | separate
-// (separate: the trailing stats + streaming z-score kernels of round 1).
+// (kernel: mean / 1/std finished by the transform kernel; separate: by the statistics kernel of round 1).
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -925,6 +737,10 @@ static int env_int(const char* name, int dflt) {
 static int cfg_teams() {
     static int v = env_int("ASRK_SPEC_TEAMS", 3);
     return v == 2 ? 2 : 3;
+}
+static int cfg_sepout() {      // int16, three teams: out tile in its own buffer (one team barrier less per sub-tile)
+    static int v = env_int("ASRK_SPEC_SEPOUT", 0);
+    return v;
 }
 static int cfg_zscore_in_kernel() {
     static int v = [] {
@@ -987,9 +803,9 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
     // case); a harness that times the phases one by one gets the separate kernels
     const bool both = (phases & ASRK_PHASE_SPEC_MAIN) && (phases & ASRK_PHASE_SPEC_NORMALIZE);
     const int teams = cfg_teams();
-    // (the float32 / noise-mix staging of three teams leaves no shared memory for the z-score buffers)
-    const bool z_fits = !(sample_dtype == ASRK_DTYPE_F32 && teams == 3);
-    const int zin = (mode == ASRK_SPEC_FBANK && both && z_fits && cfg_zscore_in_kernel()) ? 1 : 0;
+    // mean / 1/std are finished inside the transform kernel when both phases come in one call (the normal
+    // case); a harness that times the phases one by one gets the separate statistics kernel
+    const int zin = (mode == ASRK_SPEC_FBANK && both && cfg_zscore_in_kernel()) ? 1 : 0;
 
     // the kernel locates units through a prefix array in shared memory: at most
     // kMaxBatch utterances per launch, larger batches go in slices
@@ -1009,25 +825,25 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         p.out = out;
         p.counters = reinterpret_cast<int*>(ws + l.counters);
         p.done = reinterpret_cast<int*>(ws + l.done);
-        p.queue = reinterpret_cast<unsigned long long*>(ws + l.queue);
         p.tile_off_g = reinterpret_cast<int*>(ws + l.tile_off);
         p.partials = reinterpret_cast<double2*>(ws + l.partials);
         p.stats = reinterpret_cast<float*>(ws + l.stats) + (size_t)b0 * 3 * kBins;
         if (phases & ASRK_PHASE_SPEC_MAIN) {
-            // counters (| done | queue when the z-score runs in the kernel) start from zero
+            // counters (| done when the statistics are finished in the kernel) start from zero
             if (cudaMemsetAsync(ws + l.counters, 0, zin ? l.zero_bytes : sizeof(int) * 4, stream) != cudaSuccess)
                 return ASRK_E_CUDA;
             if (sample_dtype == ASRK_DTYPE_I16) {
                 if (teams == 2) launch_main<false, 2, true>(p, grid, stream);
+                else if (cfg_sepout()) launch_main<false, 3, true>(p, grid, stream);
                 else launch_main<false, 3, false>(p, grid, stream);
             } else {
                 if (teams == 2) launch_main<true, 2, true>(p, grid, stream);
                 else launch_main<true, 3, false>(p, grid, stream);
             }
         }
-        if (mode == ASRK_SPEC_FBANK && !zin && (phases & ASRK_PHASE_SPEC_NORMALIZE)) {
-            stats_kernel<<<nb, 256, 0, stream>>>(p);
-            normalize_kernel<<<dim3(32, nb), 128, 0, stream>>>(p);   // small CTAs: they fit next to the CTC kernel
+        if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE)) {
+            if (!zin) stats_kernel<<<nb, 256, 0, stream>>>(p), asrk::note_launch();
+            normalize_kernel<<<dim3(32, nb), 128, 0, stream>>>(p), asrk::note_launch();   // small CTAs: they fit next to the CTC kernel
         }
     }
     return launch_status();

@@ -81,6 +81,11 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
         torch.as_tensor(np.asarray(labels).astype(np.int32)).to(dev)
     labels = labels.reshape(B, -1).contiguous()
     Ls = labels.shape[1]
+    # length vectors that live on the host (numpy, lists, CPU tensors -- what Keras / the loader hand over)
+    if isinstance(input_len, torch.Tensor) and not input_len.is_cuda:
+        input_len = input_len.numpy()
+    if isinstance(label_len, torch.Tensor) and not label_len.is_cuda:
+        label_len = label_len.numpy()
     if bounds is None and not isinstance(input_len, torch.Tensor) and np.size(input_len):
         lmax = Ls if (label_len is None or isinstance(label_len, torch.Tensor) or not np.size(label_len)) \
             else int(np.max(label_len))

@@ -49,6 +49,8 @@ typedef void* asrk_stream_t;
 
 int asrk_version(void);
 const char* asrk_error_string(int code);
+/* number of CUDA kernels the library has launched since it was loaded (measurement aid) */
+unsigned long long asrk_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * Part 1: spectrogram features (+ optional fused noise mix)

@@ -102,21 +102,83 @@ def test_mixdict_vocab_and_unaligned_vocab():
         _check(x, labels, ll, il, V - 1)
 
 
+def _keras_case(rng, T_list, V, lo, hi, lmax):
+    import torch
+    x, labels, ll, il = synth.ctc_batch(rng, T_list, V, lo, hi, lmax=lmax)
+    p = torch.softmax(torch.as_tensor(x).permute(1, 0, 2), -1).contiguous()      # [B,T,V]
+    return p, labels, ll, il
+
+
+def _assert_prob_grad_close(got, ref, p, il):
+    """Gradient w.r.t. y_pred: dL/dp = (y - occupancy) / (p + eps).  "Within 1e-3 relative" on the two
+    probability terms, i.e. |d| (p + eps) <= rtol (|y - occ| + occ) + atol (the same rule as
+    assert_ctc_grad_close, carried through the division)."""
+    pe = p.astype(np.float64) + 1e-7
+    y = pe / pe.sum(-1, keepdims=True)
+    B, T, _ = p.shape
+    valid = (np.arange(T)[None, :] < np.asarray(il)[:, None])[:, :, None]
+    dref = ref * pe                               # y - occ
+    occ = np.abs(y * valid - dref)
+    tol = CTC_RTOL * (np.abs(dref) + occ) + CTC_ATOL
+    bad = np.abs(got - ref) * pe > tol
+    assert not bad.any(), (int(bad.sum()), float((np.abs(got - ref) * pe)[bad].max()))
+    assert not got[~np.broadcast_to(valid, got.shape)].any()
+
+
 def test_keras_ctc_batch_cost_and_autograd():
+    """K.ctc_batch_cost in ONE kernel: log(y_pred + 1e-7) formed on load, gradient written w.r.t. y_pred,
+    upstream scale inside (cnn_ctc.py:149-152).  Small lattices (fused kernel) and a long one (generic
+    kernels); `.sum().backward()` and the batch mean with the scale stated up front."""
+    import torch
+    from asr_dfcnn_transformer_b200 import _lib, ctc
+    rng = np.random.default_rng(5)
+    for T_list, V, lo, hi, lmax in (([30, 22, 16, 30], 60, 3, 9, 16), ([63, 40, 88, 12], 1424, 8, 24, 64),
+                                    ([300, 150], 64, 40, 60, 64)):
+        p, labels, ll, il = _keras_case(rng, T_list, V, lo, hi, lmax)
+        B = len(il)
+        args = (torch.as_tensor(labels.astype(np.float32)), None, torch.as_tensor(il.reshape(-1, 1).astype(np.int64)),
+                torch.as_tensor(ll.reshape(-1, 1).astype(np.int64)))
+        rl, rgp = ctc_ref.keras_ctc_batch_cost(labels, p.numpy(), il, ll)
+        # (a) .sum(): exactly one kernel of the library for forward + backward
+        pt = p.cuda().requires_grad_(True)
+        torch.cuda.synchronize()
+        n0 = _lib.lib().asrk_launch_count()
+        cost = ctc.ctc_batch_cost(args[0], pt, args[2], args[3])
+        assert tuple(cost.shape) == (B, 1)
+        cost.sum().backward()
+        n1 = _lib.lib().asrk_launch_count()
+        if max(T_list) <= 88:
+            assert n1 - n0 == 1, n1 - n0            # the fused kernel, nothing else
+        np.testing.assert_allclose(cost.detach().cpu().numpy(), rl, rtol=CTC_RTOL, atol=CTC_ATOL)
+        _assert_prob_grad_close(pt.grad.cpu().numpy().astype(np.float64), rgp, p.numpy(), il)
+        # (b) Keras' batch mean with the upstream gradient stated: still no extra pass, gradient scaled by 1/B
+        pt2 = p.cuda().requires_grad_(True)
+        ctc.ctc_batch_cost(args[0], pt2, args[2], args[3], upstream=1.0 / B).mean().backward()
+        _assert_prob_grad_close(pt2.grad.cpu().numpy().astype(np.float64) * B, rgp, p.numpy(), il)
+        # (c) a non-uniform upstream gradient falls back to one element-wise pass and is still right
+        pt3 = p.cuda().requires_grad_(True)
+        w = torch.arange(1, B + 1, dtype=torch.float32, device="cuda").view(B, 1)
+        (ctc.ctc_batch_cost(args[0], pt3, args[2], args[3]) * w).sum().backward()
+        _assert_prob_grad_close(pt3.grad.cpu().numpy().astype(np.float64) / w.cpu().numpy().reshape(B, 1, 1), rgp,
+                                p.numpy(), il)
+
+
+def test_ctc_loss_v2_blank_default_like_tf():
     import torch
     from asr_dfcnn_transformer_b200 import ctc
-    rng = np.random.default_rng(5)
-    x, labels, ll, il = synth.ctc_batch(rng, [30, 22, 16, 30], 60, 3, 9, lmax=16)
-    p = torch.softmax(torch.as_tensor(x).permute(1, 0, 2), -1).contiguous()      # [B,T,V]
-    pt = p.cuda().requires_grad_(True)
-    cost = ctc.ctc_batch_cost(torch.as_tensor(labels.astype(np.float32)), pt,
-                              torch.as_tensor(il.reshape(-1, 1).astype(np.int64)),
-                              torch.as_tensor(ll.reshape(-1, 1).astype(np.int64)))
-    assert tuple(cost.shape) == (4, 1)
-    cost.sum().backward()
-    rl, rgp = ctc_ref.keras_ctc_batch_cost(labels, p.numpy(), il, ll)
-    np.testing.assert_allclose(cost.detach().cpu().numpy(), rl, rtol=CTC_RTOL, atol=CTC_ATOL)
-    np.testing.assert_allclose(pt.grad.cpu().numpy(), rgp, rtol=2e-3, atol=1e-3)
+    rng = np.random.default_rng(15)
+    x, labels, ll, il = synth.ctc_batch(rng, [20, 14], 12, 2, 5)
+    labels = labels + 1                                   # blank 0: labels in 1..V-1
+    labels[labels >= 12] = 11
+    xs = torch.as_tensor(x).cuda()
+    loss = ctc.ctc_loss_v2(torch.as_tensor(labels), xs, torch.as_tensor(ll), torch.as_tensor(il))   # blank_index=None -> 0
+    rl, _, _ = ctc_ref.ctc_loss_grad_batch(x, labels, ll, il, 0)
+    np.testing.assert_allclose(loss.cpu().numpy(), rl, rtol=CTC_RTOL, atol=CTC_ATOL)
+    with pytest.raises(ValueError):
+        ctc.ctc_loss_v2(ctc.dense_to_sparse(torch.as_tensor(labels)), xs, None, torch.as_tensor(il))
+    # T == 0: every row rejected, nothing undefined
+    r = ctc.ctc_loss_grad(torch.zeros((0, 2, 12), device="cuda"), labels, ll, il, 11)
+    assert (r.row_status.cpu().numpy() == 3).all() and np.isnan(r.loss.cpu().numpy()).all()
 
 
 def test_ctc_loss_v2_raises_like_tf():
