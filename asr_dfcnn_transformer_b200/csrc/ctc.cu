@@ -1109,7 +1109,8 @@ __global__ void fill_bad_rows_kernel(float* loss, int* row_status, int* token_le
 
 // [sum of the losses of the rows TF would accept, number of such rows] in float64, one
 // CTA, fixed order (reproducible): the operand of the path's only collective.
-__global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const int* row_status, int B, double* out2) {
+__global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const int* row_status, int B, double* out2,
+                                                       int accumulate) {
     __shared__ double s_sum[256];
     __shared__ int s_cnt[256];
     double a = 0.0;
@@ -1124,7 +1125,36 @@ __global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const 
         if (threadIdx.x < o) { s_sum[threadIdx.x] += s_sum[threadIdx.x + o]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out2[0] = s_sum[0]; out2[1] = (double)s_cnt[0]; }
+    if (threadIdx.x == 0) {
+        if (accumulate) { out2[0] += s_sum[0]; out2[1] += (double)s_cnt[0]; }
+        else { out2[0] = s_sum[0]; out2[1] = (double)s_cnt[0]; }
+    }
+}
+
+// Device -> host return of the gradient without its padding: the mirror of stage_logits_kernel.  Rows
+// t < input_len[b] are written straight into (mapped, pinned) host memory by the SMs with 16-byte stores;
+// rows t >= input_len[b] (all zeros by definition) never cross PCIe.
+__global__ void __launch_bounds__(256) unstage_rows_kernel(const float* src, long long sst, long long ssb, float* dst,
+                                                           long long dst_t, long long dst_b, const int* input_len,
+                                                           int T, int B, int V) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)T * B;
+    const int V4 = V >> 2;
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+        const int t = (int)(row / B), b = (int)(row % B);
+        if (t >= input_len[b]) continue;
+        const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)t * sst + (size_t)b * ssb);
+        float4* d4 = reinterpret_cast<float4*>(dst + (size_t)t * dst_t + (size_t)b * dst_b);
+        for (int i0 = lane; i0 < V4; i0 += 32 * 6) {
+            float4 v[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e)
+                if (i0 + 32 * e < V4) v[e] = ldg_stream(s4 + i0 + 32 * e);
+#pragma unroll
+            for (int e = 0; e < 6; ++e)
+                if (i0 + 32 * e < V4) d4[i0 + 32 * e] = v[e];
+        }
+    }
 }
 
 // Host -> device staging of the logits without their padding: rows t < input_len[b] only are pulled
@@ -1390,7 +1420,27 @@ extern "C" int asrk_ctc_greedy_decode_run(const float* logits, long long stride_
 extern "C" int asrk_ctc_loss_sum_run(const float* loss, const int* row_status, int B, double* out2,
                                      asrk_stream_t stream_) {
     if (B < 0 || !out2 || (B > 0 && !loss)) return ASRK_E_BADARG;
-    loss_sum_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(loss, row_status, B, out2), asrk::note_launch();
+    loss_sum_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(loss, row_status, B, out2, 0), asrk::note_launch();
+    return launch_status();
+}
+
+extern "C" int asrk_ctc_loss_sum_acc_run(const float* loss, const int* row_status, int B, double* out2,
+                                         asrk_stream_t stream_) {
+    if (B < 0 || !out2 || (B > 0 && !loss)) return ASRK_E_BADARG;
+    loss_sum_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(loss, row_status, B, out2, 1), asrk::note_launch();
+    return launch_status();
+}
+
+extern "C" int asrk_ctc_unstage_rows_run(const float* src, long long src_stride_t, long long src_stride_b,
+                                         float* dst, long long dst_stride_t, long long dst_stride_b,
+                                         const int* input_len, int T, int B, int V, asrk_stream_t stream_) {
+    if (T < 0 || B < 0 || V < 1) return ASRK_E_BADARG;
+    if (T == 0 || B == 0) return ASRK_OK;
+    if (!src || !dst || !input_len) return ASRK_E_BADARG;
+    if (V % 4 != 0 || (src_stride_t % 4) || (src_stride_b % 4) || (dst_stride_t % 4) || (dst_stride_b % 4)) return ASRK_E_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return ASRK_E_ALIGN;
+    unstage_rows_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+        src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, T, B, V), asrk::note_launch();
     return launch_status();
 }
 

@@ -151,16 +151,33 @@ def stage_logits(host_logits, input_len, out=None, layout="tbv", stream=None):
     return out
 
 
-def loss_sum(loss, row_status=None, out=None, stream=None):
+def loss_sum(loss, row_status=None, out=None, stream=None, accumulate=False):
     """[sum of the accepted rows' losses, their number] as a float64 device tensor of 2
-    (the operand of the batch mean / of the cross-rank all-reduce)."""
+    (the operand of the batch mean / of the cross-rank all-reduce).  ``accumulate=True`` adds to ``out``
+    (mean over several steps with one all-reduce, like the reference's print every second step)."""
     torch = _lib.require_cuda()
     if out is None:
+        if accumulate:
+            raise ValueError("accumulate needs the running tensor in `out`")
         out = torch.empty(2, dtype=torch.float64, device=loss.device)
-    st = _lib.lib().asrk_ctc_loss_sum_run(_lib.ptr(loss), _lib.ptr(row_status), int(loss.numel()), _lib.ptr(out),
-                                          _lib.stream_ptr(stream))
+    fn = _lib.lib().asrk_ctc_loss_sum_acc_run if accumulate else _lib.lib().asrk_ctc_loss_sum_run
+    st = fn(_lib.ptr(loss), _lib.ptr(row_status), int(loss.numel()), _lib.ptr(out), _lib.stream_ptr(stream))
     _lib.check(st, "asrk_ctc_loss_sum_run")
     return out
+
+
+def unstage_rows(dev_tensor, input_len, host_out, layout="tbv", stream=None):
+    """Device -> host copy of a ``[T,B,V]`` / ``[B,T,V]`` tensor (the gradient) WITHOUT its padding: only rows
+    t < input_len[b] cross PCIe, written by the SMs into the pinned host tensor ``host_out`` (rows past
+    input_len keep what the buffer held: zeros if it was cleared once)."""
+    if not host_out.is_pinned():
+        raise ValueError("unstage_rows needs pinned (page-locked) host memory")
+    T, B, V, st, sb = _strides(dev_tensor, layout)
+    _, _, _, dt, db = _strides(host_out, layout)
+    rc = _lib.lib().asrk_ctc_unstage_rows_run(_lib.ptr(dev_tensor), st, sb, ctypes.c_void_p(host_out.data_ptr()), dt, db,
+                                              _lib.ptr(input_len), T, B, V, _lib.stream_ptr(stream))
+    _lib.check(rc, "asrk_ctc_unstage_rows_run")
+    return host_out
 
 
 def _raise_on_status(status):

@@ -83,3 +83,87 @@ class HotPathStep:
                                 grad_scale=grad_scale, grad_out=grad_out, decode=decode, bounds=ctc_bounds)
         cur.wait_event(self._ev_join)
         return feats, res
+
+
+class HostRoundTrip:
+    """The hot path with HOST buffers on both sides, double-buffered: while step k computes, the inputs
+    of step k+1 go host -> device on a copy-in stream and the results of step k-1 come back on a
+    copy-out stream (PCIe is full duplex).  Per step:
+
+      in   PCM + labels (DMA from pinned memory), logits without their padding (``ctc.stage_logits``)
+      out  per-utterance loss, the features (DMA into pinned memory) and the gradient without its
+           all-zero padding rows (``ctc.unstage_rows``)
+
+    ``submit`` returns a slot; ``wait(slot)`` blocks until that step's results are in its host buffers
+    (``slot.h_loss / h_feat / h_grad``).  A slot's buffers are reused by the submit after next."""
+
+    class Slot:
+        pass
+
+    def __init__(self, step, total_frames_max, samples_max, sample_dtype, T, B, V, label_stride, slots=2,
+                 return_outputs=True):
+        torch = step.torch
+        self.step, self.torch = step, torch
+        dev = step.device
+        self.return_outputs = return_outputs
+        self.s_in = torch.cuda.Stream(device=dev)
+        self.s_out = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(slots):
+            s = HostRoundTrip.Slot()
+            s.samples = torch.empty(samples_max, dtype=sample_dtype, device=dev)
+            s.labels = torch.empty((B, label_stride), dtype=torch.int32, device=dev)
+            s.logits = torch.zeros((T, B, V), dtype=torch.float32, device=dev)
+            s.feat = torch.empty((total_frames_max, 200), dtype=torch.float32, device=dev)
+            s.grad = torch.empty((T, B, V), dtype=torch.float32, device=dev)
+            s.h_loss = torch.empty(B, dtype=torch.float32).pin_memory()
+            if return_outputs:
+                s.h_feat = torch.empty((total_frames_max, 200), dtype=torch.float32).pin_memory()
+                s.h_grad = torch.zeros((T, B, V), dtype=torch.float32).pin_memory()
+            s.ev_in, s.ev_done, s.ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            s.busy = False
+            self.slots.append(s)
+        self.k = 0
+
+    def submit(self, h_samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames, h_logits,
+               h_labels, label_len, input_len, blank=None, grad_scale=None, ctc_bounds=None):
+        """Host tensors are pinned; offsets / lengths are device tensors (they are a few KB and belong to the
+        batch description).  Returns the slot (h2d_bytes / d2h_bytes attributes say what crossed PCIe)."""
+        torch = self.torch
+        s = self.slots[self.k % len(self.slots)]
+        self.k += 1
+        if s.busy:
+            self.wait(s)
+        cur = torch.cuda.current_stream(self.step.device)
+        n = h_samples.numel()
+        with torch.cuda.stream(self.s_in):
+            s.samples[:n].copy_(h_samples, non_blocking=True)
+            s.labels.copy_(h_labels, non_blocking=True)
+            ctc.stage_logits(h_logits, input_len, out=s.logits, stream=self.s_in)
+            s.ev_in.record(self.s_in)
+        cur.wait_event(s.ev_in)
+        feats, res = self.step(s.samples[:n], sample_offsets, sample_counts, frame_offsets, batch, total_frames,
+                               s.logits, s.labels, label_len, input_len, blank, feat_out=s.feat[:total_frames],
+                               grad_out=s.grad, grad_scale=grad_scale, ctc_bounds=ctc_bounds)
+        s.ev_done.record(cur)
+        self.s_out.wait_event(s.ev_done)
+        with torch.cuda.stream(self.s_out):
+            s.h_loss.copy_(res.loss, non_blocking=True)
+            if self.return_outputs:
+                s.h_feat[:total_frames].copy_(feats, non_blocking=True)
+                ctc.unstage_rows(s.grad, input_len, s.h_grad, stream=self.s_out)
+            s.ev_out.record(self.s_out)
+        s.res, s.total_frames, s.busy = res, total_frames, True
+        s.h2d_bytes = n * h_samples.element_size() + h_labels.numel() * 4
+        s.d2h_bytes = s.h_loss.numel() * 4 + (total_frames * 800 if self.return_outputs else 0)
+        return s
+
+    def wait(self, s):
+        s.ev_out.synchronize()
+        s.busy = False
+        return s
+
+    def drain(self):
+        for s in self.slots:
+            if s.busy:
+                self.wait(s)

@@ -4,15 +4,22 @@ loss + gradient) on N B200s, with the HBM roofline of the dominant kernel and th
 CPU baseline timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c3|c4|c5] [--surface logits|keras]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C2"): per GPU an AISHELL-shaped synthetic
-batch of 256 utterances of U(3,7) s 16 kHz int16 audio (generator G2), CTC logits
-[Tmax, 256, 1424] fp32 with T_ctc = min(200, n_frames//8+1) and labels ~ U{8..24}.
-One step = features (frames -> Hamming -> 400-pt FFT -> log(|X|+1) -> z-score) of
-the whole batch + CTC loss and gradient w.r.t. the logits of the whole batch.
-Utterances are sharded by batch across ranks (weak scaling: every rank owns its own
-256 utterances); the only collective is the all-reduce of [sum loss, n].
+Workloads (BASELINE.json `configs`; C2 is the default and the headline -- the configuration the metric is
+quoted on; C1 is the reference's own CPU-runnable case and a parity-test case only):
+  c2  per GPU 256 utterances of U(3,7) s 16 kHz int16 audio (generator G2), z-scored features + CTC loss and
+      gradient on logits [Tmax,256,1424] with T_ctc = min(200, n_frames//8+1), labels ~ U{8..24}
+      (--surface keras: the CTC part through K.ctc_batch_cost's input, probabilities [B,T,V])
+  c3  64 utterances of 20 s, frame-rate CTC (T = 1998, labels ~ U{280..320}): the generic long-lattice kernels
+  c4  noise-augmented features only: 512 utterances of U(3,7) s float32 signal + noise at 5..10 dB, gains on
+      the device, mix fused into the frame load
+  c5  the sweep shape: C2 batches from a larger rotating pool, greedy decode fused into the CTC pass and the
+      label error (device edit distance) computed per step
+One step = the whole batch through the path.  Utterances are sharded by batch across ranks (weak scaling:
+every rank owns its own batch); the only collective is the all-reduce of [sum loss, n], issued every second
+step on the accumulated sums (the reference prints its mean loss every second step, train.py:71-73).
 """
 import argparse
 import json
@@ -32,29 +39,22 @@ from oracle import synth  # noqa: E402  (pure data generation, no reference arit
 
 FS = 16000
 V = synth.VOCAB_DICT_TXT
-BATCH = 256
-POOL = 3          # distinct device-resident batches rotated through the timed loop
 METRIC = "audio-sec/sec (fbank+CTC loss+grad)"
-WORKLOAD = ("C2: AISHELL-shaped 256 utt/GPU x U(3,7) s int16 16 kHz (G2), fbank z-scored + CTC loss/grad, V=1424, "
-            "T_ctc=min(200,n_frames//8+1), L~U{8..24}")
-
-
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from
-    the committed `ncu --set full` capture of this workload (profiles/traffic.json)."""
-    try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["dram_bytes"])
-    except Exception:
-        return None
-
-
-def ncu_fp64_pct(kernel):
-    """fp64 pipe utilisation of that kernel in the same capture (the spectrogram kernel is bound by the
-    fp64 pipe and its feeding, not by HBM: the HBM fraction alone would misread it)."""
-    try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["fp64_pipe_pct"])
-    except Exception:
-        return None
+REDUCE_EVERY = 2
+WORKLOADS = {
+    "c2": dict(batch=256, pool=3, ctc=True,
+               name="C2: AISHELL-shaped 256 utt/GPU x U(3,7) s int16 16 kHz (G2), fbank z-scored + CTC loss/grad, "
+                    "V=1424, T_ctc=min(200,n_frames//8+1), L~U{8..24}"),
+    "c3": dict(batch=64, pool=2, ctc=True,
+               name="C3: long utterances 64 utt/GPU x 20 s int16 (G2), fbank z-scored + frame-rate CTC loss/grad, "
+                    "V=1424, T=1998, L~U{280..320} (generic lattice kernels)"),
+    "c4": dict(batch=512, pool=2, ctc=False,
+               name="C4: noise-augmented features 512 utt/GPU x U(3,7) s float32 signal + noise at 5..10 dB, gains "
+                    "(SNR2K) on the device, mix fused into the frame load, fbank z-scored; no CTC"),
+    "c5": dict(batch=256, pool=8, ctc=True,
+               name="C5: sweep of C2-shaped batches (256 utt/GPU per step from a rotating pool of 8), fbank z-scored "
+                    "+ CTC loss/grad with the greedy decode fused + device label error"),
+}
 
 
 def peaks():
@@ -65,6 +65,14 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_capture(kernel, key):
+    """per-launch figures of a kernel from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel][key])
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -80,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -119,72 +127,106 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------
-# workload
+# workloads (host arrays)
 # ----------------------------------------------------------------------------
-def make_batch(seed, batch=BATCH):
-    """One C2 batch as host arrays (numpy)."""
+def _cached(name, build):
     cache = os.environ.get("ASRK_BENCH_CACHE")
-    cpath = os.path.join(cache, "c2_%d_%d.npz" % (seed, batch)) if cache else None
-    if cpath and os.path.isfile(cpath):
-        d = np.load(cpath)
-        lens = d["lens"]
-        offs = np.concatenate([[0], np.cumsum(lens)])
-        pcm = [d["pcm"][offs[i]:offs[i + 1]] for i in range(len(lens))]
-        return dict(pcm=pcm, lens=lens, nfr=d["nfr"], logits=d["logits"], labels=d["labels"],
-                    label_len=d["label_len"], input_len=d["input_len"])
-    rng = np.random.default_rng(seed)
-    lens = synth.ragged_lengths(rng, batch, 3.0, 7.0)
-    # G2 synthesis of 256 x 5 s costs seconds per batch on the host; the bench
-    # needs the *shape* of the signal (harmonics + AM + floor), so build it
-    # vectorised here with the same recipe.
-    pcm = []
-    for n in lens:
-        pcm.append(synth.g2_voiced(rng, int(n)))
-    nfr = np.array([synth.n_frames(int(n)) for n in lens], dtype=np.int64)
-    il = np.array([synth.t_ctc(int(f)) for f in nfr], dtype=np.int32)
-    x, labels, ll, il = synth.ctc_batch(rng, il, V, 8, 24, lmax=64, scale=3.0)
-    if cpath:
+    path = os.path.join(cache, name + ".npz") if cache else None
+    if path and os.path.isfile(path):
+        d = dict(np.load(path))
+        offs = np.concatenate([[0], np.cumsum(d["lens"])])
+        for k in ("pcm", "noise"):
+            if k in d:
+                d[k] = [d[k][offs[i]:offs[i + 1]] for i in range(len(d["lens"]))]
+        return d
+    d = build()
+    if path:
         os.makedirs(cache, exist_ok=True)
-        np.savez(cpath, pcm=np.concatenate(pcm), lens=lens, nfr=nfr, logits=x, labels=labels, label_len=ll,
-                 input_len=il)
-    return dict(pcm=pcm, lens=lens, nfr=nfr, logits=x, labels=labels, label_len=ll, input_len=il)
+        flat = dict(d)
+        for k in ("pcm", "noise"):
+            if k in flat:
+                flat[k] = np.concatenate(flat[k])
+        np.savez(path, **flat)
+    return d
 
 
-def algorithmic_bytes(b):
-    """features 2N + 800 n_frames per utterance; CTC 8 T_ctc V."""
-    feat = int(2 * b["lens"].sum() + 800 * b["nfr"].sum())
-    ctc = int(8 * V * b["input_len"].astype(np.int64).sum())
+def make_batch(seed, batch=256, workload="c2"):
+    """One batch of the workload as host arrays (numpy).  c2 / c5: the AISHELL shape; c3: 20 s utterances;
+    c4: float32 signal + noise + SNR."""
+    def build():
+        rng = np.random.default_rng(seed)
+        if workload == "c3":
+            lens = np.full(batch, 320000, dtype=np.int64)
+        else:
+            lens = synth.ragged_lengths(rng, batch, 3.0, 7.0)
+        pcm = [synth.g2_voiced(rng, int(n)) for n in lens]
+        nfr = np.array([synth.n_frames(int(n)) for n in lens], dtype=np.int64)
+        if workload == "c4":
+            sig = [(p.astype(np.float32) / np.float32(32768.0)) for p in pcm]
+            noise = []
+            for i, n in enumerate(lens):
+                x = rng.standard_normal(int(n))          # coloured-noise stand-in: the generator is an input of the mix
+                nz = np.cumsum(x) if i % 2 else x
+                nz = nz - nz.mean()
+                noise.append((nz / nz.max()).astype(np.float32))
+            return dict(pcm=sig, noise=noise, snr_db=rng.integers(5, 11, batch).astype(np.int32), lens=lens, nfr=nfr)
+        if workload == "c3":
+            il = nfr.astype(np.int32)
+            x, labels, ll, il = synth.ctc_batch(rng, il, V, 280, 320)
+        else:
+            il = np.array([synth.t_ctc(int(f)) for f in nfr], dtype=np.int32)
+            x, labels, ll, il = synth.ctc_batch(rng, il, V, 8, 24, lmax=64, scale=3.0)
+        return dict(pcm=pcm, lens=lens, nfr=nfr, logits=x, labels=labels, label_len=ll, input_len=il)
+    tag = "c2" if workload == "c5" else workload
+    return _cached("%s_%d_%d" % (tag, seed, batch), build)
+
+
+def algorithmic_bytes(b, workload):
+    """SURVEY.md 8(d): features 2N + 800 n_frames per utterance (noise mode: 4N + 4N + 800 n_frames);
+    CTC loss+grad 8 T_ctc V (the fused greedy decode of c5 shares the logits read: 0 extra)."""
+    n, f = int(b["lens"].sum()), int(b["nfr"].sum())
+    feat = (8 * n if workload == "c4" else 2 * n) + 800 * f
+    ctc = int(8 * V * b["input_len"].astype(np.int64).sum()) if "input_len" in b else 0
     return feat, ctc
 
 
 class DeviceBatch:
     """A batch resident in HBM plus its pinned host copy (for the e2e leg)."""
 
-    def __init__(self, hb, dev, torch):
+    def __init__(self, hb, dev, torch, workload, surface):
         from asr_dfcnn_transformer_b200 import features
-        self.hb = hb
-        pk = features.pack_host(hb["pcm"], FS, "fbank")
+        self.hb, self.workload = hb, workload
+        noises = hb.get("noise")
+        pk = features.pack_host(hb["pcm"], FS, "fbank", noises=noises)
         self.pk = pk
         self.B = len(hb["pcm"])
-        self.h_samples = pk.samples                       # pinned int16
-        self.h_logits = torch.from_numpy(hb["logits"]).pin_memory()
-        self.h_labels = torch.from_numpy(hb["labels"]).pin_memory()
+        self.h_samples = pk.samples                       # pinned
         self.samples = pk.samples.to(dev)
+        self.noise = pk.noise.to(dev) if pk.noise is not None else None
+        self.h_noise = pk.noise
+        self.snr_db = torch.from_numpy(hb["snr_db"]).to(dev) if "snr_db" in hb else None
         self.so = torch.from_numpy(pk.sample_offsets).to(dev)
         self.sc = torch.from_numpy(pk.sample_counts).to(dev)
         self.fo = torch.from_numpy(pk.frame_offsets).to(dev)
         self.total_frames = pk.total_frames
-        self.logits = self.h_logits.to(dev)
-        self.labels = self.h_labels.to(dev)
-        self.label_len = torch.from_numpy(hb["label_len"]).to(dev)
-        self.input_len = torch.from_numpy(hb["input_len"]).to(dev)
         self.feat = torch.empty((pk.total_frames, 200), dtype=torch.float32, device=dev)
-        self.grad = torch.empty_like(self.logits)
-        self.grad_scale = torch.full((self.B,), 1.0 / self.B, dtype=torch.float32, device=dev)
         self.audio_s = float(hb["lens"].sum()) / FS
-        # the loader's host-side length vectors bound the batch: every lattice fits the fused CTC kernel
-        self.ctc_bounds = (int(hb["input_len"].max()), int(hb["label_len"].max()))
-        self.bytes_feat, self.bytes_ctc = algorithmic_bytes(hb)
+        self.bytes_feat, self.bytes_ctc = algorithmic_bytes(hb, workload)
+        if "logits" in hb:
+            self.h_logits = torch.from_numpy(hb["logits"]).pin_memory()
+            self.h_labels = torch.from_numpy(hb["labels"]).pin_memory()
+            self.logits = self.h_logits.to(dev)
+            if surface == "keras":                        # what the Keras model hands to K.ctc_batch_cost: softmax [B,T,V]
+                self.probs = torch.softmax(self.logits.permute(1, 0, 2), -1).contiguous()
+                self.grad = torch.empty_like(self.probs)
+            else:
+                self.grad = torch.empty_like(self.logits)
+            self.labels = self.h_labels.to(dev)
+            self.label_len = torch.from_numpy(hb["label_len"]).to(dev)
+            self.input_len = torch.from_numpy(hb["input_len"]).to(dev)
+            self.grad_scale = torch.full((self.B,), 1.0 / self.B, dtype=torch.float32, device=dev)
+            # the loader's host-side length vectors bound the batch (data_loader.py:132-148)
+            self.ctc_bounds = (int(hb["input_len"].max()), int(hb["label_len"].max()))
 
 
 _STEP = {}
@@ -197,34 +239,58 @@ def hot_path(dev):
     return _STEP[dev]
 
 
-def run_step(db, phases_timer=None):
-    """The hot path on device-resident inputs.  Returns the CtcResult."""
-    from asr_dfcnn_transformer_b200 import _lib, ctc, features
-    if phases_timer is None:
-        _, r = hot_path(db.samples.device)(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames,
-                                           db.logits, db.labels, db.label_len, db.input_len, V - 1,
-                                           feat_out=db.feat, grad_out=db.grad, grad_scale=db.grad_scale,
-                                           ctc_bounds=db.ctc_bounds)
+def run_step(db, surface="logits"):
+    """The hot path on device-resident inputs.  Returns the CtcResult (None for c4)."""
+    from asr_dfcnn_transformer_b200 import ctc, features, utils
+    w = db.workload
+    if w == "c4":
+        features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", noise=db.noise,
+                                    snr_db=db.snr_db, out=db.feat)
+        return None
+    if surface == "keras":
+        hp = hot_path(db.samples.device)
+        torch = hp.torch
+        cur = torch.cuda.current_stream(hp.device)
+        hp._ev_fork.record(cur)
+        hp.side.wait_event(hp._ev_fork)
+        with torch.cuda.stream(hp.side):
+            features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat,
+                                        stream=hp.side)
+            hp._ev_join.record(hp.side)
+        r = ctc.ctc_loss_grad(db.probs, db.labels, db.label_len, db.input_len, V - 1, layout="btv",
+                              grad_scale=db.grad_scale, grad_out=db.grad, bounds=db.ctc_bounds, input_kind="prob")
+        cur.wait_event(hp._ev_join)
         return r
-    # same launches, issued phase by phase with CUDA events between them
-    ev = phases_timer
-    ev.mark()
-    for ph in (_lib.PHASE_SPEC_SETUP, _lib.PHASE_SPEC_MAIN, _lib.PHASE_SPEC_NORMALIZE):
-        features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank",
-                                    out=db.feat, phases=ph)
-        ev.mark()
-    r = None
-    for ph in (_lib.PHASE_CTC_PREP, _lib.PHASE_CTC_FUSED, _lib.PHASE_CTC_ROWS, _lib.PHASE_CTC_LATTICE,
-               _lib.PHASE_CTC_GRAD):
-        r = ctc.ctc_loss_grad(db.logits, db.labels, db.label_len, db.input_len, V - 1,
-                              grad_scale=db.grad_scale, grad_out=db.grad, phases=ph,
-                              outputs=None if r is None else (r.loss, db.grad, r.row_status, None, None, None))
-        ev.mark()
+    _, r = hot_path(db.samples.device)(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames,
+                                       db.logits, db.labels, db.label_len, db.input_len, V - 1,
+                                       feat_out=db.feat, grad_out=db.grad, grad_scale=db.grad_scale,
+                                       ctc_bounds=db.ctc_bounds, decode=(w == "c5"))
+    if w == "c5":
+        db.label_err = utils.edit_distance(r.tokens, r.token_len, db.labels, db.label_len)
     return r
 
 
 KERNELS = ["spec_setup", "spec_main", "spec_normalize", "ctc_prep", "ctc_fused", "ctc_rows", "ctc_lattice",
            "ctc_grad"]
+
+
+def run_step_phases(db, ev):
+    """the same launches issued phase by phase with CUDA events between them (c4: feature phases only)"""
+    from asr_dfcnn_transformer_b200 import _lib, ctc, features
+    ev.mark()
+    for ph in (_lib.PHASE_SPEC_SETUP, _lib.PHASE_SPEC_MAIN, _lib.PHASE_SPEC_NORMALIZE):
+        features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat,
+                                    noise=db.noise, snr_db=db.snr_db, phases=ph)
+        ev.mark()
+    r = None
+    for ph in (_lib.PHASE_CTC_PREP, _lib.PHASE_CTC_FUSED, _lib.PHASE_CTC_ROWS, _lib.PHASE_CTC_LATTICE,
+               _lib.PHASE_CTC_GRAD):
+        if db.workload != "c4":
+            r = ctc.ctc_loss_grad(db.logits, db.labels, db.label_len, db.input_len, V - 1,
+                                  grad_scale=db.grad_scale, grad_out=db.grad if db.grad.shape == db.logits.shape else None,
+                                  phases=ph,
+                                  outputs=None if r is None else (r.loss, r.grad, r.row_status, None, None, None))
+        ev.mark()
 
 
 class PhaseTimer:
@@ -255,8 +321,11 @@ class PhaseTimer:
 # ----------------------------------------------------------------------------
 # CPU baseline (oracle port / reference arm)
 # ----------------------------------------------------------------------------
-def _cpu_features_worker(sig):
+def _cpu_features_worker(arg):
     from oracle import fbank_ref
+    sig, nz, db = arg
+    if nz is not None:
+        sig = fbank_ref.mix_noise(sig, nz, db)          # noise.py:48-52,108 on the host, then the features
     return fbank_ref.compute_fbank(sig).shape[0]
 
 
@@ -272,40 +341,49 @@ def _pool(cores):
 
 
 def cpu_sample(hb, n_utt, cores):
-    """Time the oracle (port of the reference's CPU path) on the first n_utt
-    utterances of the workload: per-frame scipy FFT features fanned out over the
-    host cores + the float32 C restatement of TF's CTC loss/grad (OpenMP)."""
-    import multiprocessing as mp
+    """Time the oracle (port of the reference's CPU path) on the first n_utt utterances of the workload:
+    per-frame scipy FFT features (+ the numpy noise mix for c4) fanned out over the host cores + the float32 C
+    restatement of TF's CTC loss/grad (OpenMP)."""
     from oracle import build_c
     build_c.lib()
     sigs = hb["pcm"][:n_utt]
+    noises = hb["noise"][:n_utt] if "noise" in hb else [None] * n_utt
+    dbs = hb["snr_db"][:n_utt] if "snr_db" in hb else [0] * n_utt
     audio_s = sum(len(s) for s in sigs) / FS
+    args = list(zip(sigs, noises, [int(d) for d in dbs]))
     t0 = time.perf_counter()
     if cores > 1:
-        _pool(cores).map(_cpu_features_worker, sigs, chunksize=1)
+        _pool(cores).map(_cpu_features_worker, args, chunksize=1)
     else:
-        for s in sigs:
-            _cpu_features_worker(s)
+        for a in args:
+            _cpu_features_worker(a)
     t_feat = time.perf_counter() - t0
-    il = hb["input_len"][:n_utt]
-    T = int(il.max())
-    x = np.ascontiguousarray(hb["logits"][:T, :n_utt])
-    t0 = time.perf_counter()
-    build_c.ctc_loss_grad(x, hb["labels"][:n_utt], hb["label_len"][:n_utt], il, V - 1, real="f32",
-                          threads=cores)
-    t_ctc = time.perf_counter() - t0
+    t_ctc = 0.0
+    if "logits" in hb:
+        il = hb["input_len"][:n_utt]
+        T = int(il.max())
+        x = np.ascontiguousarray(hb["logits"][:T, :n_utt])
+        t0 = time.perf_counter()
+        build_c.ctc_loss_grad(x, hb["labels"][:n_utt], hb["label_len"][:n_utt], il, V - 1, real="f32", threads=cores)
+        t_ctc = time.perf_counter() - t0
     return audio_s, t_feat, t_ctc
 
 
+def cpu_sample_size(workload, n_utt, cores):
+    # bounded: ~1 s per pass on 16 cores
+    return {"c2": n_utt, "c5": n_utt, "c3": min(n_utt, 16), "c4": min(n_utt, 256)}[workload]
+
+
 def reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (the oracle
-    port: /root/reference is Python+TensorFlow and does not exist on the GPU box)
-    on the host cores, same workload/metric, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: /root/reference is
+    Python+TensorFlow and does not exist on the GPU box) on the host cores, same workload/metric, bounded
+    sample per step."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    hb = make_batch(2000)                      # one full C2 batch per step (~1 s of wall time on 16 cores)
-    n_utt = len(hb["pcm"])
+    w = WORKLOADS[args.workload]
+    hb = make_batch(2000, w["batch"], args.workload)
+    n_utt = cpu_sample_size(args.workload, len(hb["pcm"]), cores)
     for _ in range(args.warmup):
         cpu_sample(hb, min(n_utt, 2 * cores), cores)
     tot_audio, tot_t = 0.0, 0.0
@@ -319,15 +397,38 @@ def reference_arm(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "utterances_per_gpu": BATCH,
+        "config": {"workload": w["name"], "utterances_per_gpu": w["batch"],
                    "sample": "%d utterances of the workload per step" % n_utt, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": val, "unit": "audio-sec/sec", "cores": cores, "kind": "port",
-                         "sample": "%d C2 utterances per step: oracle/fbank_ref.py (per-frame scipy FFT, "
-                                   "multiprocessing) + oracle/ctc_ref.c float32 (OpenMP)" % n_utt},
+                         "sample": "%d %s utterances per step: oracle/fbank_ref.py (per-frame scipy FFT, "
+                                   "multiprocessing) + oracle/ctc_ref.c float32 (OpenMP)" % (n_utt, args.workload.upper())},
         "e2e": {"value": val, "unit": "audio-sec/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def pin_to_gpu_numa_node(local_rank):
+    """Keep this rank's threads (and therefore its first-touched pinned buffers) on the NUMA node of its GPU:
+    eight ranks staging through one node's memory is what limited the end-to-end scaling in round 1."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        devid = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/" % (dom, bus, devid)
+        node = int(open(path + "numa_node").read())
+        if node < 0:
+            return None
+        cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, ids)
+        return node
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------
@@ -339,9 +440,13 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--surface", default="logits", choices=["logits", "keras"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.surface == "keras" and args.workload != "c2":
+        ap.error("--surface keras is a variant of the c2 workload")
 
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # started by hand with --gpus N: become the launch the driver uses (one rank per GPU, NCCL, loopback)
@@ -360,6 +465,8 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
+    wl = WORKLOADS[args.workload]
+    BATCH, POOL = wl["batch"], wl["pool"]
 
     # ---- (0) CPU baseline on rank 0 (N = 1 only), BEFORE CUDA is initialised so that the
     # worker processes can be forked safely ---------------------------------------------
@@ -367,45 +474,55 @@ def main():
     hb0 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        hb0 = make_batch(2000)
-        n_utt = len(hb0["pcm"])                             # the whole C2 batch, twice: ~10 s of CPU work
+        hb0 = make_batch(2000, BATCH, args.workload)
+        n_utt = cpu_sample_size(args.workload, len(hb0["pcm"]), cores)
         cpu_sample(hb0, min(n_utt, cores), cores)          # warm the pool / page cache
         a = tf_ = tc_ = 0.0
         for _ in range(2):
             a1, t1, t2 = cpu_sample(hb0, n_utt, cores)
             a, tf_, tc_ = a + a1, tf_ + t1, tc_ + t2
         cpu = {"value": a / (tf_ + tc_), "unit": "audio-sec/sec", "cores": cores, "kind": "port",
-               "sample": "2 passes over the %d utterances of one C2 batch (%.0f audio-s): oracle/fbank_ref.py "
-                         "features (per-frame scipy FFT, %d processes, %.2f s) + oracle/ctc_ref.c float32 CTC "
-                         "loss/grad (OpenMP, %.2f s)" % (n_utt, a, cores, tf_, tc_)}
+               "sample": "2 passes over %d utterances of one %s batch (%.0f audio-s): oracle/fbank_ref.py features "
+                         "(per-frame scipy FFT, %d processes, %.2f s) + oracle/ctc_ref.c float32 CTC loss/grad "
+                         "(OpenMP, %.2f s)" % (n_utt, args.workload.upper(), a, cores, tf_, tc_)}
 
     import torch
     import torch.distributed as dist
-    from asr_dfcnn_transformer_b200 import _lib
-    _lib.lib()
+    from asr_dfcnn_transformer_b200 import _lib, ctc, pipeline
+    L = _lib.lib()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- data: POOL distinct batches per rank, resident in HBM --------------
-    pool = [DeviceBatch(hb0 if (i == 0 and rank == 0 and hb0 is not None) else make_batch(2000 + 100 * rank + i),
-                        dev, torch) for i in range(POOL)]
+    pool = [DeviceBatch(hb0 if (i == 0 and rank == 0 and hb0 is not None)
+                        else make_batch(2000 + 100 * rank + i, BATCH, args.workload), dev, torch, args.workload,
+                        args.surface) for i in range(POOL)]
     audio_per_step = float(np.mean([d.audio_s for d in pool]))
-    red = torch.zeros(2, dtype=torch.float64, device=dev)
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)     # running [sum loss, n] of this rank
+    red = torch.zeros(2, dtype=torch.float64, device=dev)     # operand / result of the all-reduce
     side = torch.cuda.Stream(device=dev)
+    step_no = [0]
 
-    def reduce_loss(r, db):
-        # the path's only collective: all-reduce of [sum loss, n] (one tiny kernel fills
-        # the operand), on a side stream so that it overlaps the next step
-        from asr_dfcnn_transformer_b200 import ctc, pipeline
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(side)      # the previous step's all-reduce is done with `red`
-        ctc.loss_sum(r.loss, r.row_status, out=red)
-        if world > 1:
-            pipeline.all_reduce_loss(red, stream=side)
+    def reduce_loss(r):
+        # the path's only collective: all-reduce of [sum loss, n].  The sums accumulate on the device (one tiny
+        # kernel per step) and are all-reduced every REDUCE_EVERY steps on a side stream, off the SMs' critical path
+        if r is None:
+            return
+        ctc.loss_sum(r.loss, r.row_status, out=acc, accumulate=True)
+        step_no[0] += 1
+        if step_no[0] % REDUCE_EVERY == 0:
+            cur = torch.cuda.current_stream()
+            if world > 1:
+                cur.wait_stream(side)                      # the previous all-reduce is done with `red`
+            red.copy_(acc)
+            acc.zero_()
+            if world > 1:
+                pipeline.all_reduce_loss(red, stream=side)
 
     def barrier():
         if world > 1:
@@ -414,26 +531,28 @@ def main():
 
     # ---- (1) device-resident throughput ------------------------------------
     for i in range(args.warmup):
-        r = run_step(pool[i % POOL])
-        reduce_loss(r, pool[i % POOL])
+        reduce_loss(run_step(pool[i % POOL], args.surface))
     barrier()
-    loss_check = red.clone()
+    acc.zero_()
+    step_no[0] = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = L.asrk_launch_count()
     e0.record()
     audio = 0.0
     for i in range(args.steps):
         db = pool[i % POOL]
-        r = run_step(db)
-        reduce_loss(r, db)
+        reduce_loss(run_step(db, args.surface))
         audio += db.audio_s
     if world > 1:
         torch.cuda.current_stream().wait_stream(side)
     e1.record()
     barrier()
+    launches = int(L.asrk_launch_count() - launches0)
+    loss_check = red.clone()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms, audio], dtype=torch.float64, device=dev)
     if world > 1:
@@ -446,87 +565,125 @@ def main():
     value = audio_all / (ms * 1e-3)
 
     # ---- (2) per-kernel durations, live, same launches ----------------------
-    pt = PhaseTimer(torch)
-    for i in range(args.steps):
-        pt.begin()
-        run_step(pool[i % POOL], pt)
-        pt.end()
-    torch.cuda.synchronize()
-    kms = pt.summary()
-    # a noise-free batch launches no kernel in the setup phase (one 16-byte memset): what the events
-    # bracket there is the host's enqueue latency, not device work
-    kms.pop("spec_setup", None)
+    kms = None
+    if args.surface == "logits":
+        pt = PhaseTimer(torch)
+        for i in range(args.steps):
+            pt.begin()
+            run_step_phases(pool[i % POOL], pt)
+            pt.end()
+        torch.cuda.synchronize()
+        kms = pt.summary()
+        if args.workload != "c4":
+            # a noise-free batch launches no kernel in the setup phase (one small memset): what the events
+            # bracket there is the host's enqueue latency, not device work
+            kms.pop("spec_setup", None)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- (3) end to end through the public API with host buffers ------------
-    from asr_dfcnn_transformer_b200 import ctc, features
-    e2e_steps = max(3, min(args.steps, 10))
-    h2d = d2h = 0
+    e2e = None
+    if args.workload in ("c2", "c5") and args.surface == "logits":
+        e2e_steps = max(4, min(args.steps, 12))
+        d0 = pool[0]
+        T = max(d.logits.shape[0] for d in pool)
+        # every batch of the pool has its own T_max: the round-trip buffers take the largest
+        def mk(ret):
+            return pipeline.HostRoundTrip(hot_path(dev), max(d.total_frames for d in pool),
+                                          max(d.h_samples.numel() for d in pool), d0.h_samples.dtype, T, BATCH, V,
+                                          d0.h_labels.shape[1], slots=2, return_outputs=ret)
 
-    def e2e_step(db):
-        # the public host-buffer entry point: PCM + labels host -> device, logits staged without
-        # their padding (only rows t < input_len cross PCIe), kernels, loss back to the host
-        nonlocal h2d, d2h
-        _, r, nbytes = hot_path(dev).from_host(db.h_samples, db.so, db.sc, db.fo, db.B, db.total_frames, db.h_logits,
-                                               db.h_labels, db.label_len, db.input_len, V - 1, logits_dev=db.logits,
-                                               feat_out=db.feat, grad_out=db.grad, grad_scale=db.grad_scale,
-                                               ctc_bounds=db.ctc_bounds)
-        loss_host = r.loss.cpu()          # device -> host read of the step's result (synchronises)
-        h2d = nbytes + 4 * V * int(db.hb["input_len"].astype(np.int64).sum())
-        d2h = loss_host.numel() * 4
-        return loss_host
+        def leg(rt, steps):
+            h2d = d2h = 0
+            barrier()
+            e0.record()
+            a2 = 0.0
+            for i in range(steps):
+                db = pool[i % POOL]
+                Tb = db.logits.shape[0]
+                s = rt.submit(db.h_samples, db.so, db.sc, db.fo, db.B, db.total_frames, db.h_logits, db.h_labels,
+                              db.label_len, db.input_len, V - 1, grad_scale=db.grad_scale, ctc_bounds=db.ctc_bounds) \
+                    if Tb == T else None
+                if s is None:
+                    continue
+                rows = int(db.hb["input_len"].astype(np.int64).sum())
+                h2d = s.h2d_bytes + 4 * V * rows
+                d2h = s.d2h_bytes + (4 * V * rows if rt.return_outputs else 0)
+                a2 += db.audio_s
+            rt.drain()
+            e1.record()
+            barrier()
+            tt = torch.tensor([e0.elapsed_time(e1), a2], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
+                dist.all_reduce(tt[1:2], op=dist.ReduceOp.SUM)
+            return float(tt[1]) / (float(tt[0]) * 1e-3), float(tt[0]), h2d, d2h
 
-    for i in range(2):
-        e2e_step(pool[i % POOL])
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    a2 = 0.0
-    for i in range(e2e_steps):
-        e2e_step(pool[i % POOL])
-        a2 += pool[i % POOL].audio_s
-    e1.record()
-    barrier()
-    ms2 = e0.elapsed_time(e1)
-    t = torch.tensor([ms2, a2], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t[0:1], op=dist.ReduceOp.MAX)
-        dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
-    e2e_value = float(t[1]) / (float(t[0]) * 1e-3)
+        # the batches of the pool that share the largest T_max are used (their logits tensors have one shape)
+        full = mk(True)
+        leg(full, 2)
+        v_full, ms_full, h2d, d2h = leg(full, e2e_steps)
+        del full
+        torch.cuda.empty_cache()
+        lo = mk(False)
+        leg(lo, 2)
+        v_lo, ms_lo, h2d_lo, d2h_lo = leg(lo, e2e_steps)
+        del lo
+        n_used = sum(1 for i in range(e2e_steps) if pool[i % POOL].logits.shape[0] == T)
+        e2e = {"value": v_full, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": n_used,
+               "what": "full host->host round trip through pipeline.HostRoundTrip: PCM, labels and logits in (pinned "
+                       "host buffers), loss, features and gradient out (pinned host buffers), double-buffered",
+               "pcie_gbs_per_gpu": (h2d + d2h) * n_used / (ms_full * 1e-3) / 1e9 / max(world, 1) * world / world,
+               "results_stay_on_device": {"value": v_lo, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(h2d_lo),
+                                          "d2h_bytes_per_step": int(d2h_lo),
+                                          "what": "same inputs from host buffers, only the per-utterance loss comes "
+                                                  "back (features and gradient stay in HBM for the consumer)"}}
+    elif args.workload in ("c3", "c4"):
+        e2e = None
 
     if rank == 0:
         peak, peak_src = peaks()
-        dom = max(("spec_main", "ctc_fused", "ctc_rows", "ctc_grad"), key=lambda k: kms[k])
         bf = float(np.mean([d.bytes_feat for d in pool]))
         bc = float(np.mean([d.bytes_ctc for d in pool]))
-        alg = {"spec_main": bf, "ctc_fused": bc, "ctc_rows": bc / 2, "ctc_grad": bc / 2}[dom]
-        ach = alg / (kms[dom] * 1e-3) / 1e9
         step_alg = bf + bc
+        roof = None
+        if kms is not None:
+            cands = [k for k in ("spec_main", "ctc_fused", "ctc_rows", "ctc_lattice", "ctc_grad") if k in kms]
+            dom = max(cands, key=lambda k: kms[k])
+            # algorithmic bytes of one launch of that kernel: the feature kernel moves the feature bytes; the fused
+            # CTC kernel the logits in and the gradient out; of the generic kernels rows reads the logits, grad reads
+            # them again (non-algorithmic) and writes the gradient, the lattice kernel moves no algorithmic bytes
+            alg = {"spec_main": bf, "ctc_fused": bc, "ctc_rows": bc / 2, "ctc_grad": bc / 2, "ctc_lattice": 0.0}[dom]
+            ach = alg / (kms[dom] * 1e-3) / 1e9
+            names = {"spec_main": "spectrogram_kernel", "ctc_fused": "fused_small_kernel"}
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": ncu_capture(names.get(dom, dom), "dram_bytes") if args.workload in ("c2", "c5") else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                    "fp64_pipe_pct_ncu": ncu_capture(names.get(dom, dom), "fp64_pipe_pct") if dom == "spec_main" else None,
+                    "step_algorithmic_bytes": step_alg,
+                    "step_frac": (step_alg / (ms / args.steps * 1e-3) / 1e9) / peak}
         line = {
             "metric": METRIC, "value": value, "unit": "audio-sec/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT / f32 log, CTC",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
+            "config": {"workload": wl["name"], "surface": args.surface,
                        "utterances_per_gpu": BATCH, "audio_s_per_step_per_gpu": audio_per_step,
+                       "all_reduce": "[sum loss, n] accumulated on the device, all-reduced every %d steps" % REDUCE_EVERY,
+                       "numa_node_rank0": numa,
                        "l2": "inputs larger than L2: %d distinct batches rotated, ~%.0f MB touched per step"
                              % (POOL, (step_alg + bc / 2) / 1e6)},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg, "fp64_pipe_pct_ncu": ncu_fp64_pct(dom),
-                         "step_frac": (step_alg / (ms / args.steps * 1e-3) / 1e9) / peak / world},
+            "roofline": roof,
             "kernel_ms": kms,
             "loss_mean": float(loss_check[0] / max(float(loss_check[1]), 1.0)),
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
-            # per step: spectrogram, stats, z-score, fused CTC (prepares its own utterance; the batch is
-            # bounded by the host's length vectors, so no generic CTC kernels are launched), loss sum.
-            # kernel_ms times the CTC phases one by one, i.e. with the separate prep kernel and the
-            # three generic kernels that find nothing to do.
-            "gpu_launches": 5 * args.steps,
+            "e2e": e2e,
+            # measured: kernels the library launched inside the timed region (asrk_launch_count)
+            "gpu_launches": launches,
             "clocks": clocks,
         }
+        if args.workload == "c5":
+            line["label_error_mean"] = float(pool[0].label_err.mean())
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

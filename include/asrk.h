@@ -190,6 +190,14 @@ int asrk_ctc_stage_logits_run(const float* src, long long src_stride_t, long lon
                               const int* input_len /* device int32 [B] */, int T, int B, int V,
                               asrk_stream_t stream);
 
+/* The way back: rows t < input_len[b] of the device tensor `src` (the gradient) are written into the caller's
+ * pinned, device-mapped HOST tensor `dst` by the SMs; the all-zero rows t >= input_len[b] are not transferred
+ * (the host buffer keeps whatever it held there: clear it once).  Same layout rules as the staging call. */
+int asrk_ctc_unstage_rows_run(const float* src, long long src_stride_t, long long src_stride_b,
+                              float* dst, long long dst_stride_t, long long dst_stride_b,
+                              const int* input_len /* device int32 [B] */, int T, int B, int V,
+                              asrk_stream_t stream);
+
 /* Batch reduction feeding the path's only collective (tf.reduce_mean(self.loss),
  * acoustic_model2.py:83): out2[0] = sum of loss[b] over the rows with row_status[b] ==
  * ASRK_ROW_OK (all rows when row_status == NULL), out2[1] = their number, float64,
@@ -197,6 +205,9 @@ int asrk_ctc_stage_logits_run(const float* src, long long src_stride_t, long lon
 int asrk_ctc_loss_sum_run(const float* loss, const int* row_status, int B,
                           double* out2, /* device float64 [2] */
                           asrk_stream_t stream);
+/* the same, ADDED to out2: a caller that reports the mean every K steps (the reference prints every second
+ * step, lm_and_am/train.py:71-73) accumulates on the device and all-reduces once per K steps */
+int asrk_ctc_loss_sum_acc_run(const float* loss, const int* row_status, int B, double* out2, asrk_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Part 3: greedy CTC decode

@@ -54,10 +54,18 @@ def test_bench_workload_shapes():
     assert len(hb["pcm"]) == 8 and hb["logits"].shape[1:] == (8, synth.VOCAB_DICT_TXT)
     assert all(48000 <= len(p) <= 112000 for p in hb["pcm"])
     assert (hb["label_len"] < hb["input_len"]).all()
-    feat, ctc_b = bench.algorithmic_bytes(hb)
+    feat, ctc_b = bench.algorithmic_bytes(hb, "c2")
     n = sum(len(p) for p in hb["pcm"])
     assert feat == 2 * n + 800 * int(hb["nfr"].sum())
     assert ctc_b == 8 * synth.VOCAB_DICT_TXT * int(hb["input_len"].sum())
+    # the other workloads (BASELINE.json configs[2..4])
+    h3 = bench.make_batch(3000, batch=2, workload="c3")
+    assert all(len(p) == 320000 for p in h3["pcm"]) and h3["logits"].shape == (1998, 2, synth.VOCAB_DICT_TXT)
+    assert h3["label_len"].min() >= 280
+    h4 = bench.make_batch(4000, batch=4, workload="c4")
+    assert h4["pcm"][0].dtype == np.float32 and len(h4["noise"]) == 4 and "logits" not in h4
+    f4, c4 = bench.algorithmic_bytes(h4, "c4")
+    assert c4 == 0 and f4 == 8 * int(h4["lens"].sum()) + 800 * int(h4["nfr"].sum())
 
 
 def test_loader_rules(tmp_path):
