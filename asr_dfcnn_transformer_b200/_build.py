@@ -15,7 +15,9 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # ASRK_LIB_SUFFIX builds / loads a variant library next to the default one (experiments: other -D switches)
 SUFFIX = os.environ.get("ASRK_LIB_SUFFIX", "")
 LIB_PATH = os.path.join(PKG_DIR, "libasrk%s.so" % SUFFIX)
-SOURCES = ["asrk_api.cu", "spectrogram.cu", "noise.cu", "ctc.cu", "post.cu", "logfbank.cu", "color_noise.cu"]
+# ASRK_SPEC_SOURCE: another implementation file of the spectrogram entry points (A/B experiments)
+SOURCES = ["asrk_api.cu", os.environ.get("ASRK_SPEC_SOURCE", "spectrogram.cu"), "noise.cu", "ctc.cu", "post.cu", "logfbank.cu",
+           "color_noise.cu"]
 HEADERS = ["asrk_common.cuh", "asrk_fft.cuh", "asrk_tables.inc", os.path.join("..", "..", "include", "asrk.h")]
 NVCC_FLAGS = (os.environ.get("ASRK_EXTRA_NVCC", "").split()) + [
     "-gencode", "arch=compute_100a,code=sm_100a",

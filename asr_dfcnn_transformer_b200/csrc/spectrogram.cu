@@ -8,41 +8,42 @@
 //     amplified by the z-score) is not reachable with fp32 butterflies on
 //     high-dynamic-range audio, so the 400-point transform runs in fp64 -- B200
 //     has a half-rate fp64 pipe (64 lanes/SM/clk), which is the bound of this
-//     kernel; everything after |X|^2 (sqrt, log, z-score) is fp32.
-//   * ONE persistent kernel, one CTA per SM: kTeams independent teams of five warps.
+//     kernel (register-resident codelets reach > 90 % of it, tools/ubench);
+//     everything after |X|^2 (sqrt, log, z-score) is fp32.
+//   * ONE persistent kernel, one CTA per SM, THREE independent teams of five warps.
 //     A team transforms 16 consecutive frames at a time: lane = (frame, role half), the
 //     two half-warps of warp q own roles q and q + 5 of the 20 x 10 Cooley-Tukey split
 //     of the 200-point complex DFT (400-point real DFT = 200-point complex DFT + real-
 //     input split; both factors twiddle-free prime-factor codelets), so window values
 //     and twiddles are half-warp broadcasts from shared memory and the two passes
 //     exchange through the team's own conflict-free 50 KB fp64 buffer with team-wide
-//     named barriers only.  While one team loads, exchanges or copies out, the others
-//     keep the fp64 pipe busy.
-//   * instruction diet (round 2; the kernel is co-bound by issue slots): fewer fp64
-//     instructions in the codelets (asrk_fft.cuh), a cheaper int16 -> fp64 step (see
-//     ASRK_SPEC_CONV below); 16-byte exchange accesses; the out tile is copied to global memory
-//     and summed for the z-score with 16-byte accesses (lane = (4 bins, row phase));
-//     log(|X| + 1) is one MUFU.SQRT + FFMA + MUFU.LG2 + FMUL; role 0's operand selects
-//     run only in the warp that owns role 0.
+//     named barriers only.  15 transform warps sit 4/4/4/3 on the four schedulers (a
+//     single 10-role team sits 3/3/2/2 and leaves a sixth of the fp64 pipe idle), and
+//     while one team loads, exchanges or copies out, the other two keep the pipe busy.
 //   * a team claims units of 32 consecutive frames of one utterance from an atomic
-//     counter (in utterance order) and stages the PCM of a 16-frame sub-tile with
-//     16-byte cp.async behind the previous sub-tile's second pass (zero-filled past the
-//     end; the noise mix fl32(s + fl32(K n)) is applied on the way in).
-//   * z-score: per-bin sums of every unit are accumulated during the copy-out (fp32,
-//     shifted by the unit's first row so that nothing cancels; un-shifted in fp64, fixed
-//     order: reproducible, no float atomics).  The team that completes an utterance
-//     (release fence one unit late + per-utterance counter: the fence then has nothing to
-//     wait for) turns the unit sums into mean / 1/std inside the kernel; one streaming
-//     kernel with the whole chip's memory parallelism normalises in place behind it
-//     (newest utterances first: their rows are still in L2) and runs next to the CTC
-//     kernel.  Two ways of normalising INSIDE the transform kernel were built and measured
-//     this round (a dedicated z-score warp per CTA fed by TMA bulk copies; one 16-row
-//     chunk per team and sub-tile, also through TMA) -- both parity-green, both slower
-//     than the trailing kernel because the transform is latency bound and every
-//     instruction added to its warps costs more than the HBM round trip it saves
-//     (profiles/r2_spectrogram.md).
+//     counter (in utterance order), stages their PCM with 16-byte cp.async while the
+//     previous unit's last sub-tile is still in flight (zero-filled past the end; the
+//     noise mix fl32(s + fl32(K n)) is applied on the way in), and copies finished
+//     16 x 200 log-magnitude tiles to global memory column-wise: warp q owns bins
+//     40 q .. 40 q + 39, so every store is a full 32-byte sector and every bin's
+//     z-score sums live in exactly one lane.
+//   * z-score: the per-bin sums of every unit are accumulated during the copy-out
+//     (fp32, shifted by the unit's first row so that nothing cancels) and written
+//     un-shifted in fp64 per unit (fixed order: reproducible, no float atomics).  A tiny kernel turns the tile partials of every utterance into mean and
+//     1/std, and a purely streaming kernel with the whole chip's memory parallelism
+//     normalises in place (the rows are largely still in L2).  [Measured alternatives:
+//     an in-kernel z-score by the CTA that retires an utterance's last tile -- one
+//     CTA's 448 threads cannot keep enough L2 requests in flight, 40 us per utterance;
+//     per-tile release fence + counter in the helpers -- the membar costs 19 us.]
+//
+// Round 2: the codelets lost 12 % of their fp64 instructions (asrk_fft.cuh: 32-instruction DFT5, 14-instruction
+// split).  A rewrite of this kernel around an "instruction diet" (one-DFMA / I2F sample conversion, 16-byte
+// exchange and copy-out accesses, role-0 selects confined to one warp, per-sub-tile PCM staging, z-score inside
+// the kernel through TMA bulk copies -- first by a dedicated warp, then spread over the teams) executed 32 %
+// fewer instructions, was parity-green, and was SLOWER in every context (A/B in profiles/r2_spectrogram.md):
+// the kernel is bound by shared-memory wavefronts and dependent-issue latency, not by issue slots, so this
+// layout was kept.
 #include <math.h>
-#include <stdlib.h>
 
 #include "asrk_common.cuh"
 #include "asrk_fft.cuh"
@@ -50,44 +51,39 @@
 namespace asrk {
 namespace spec {
 
+constexpr int kTeams = 3;
 constexpr int kTeamWarps = 5;
 constexpr int kTeamThreads = kTeamWarps * 32;        // 160
+constexpr int kThreads = kTeams * kTeamThreads;      // 480
 constexpr int kSub = 16;                             // frames per sub-tile (= lanes of a half-warp)
-constexpr int kUnit = 32;                            // frames per claimed unit
 constexpr int kHop = 160, kFrameLen = 400, kBins = 200;
-constexpr int kOutStride = 204;                      // padded, 16-byte aligned row of the out tile
-constexpr int kSubHopRows = kSub + 2;                // (kSub-1)*160+400 samples
+constexpr int kOutStride = 201;                      // padded row of the out tile
 // hop rows stay 16-byte aligned (for 16-byte async copies) and are padded by 16
 // bytes: frame f reads word 84 f + c -> the 16 frames of a half-warp hit 8 distinct
 // banks (2-way conflict on the 20 sample loads of a thread per sub-tile).
 constexpr int kHopWordsI16 = 84;                     // 80 words of int16 pairs + 4 pad
 constexpr int kHopWordsF32 = 164;                    // 160 words + 4 pad
 constexpr int kTabDoubles = 1200;                    // window[400] | tw[r][k1] | P[k]
-constexpr int kMaxBatch = 1023;                      // utterances per launch (unit prefix in smem)
-constexpr int kZRows = 16;                           // rows per z-score chunk
-constexpr int kZBytes = kZRows * kBins * 4;          // 12 800
+constexpr int kMaxBatch = 2047;                      // utterances per launch (unit prefix in smem)
+constexpr int kUttCache = 512;                       // utterances whose constants are cached in smem
 
 __device__ const double g_tab[kTabDoubles] = {
 #include "asrk_tables.inc"
 };
 
-struct __align__(16) cplx16 {   // cplx with the alignment that makes exchange accesses LDS/STS.128
-    double x, y;
-};
-
-struct Meta {               // one unit, written by the team's first thread one unit ahead
+struct Meta {               // one tile, written by helper thread 0
     int valid;
     int b;
     int f0;
-    int ntiles_b;            // units of utterance b
-    int tile;                // unit index (row of the partial sums)
-    float gain;
-    // raw per-utterance constants, copied global -> shared with cp.async (no registers, no stall of the
-    // claiming thread); complete at the team's next "PCM is in place" barrier
-    long long fo, fo1;       // frame_offsets[b], frame_offsets[b + 1]
+    int nf;
+    int ntiles_b;            // tiles of utterance b
+    int tile;                // global tile index (row of the partial sums)
     long long sbase;         // first sample of the utterance in the ragged buffer
     long long nsamp;         // samples of the utterance
-    long long row0;          // out_row_offsets[b] (when given)
+    long long row0;          // output row of frame 0 of the utterance
+    long long nfr;           // frames of the utterance
+    float half_mag;
+    float gain;
 };
 
 struct Params {
@@ -100,36 +96,28 @@ struct Params {
     const long long* out_row_offsets;
     int batch;
     int mode;
-    int zscore_in_kernel;
     float* out;
     // workspace
-    int* counters;           // [0] next unit                                   (zeroed per launch)
-    int* done;               // [B] published units per utterance               (zeroed per launch)
-    int* tile_off_g;         // [B + 1] first unit of every utterance (written by CTA 0)
-    double2* partials;       // [units][200]: per-unit column sums (sum y, sum y^2)
+    int* counters;           // [0] next tile (zeroed per launch)
+    int* tile_off_g;         // [B + 1] first tile of every utterance (written by CTA 0)
+    double2* partials;       // [tiles][200]: per-tile column sums (sum y, sum y^2)
     float* stats;            // [B][3][200]: mean (hi, lo), 1/std
 };
 
 struct WsLayout {
-    size_t counters, done, zero_bytes, tile_off, gains, stats, partials, total;
+    size_t counters, tile_off, gains, stats, partials, total;
 };
-
-static size_t max_units(int batch, long long total_frames) {
-    return (size_t)(total_frames / kUnit) + (size_t)batch + 1;
-}
 
 static WsLayout ws_layout(int batch, long long total_frames) {
     WsLayout l;
     size_t o = 0;
-    // counters | done are contiguous: one memset per launch
     l.counters = o;  o = align_up(o + sizeof(int) * 4, 256);
-    l.done = o;      o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
-    l.zero_bytes = o;
     l.tile_off = o;  o = align_up(o + sizeof(int) * (size_t)(batch + 1), 256);
     l.gains = o;     o = align_up(o + sizeof(float) * (size_t)batch, 256);
     l.stats = o;     o = align_up(o + sizeof(float) * 3 * kBins * (size_t)batch, 256);
     l.partials = o;
-    o = align_up(o + sizeof(double2) * kBins * max_units(batch, total_frames), 256);
+    const size_t max_tiles = (size_t)(total_frames / kSub) + (size_t)batch + 1;
+    o = align_up(o + sizeof(double2) * kBins * max_tiles, 256);
     l.total = o;
     return l;
 }
@@ -137,51 +125,38 @@ static WsLayout ws_layout(int batch, long long total_frames) {
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
-// int16 sample pair -> fp64.  Two variants (ASRK_SPEC_CONV, measured in profiles/r2_spectrogram.md):
-//   1  sign-extend + I2F.F64.S32 (conversion on the XU pipe), window multiply = DMUL
-//   0  no conversion instruction: the pair is biased to unsigned with one XOR and each half is
-//      byte-permuted into mantissa bits 32..47 of 2^20 (d = 2^20 + 2^15 + x exactly, low word zero);
-//      x w = d w - (2^20 + 2^15) w is ONE DFMA with the constant tabulated next to the window.
-#ifndef ASRK_SPEC_CONV
-#define ASRK_SPEC_CONV 1
-#endif
-#ifndef ASRK_SPEC_TWGEN
-#define ASRK_SPEC_TWGEN 0
-#endif
-#ifndef ASRK_SPEC_PGEN
-#define ASRK_SPEC_PGEN 0
-#endif
-#if ASRK_SPEC_CONV == 0
-constexpr double kMagic = 1081344.0;                 // 2^20 + 2^15
-#else
-constexpr double kMagic = 0.0;
-#endif
+__device__ __forceinline__ double i16_to_f64(int v) {
+    // exact int -> double with one integer op and one DADD (the I2F.F64 path is
+    // a quarter-rate conversion): 2^52 + 2^31 + v has v in its low mantissa bits.
+    return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)v)) - 4503601774854144.0;
+}
 
-// log(|X| * mag + 1) from p4 = 4 |X|^2, natural log (wav_util.py:76,107,111), fp32: lg2.approx
-// returns exponent + log2(mantissa) with an absolute error of 2^-22 on the mantissa part, i.e. the
-// result is as good as its own float32 rounding (ulp 1e-6 at log|X| ~ 15; tolerance 1e-4 max(|ref|,1)).
+// log(|X| * mag + 1) from p4 = 4 |X|^2, natural log (wav_util.py:76,107,111), fp32:
+// v = 1 + m is split into 2^e * f exactly; lg2.approx on f in [1,2) has an absolute
+// error of 2^-22, so the result carries an absolute error of ~2e-7 at any magnitude
+// (the tolerance is 1e-4 * max(|ref|, 1)); sqrt.approx is good to 2^-23 relative.
 __device__ __forceinline__ float log_mag(float p4, float half_mag) {
-    float r, l2;
+    float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p4));
     const float v = fmaf(r, half_mag, 1.0f);
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(v));
-    return l2 * 0.69314718056f;
+    const int vi = __float_as_int(v);
+    const float e = (float)((vi >> 23) - 127);
+    const float f = __int_as_float((vi & 0x007fffff) | 0x3f800000);
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(f));
+    return (e + l2) * 0.69314718056f;
 }
 
-__device__ __forceinline__ void stg4_hint(float* p, float4 v, uint64_t policy) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w), "l"(policy)
-                 : "memory");
-}
-// Synchronous staging of the PCM of one sub-tile (unaligned utterances, and the noise mix:
+// Synchronous staging of one PCM tile (unaligned utterances, and the noise mix:
 // fl32(signal + fl32(K * noise)) is formed on the way in).
-template <bool F32>
-__device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, int frame0, uint32_t* dst, int hth) {
-    const long long t0 = (long long)frame0 * kHop;   // utterance-local first sample of the sub-tile
+template <bool F32, int kHopRows>
+__device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, uint32_t* dst, int hth) {
+    constexpr int kHelperThreads = kTeamThreads;
+    const long long t0 = (long long)m.f0 * kHop;   // utterance-local first sample of the tile
     if (!F32) {
         const short* src = reinterpret_cast<const short*>(p.samples) + m.sbase;
-        constexpr int kChunks = kSubHopRows * 20;   // 16-byte chunks of 8 samples
-        for (int c = hth; c < kChunks; c += kTeamThreads) {
+        constexpr int kChunks = kHopRows * 20;   // 16-byte chunks of 8 samples
+        for (int c = hth; c < kChunks; c += kHelperThreads) {
             const long long us = t0 + (long long)c * 8;
             uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
             const short* g = src + us;
@@ -206,8 +181,8 @@ __device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, in
         const float* src = reinterpret_cast<const float*>(p.samples) + m.sbase;
         const float* nz = p.noise ? p.noise + m.sbase : nullptr;
         const float K = m.gain;
-        constexpr int kChunks = kSubHopRows * 40;   // 16-byte chunks of 4 samples
-        for (int c = hth; c < kChunks; c += kTeamThreads) {
+        constexpr int kChunks = kHopRows * 40;   // 16-byte chunks of 4 samples
+        for (int c = hth; c < kChunks; c += kHelperThreads) {
             const long long us = t0 + (long long)c * 4;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             const float* g = src + us;
@@ -234,25 +209,26 @@ __device__ __forceinline__ void load_pcm_tile(const Params& p, const Meta& m, in
                 }
             }
             float* d = reinterpret_cast<float*>(dst) + (c / 40) * kHopWordsF32 + (c % 40) * 4;
-            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float2*>(d) = make_float2(v[0], v[1]);
+            *reinterpret_cast<float2*>(d + 2) = make_float2(v[2], v[3]);
         }
     }
 }
 
-// Asynchronous staging of one sub-tile (no arithmetic on the way): 16-byte LDGSTS
+// Asynchronous staging of one PCM tile (no arithmetic on the way): 16-byte LDGSTS
 // copies into the padded hop rows, zero-filled past the end of the utterance.
 // Needs the utterance start to be 16-byte aligned.
-template <bool F32>
-__device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta& m, int frame0, uint32_t* dst,
-                                                     int hth) {
-    const long long t0 = (long long)frame0 * kHop;
+template <bool F32, int kHopRows>
+__device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta& m, uint32_t* dst, int hth) {
+    constexpr int kHelperThreads = kTeamThreads;
+    const long long t0 = (long long)m.f0 * kHop;
     constexpr int kPerChunk = F32 ? 4 : 8;             // samples per 16 bytes
     constexpr int kChunksPerHop = kHop / kPerChunk;    // 40 / 20
-    constexpr int kChunks = kSubHopRows * kChunksPerHop;
+    constexpr int kChunks = kHopRows * kChunksPerHop;
     constexpr int kBytes = F32 ? 4 : 2;
     constexpr int kRowWords = F32 ? kHopWordsF32 : kHopWordsI16;
     const char* src = reinterpret_cast<const char*>(p.samples) + m.sbase * kBytes;
-    for (int c = hth; c < kChunks; c += kTeamThreads) {
+    for (int c = hth; c < kChunks; c += kHelperThreads) {
         const long long us = t0 + (long long)c * kPerChunk;
         const long long rem = (m.nsamp - us) * kBytes;
         const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
@@ -261,108 +237,98 @@ __device__ __forceinline__ void issue_pcm_tile_async(const Params& p, const Meta
     }
 }
 
-// unit -> utterance: the last b with tile_off[b] <= unit that owns units
-__device__ __forceinline__ int find_utterance(const int* tile_off, int batch, int tile) {
-    int lo = 0, hi = batch - 1;
+// Tile -> utterance, frame range and the utterance's constants (helper thread 0).
+// per-utterance constants, staged once per CTA when the batch is small enough, so that a
+// claim costs a binary search and a few shared-memory reads instead of a global round trip
+struct UttCache {
+    long long sbase[kUttCache];
+    long long nsamp[kUttCache];
+    long long row0[kUttCache];
+    int nfr[kUttCache];
+    float gain[kUttCache];
+};
+
+__device__ void fill_meta(const Params& p, const int* tile_off, const UttCache* uc, int tile, int kTile, Meta& m) {
+    int lo = 0, hi = p.batch - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
     }
-    while (tile >= tile_off[lo + 1]) ++lo;          // skip utterances without units
-    return lo;
-}
-
-// Unit -> utterance and frame range (binary search in shared memory) by the team's first thread, one
-// unit ahead; the utterance's constants follow as 8-byte cp.async copies (L2 hits) that nobody waits
-// for before the team's next "PCM is in place" barrier.
-__device__ __forceinline__ void fill_meta(const Params& p, const int* tile_off, int tile, Meta& m) {
-    const int b = find_utterance(tile_off, p.batch, tile);
-    cp_async8(&m.fo, p.frame_offsets + b, 8);
-    cp_async8(&m.fo1, p.frame_offsets + b + 1, 8);
-    cp_async8(&m.sbase, p.sample_offsets + b, 8);
-    cp_async8(&m.nsamp, p.sample_counts + b, 8);
-    if (p.out_row_offsets) cp_async8(&m.row0, p.out_row_offsets + b, 8);
-    if (p.noise && p.gain) cp_async4(&m.gain, p.gain + b, 4);
-    else m.gain = 0.0f;
+    int b = lo;
+    while (tile >= tile_off[b + 1]) ++b;          // skip utterances without tiles
     m.valid = 1;
     m.tile = tile;
     m.b = b;
     m.ntiles_b = tile_off[b + 1] - tile_off[b];
-    m.f0 = (tile - tile_off[b]) * kUnit;
-}
-
-// mean and 1/std of utterance b from its units' partial sums, by the 160 threads of one team
-// (sklearn.preprocessing.scale, wav_util.py:79: std with ddof = 0, std < 10 eps -> 1)
-__device__ __forceinline__ void finalize_stats(const Params& p, const int* tile_off, int b, int tt) {
-    const int t_lo = tile_off[b], t_hi = tile_off[b + 1];
-    const long long nfr = p.frame_offsets[b + 1] - p.frame_offsets[b];
-    for (int k = tt; k < kBins; k += kTeamThreads) {
-        double a1 = 0.0, a2 = 0.0;
-#pragma unroll 4
-        for (int q = t_lo; q < t_hi; ++q) {               // fixed order: reproducible
-            const double2 v = __ldcg(p.partials + (size_t)q * kBins + k);
-            a1 += v.x;
-            a2 += v.y;
-        }
-        const double n = (double)(nfr > 0 ? nfr : 1);
-        const double mean = a1 / n;
-        double var = a2 / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        double sd = sqrt(var);
-        if (sd < 10.0 * 2.220446049250313e-16) sd = 1.0;
-        const float mh = (float)mean;
-        float* st = p.stats + (size_t)b * 3 * kBins;
-        __stcg(st + k, mh);
-        __stcg(st + kBins + k, (float)(mean - (double)mh));
-        __stcg(st + 2 * kBins + k, (float)(1.0 / sd));
+    m.f0 = (tile - tile_off[b]) * kTile;
+    if (uc != nullptr) {
+        m.nfr = uc->nfr[b];
+        m.sbase = uc->sbase[b];
+        m.nsamp = uc->nsamp[b];
+        m.row0 = uc->row0[b];
+        m.gain = uc->gain[b];
+    } else {
+        const long long fo = p.frame_offsets[b];
+        m.nfr = p.frame_offsets[b + 1] - fo;
+        m.sbase = p.sample_offsets[b];
+        m.nsamp = p.sample_counts[b];
+        m.row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
+        m.gain = (p.noise && p.gain) ? p.gain[b] : 0.0f;
     }
+    const long long rem = m.nfr - m.f0;
+    m.nf = rem < kTile ? (int)rem : kTile;
+    m.half_mag = 0.5f * ((p.mode == ASRK_SPEC_ASRT) ? (1.0f / (float)m.nsamp) : 1.0f);
 }
 
-template <bool F32, int kTeams, bool kSepOut>
+// ---------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------
+template <bool F32>
 struct Cfg {
-    static constexpr int kPcmWords = kSubHopRows * (F32 ? kHopWordsF32 : kHopWordsI16);
-    static constexpr int kExchBytes = 200 * kSub * 16;                       // 51 200
-    static constexpr int kOutBytes = kSepOut ? kSub * kOutStride * 4 : 0;    // 13 056
-    static constexpr int kTeamBytes = kExchBytes + kPcmWords * 4 + kOutBytes;
-    static constexpr int kThreads = kTeams * kTeamThreads;
-    static constexpr size_t smem_bytes() {
-        return (size_t)(200 * 32 + 3200 + 3200) + sizeof(int) * (kMaxBatch + 1) + (size_t)kTeams * kTeamBytes + 16;
-    }
+    // frames per claimed unit: 32 (two sub-tiles) for int16; 16 for float32 so that the
+    // staging buffers of three teams still fit next to the exchange buffers
+    static constexpr int kUnit = F32 ? 16 : 32;
+    static constexpr int kHopRows = kUnit + 2;                   // (kUnit-1)*160+400 samples
+    static constexpr int kPcmWords = kHopRows * (F32 ? kHopWordsF32 : kHopWordsI16);
 };
 
 __device__ __forceinline__ void team_bar(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kTeamThreads) : "memory");
 }
 
-// ---------------------------------------------------------------------------
-// main kernel
-// ---------------------------------------------------------------------------
-template <bool F32, int kTeams, bool kSepOut>
-// (registers are allocated per warp in units of 512: 480 threads cannot have more than 128 each)
-__global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spectrogram_kernel(Params p) {
-    using C = Cfg<F32, kTeams, kSepOut>;
-    constexpr int kPcmWords = C::kPcmWords;
-    constexpr int kThreads = C::kThreads;
-    constexpr int kRowWords = F32 ? kHopWordsF32 : kHopWordsI16;
+template <bool F32>
+__global__ void __launch_bounds__(kThreads, 1) spectrogram_kernel(Params p) {
+    constexpr int kUnit = Cfg<F32>::kUnit;
+    constexpr int kHopRows = Cfg<F32>::kHopRows;
+    constexpr int kPcmWords = Cfg<F32>::kPcmWords;
+    constexpr int kExchBytes = 200 * kSub * (int)sizeof(cplx);                // 51 200
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tabW = reinterpret_cast<double*>(smem_raw);                       // [200] x (w0, w1, c0, c1)
-    cplx16* tabTall = reinterpret_cast<cplx16*>(tabW + 800);                  // [10][20]
-    cplx16* tabP = tabTall + 200;                                             // [200]
-    int* tile_off = reinterpret_cast<int*>(tabP + 200);                       // [kMaxBatch + 1]
-    unsigned char* team_base = reinterpret_cast<unsigned char*>(tile_off + kMaxBatch + 1);
+    double* tab = reinterpret_cast<double*>(smem_raw);                        // [1200]
+    int* tile_off = reinterpret_cast<int*>(tab + kTabDoubles);                // [kMaxBatch + 1]
+    UttCache* ucache = reinterpret_cast<UttCache*>(tile_off + kMaxBatch + 1);
+    unsigned char* team_base = reinterpret_cast<unsigned char*>(ucache + 1);
     __shared__ Meta meta[kTeams][2];
-    __shared__ int s_fin[kTeams];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    const int team = warp / kTeamWarps, q = warp - team * kTeamWarps;
+    const int tt = tid - team * kTeamThreads;
+    cplx* exch = reinterpret_cast<cplx*>(team_base + (size_t)team * (kExchBytes + kPcmWords * 4));   // [200][16]
+    uint32_t* pcm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(exch) + kExchBytes);
+    float* ot = reinterpret_cast<float*>(exch);                               // out tile [16][201] aliases the exchange
 
-    for (int i = tid; i < 400; i += kThreads) {
-        const double w = g_tab[i];
-        const int m = i >> 1, e = i & 1;
-        tabW[4 * m + e] = w;
-        tabW[4 * m + 2 + e] = -kMagic * w;
+    for (int i = tid; i < kTabDoubles; i += kThreads) tab[i] = g_tab[i];
+    const UttCache* uc = (p.batch <= kUttCache) ? ucache : nullptr;
+    if (uc != nullptr) {
+        for (int b = tid; b < p.batch; b += kThreads) {
+            const long long fo = p.frame_offsets[b];
+            ucache->nfr[b] = (int)(p.frame_offsets[b + 1] - fo);
+            ucache->sbase[b] = p.sample_offsets[b];
+            ucache->nsamp[b] = p.sample_counts[b];
+            ucache->row0[b] = p.out_row_offsets ? p.out_row_offsets[b] : fo;
+            ucache->gain[b] = (p.noise && p.gain) ? p.gain[b] : 0.0f;
+        }
     }
-    for (int i = tid; i < 800; i += kThreads) reinterpret_cast<double*>(tabTall)[i] = g_tab[400 + i];
     if (warp == 0) {
         // exclusive scan of ceil(n_frames / kUnit) over the utterances
         int carry = 0;
@@ -388,16 +354,8 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     __syncthreads();
     const int total_tiles = tile_off[p.batch];
     const bool want_stats = (p.mode == ASRK_SPEC_FBANK);
-    const bool zin = want_stats && p.zscore_in_kernel;     // statistics finished inside the kernel
     if (blockIdx.x == 0 && want_stats)
         for (int i = tid; i <= p.batch; i += kThreads) p.tile_off_g[i] = tile_off[i];
-
-    const int team = warp / kTeamWarps, q = warp - team * kTeamWarps;
-    const int tt = tid - team * kTeamThreads;
-    cplx16* exch = reinterpret_cast<cplx16*>(team_base + (size_t)team * C::kTeamBytes);   // [200][16]
-    uint32_t* pcm = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(exch) + C::kExchBytes);
-    // out tile [16][204]: its own buffer, or aliased onto the exchange (then two more team barriers guard it)
-    float* ot = kSepOut ? reinterpret_cast<float*>(pcm + kPcmWords) : reinterpret_cast<float*>(exch);
 
     // lane -> (frame of the sub-tile, role): the two half-warps of warp q own roles q, q + 5
     const int f = lane & 15;
@@ -405,13 +363,12 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
     const bool j0 = (r == 0);
     const int k1a = lane_k1a(r), k1b = lane_k1b(r);
     const int kb_hi = j0 ? -110 : r;          // bin of slot s >= 6 is kb_hi + 20 s
-    const double2* tabW2 = reinterpret_cast<const double2*>(tabW);
-    const cplx16* tabT = tabTall + r * 20;
+    const double2* tabW2 = reinterpret_cast<const double2*>(tab);
+    const cplx* tabT = reinterpret_cast<const cplx*>(tab + 400) + r * 20;
+    const cplx* tabP = reinterpret_cast<const cplx*>(tab + 800);
     const bool mix = (p.noise != nullptr);
-    // copy-out geometry: lane -> (float4 column 10 q + lane / 3, row phase lane % 3)
-    const bool co_act = lane < 30;
-    const int co_c4 = 10 * q + (co_act ? lane / 3 : 0);
-    const int co_ph = co_act ? lane - 3 * (lane / 3) : kSub;   // idle lanes: no rows
+    // the un-normalised rows are read again by the z-score kernel: keep them in L2
+    const uint64_t keep = want_stats ? l2_policy_evict_last() : l2_policy_evict_first();
 
     // unit metadata: claimed and looked up by the team's first thread, one unit ahead
     int next_tile = total_tiles;
@@ -422,228 +379,123 @@ __global__ void __launch_bounds__((Cfg<F32, kTeams, kSepOut>::kThreads), 1) spec
             const int tile = next_tile;
             if (tile < total_tiles) {
                 next_tile = atomicAdd(p.counters, 1);
-                fill_meta(p, tile_off, tile, mn);
+                fill_meta(p, tile_off, uc, tile, kUnit, mn);
             } else {
                 mn.valid = 0;
             }
         }
     };
-    auto stage = [&](const Meta& m, int frame0) {
+    auto stage = [&](const Meta& m) {
         const bool aligned = (((reinterpret_cast<uintptr_t>(p.samples) + m.sbase * (F32 ? 4 : 2)) & 15) == 0);
-        if (!mix && aligned) issue_pcm_tile_async<F32>(p, m, frame0, pcm, tt);
-        else load_pcm_tile<F32>(p, m, frame0, pcm, tt);
+        if (!mix && aligned) issue_pcm_tile_async<F32, kHopRows>(p, m, pcm, tt);
+        else load_pcm_tile<F32, kHopRows>(p, m, pcm, tt);
         cp_async_commit();
     };
-    // publication of a finished unit, one unit late (the fence then finds every store of the unit
-    // acknowledged): the team's first thread counts the unit on its utterance; whoever completes the
-    // utterance makes its statistics (whole team)
-    int pub_b = -1, pub_nt = 0;      // (thread 0) utterance / unit count of the unit to publish
-    auto publish_count = [&]() {     // thread 0, after a team barrier that follows the unit's last store
-        if (tt == 0) {
-            int fin = -1;
-            if (pub_b >= 0) {
-                __threadfence();
-                const int old = atomicAdd(p.done + pub_b, 1);
-                if (old + 1 == pub_nt) { __threadfence(); fin = pub_b; }
-                pub_b = -1;
-            }
-            s_fin[team] = fin;
-        }
-    };
+
     prepare_meta(0);
-    if (tt == 0) { cp_async_commit(); cp_async_wait<0>(); }
     team_bar(team);
-    if (meta[team][0].valid) stage(meta[team][0], meta[team][0].f0);
-    // the un-normalised rows are read again by the z-score: keep them in L2
-    const uint64_t keep = want_stats ? l2_policy_evict_last() : l2_policy_evict_first();
+    if (meta[team][0].valid) stage(meta[team][0]);
     for (int u = 0;; ++u) {
         const Meta& m = meta[team][u & 1];
         if (!m.valid) break;
-        const Meta& mnext = meta[team][(u + 1) & 1];
         cp_async_wait<0>();
-        team_bar(team);                         // P: the first sub-tile's PCM and the unit's constants are in place
-        const long long m_nfr = m.fo1 - m.fo;
-        const int m_nf = (m_nfr - m.f0) < kUnit ? (int)(m_nfr - m.f0) : kUnit;
-        const long long m_row0 = p.out_row_offsets ? m.row0 : m.fo;
-        const float hm = 0.5f * ((p.mode == ASRK_SPEC_ASRT) ? (1.0f / (float)m.nsamp) : 1.0f);
-        const int nsub = (m_nf + kSub - 1) / kSub;
-        // z-score sums of this lane's four bins over the unit, shifted by the unit's first row
-        float4 cS = make_float4(0.f, 0.f, 0.f, 0.f), sS = cS, qS = cS;
-        int fin = -1;
+        team_bar(team);                         // the unit's PCM is in place; everyone is done with unit u - 1
+        prepare_meta((u + 1) & 1);              // (visible to the team after the next barrier)
+        const Meta& mnext = meta[team][(u + 1) & 1];
+        const int nsub = (m.nf + kSub - 1) / kSub;
+        // z-score sums of this lane's bins over the unit: bin 40 q + lane, and 40 q + 32 + lane (lane < 8)
+        float cA = 0.f, sA = 0.f, qA = 0.f, cB = 0.f, sB = 0.f, qB = 0.f;
         for (int sub = 0; sub < nsub; ++sub) {
-            if (sub > 0) {
-                cp_async_wait<0>();
-                team_bar(team);                 // P: the sub-tile's PCM is in place; the previous copy-out is over
-            } else {
-                prepare_meta((u + 1) & 1);      // (flags visible to the team after the next barrier)
-                if (zin) publish_count();
-                // a one-sub-tile unit stages its successor's PCM right behind pass 1: the constants must be there
-                if (nsub == 1 && tt == 0) { cp_async_commit(); cp_async_wait<0>(); }
-            }
             // ---------------- pass 1: window, DFT20 of residue r, twiddle ----------------
             {
                 cplx z[20], y[20];
+                const int F = sub * kSub + f;            // frame inside the unit
 #pragma unroll
                 for (int n1 = 0; n1 < 20; ++n1) {
                     const int hq = n1 / 8;                // hop row offset of sample 2*(10 n1 + r)
-                    const int wq = 10 * (n1 % 8) + r;     // sample-pair index inside the hop
-                    const double2 w2 = tabW2[2 * (10 * n1 + r)];
+                    const int wq = 10 * (n1 % 8) + r;     // int16-pair index inside the hop
+                    double x0, x1;
                     if (!F32) {
-                        const uint32_t w = pcm[(f + hq) * kRowWords + wq];
-#if ASRK_SPEC_CONV == 0
-                        const double2 c2 = tabW2[2 * (10 * n1 + r) + 1];
-                        const uint32_t wb = w ^ 0x80008000u;
-                        const double d0 = __hiloint2double((int)__byte_perm(wb, 0x41300000u, 0x7610), 0);
-                        const double d1 = __hiloint2double((int)__byte_perm(wb, 0x41300000u, 0x7632), 0);
-                        // wav_util.py:71 data_line * w:  x w = (M + x) w - M w, one DFMA per sample
-                        z[n1] = cplx{fma(d0, w2.x, c2.x), fma(d1, w2.y, c2.y)};
-#else
-                        z[n1] = cplx{(double)(int)(short)(w & 0xffffu) * w2.x, (double)((int)w >> 16) * w2.y};
-#endif
+                        const uint32_t w = pcm[(F + hq) * kHopWordsI16 + wq];
+                        x0 = i16_to_f64((int)(short)(w & 0xffffu));
+                        x1 = i16_to_f64((int)(short)(w >> 16));
                     } else {
                         const float2 v = *reinterpret_cast<const float2*>(
-                            reinterpret_cast<const float*>(pcm) + (f + hq) * kRowWords + 2 * wq);
-                        z[n1] = cplx{(double)v.x * w2.x, (double)v.y * w2.y};
+                            reinterpret_cast<const float*>(pcm) + (F + hq) * kHopWordsF32 + 2 * wq);
+                        x0 = (double)v.x;
+                        x1 = (double)v.y;
                     }
+                    const double2 w2 = tabW2[10 * n1 + r];
+                    z[n1] = cplx{x0 * w2.x, x1 * w2.y};   // wav_util.py:71 data_line * w
                 }
                 dft20(z, y);
-                exch[r * kSub + f] = cplx16{y[0].x, y[0].y};
-#if ASRK_SPEC_TWGEN
-                // twiddles W200^(r k1) by recurrence from W200^r: 72 fp64 instructions instead of 18 more
-                // 16-byte table broadcasts (the kernel is shared-memory-wavefront bound before it is fp64 bound)
-                const cplx16 t1l = tabT[1];
-                const cplx t1{t1l.x, t1l.y};
-                cplx tk = t1;
+                exch[r * kSub + f] = y[0];
 #pragma unroll
-                for (int k1 = 1; k1 < 20; ++k1) {
-                    const cplx v = cmul(y[k1], tk);
-                    exch[(k1 * 10 + r) * kSub + f] = cplx16{v.x, v.y};
-                    if (k1 < 19) tk = cmul(tk, t1);
-                }
-#else
-#pragma unroll
-                for (int k1 = 1; k1 < 20; ++k1) {
-                    const cplx16 t = tabT[k1];
-                    const cplx v = cmul(y[k1], cplx{t.x, t.y});
-                    exch[(k1 * 10 + r) * kSub + f] = cplx16{v.x, v.y};
-                }
-#endif
+                for (int k1 = 1; k1 < 20; ++k1) exch[(k1 * 10 + r) * kSub + f] = cmul(y[k1], tabT[k1]);
             }
-            team_bar(team);                     // A: pass-1 stores -> pass-2 loads; the PCM has been read
-            if (zin && sub == 0) fin = s_fin[team];
-            // the next sub-tile's PCM arrives behind the arithmetic
-            if (sub + 1 < nsub) stage(m, m.f0 + (sub + 1) * kSub);
-            else if (mnext.valid) stage(mnext, mnext.f0);
-            if (fin >= 0 && sub == 0) finalize_stats(p, tile_off, fin, tt);
+            team_bar(team);                     // ExchA: pass-1 stores -> pass-2 loads; the PCM has been read
+            if (sub == nsub - 1 && mnext.valid) stage(mnext);    // next unit's PCM arrives behind the arithmetic
             // ---------------- pass 2: DFT10 of rows j and 20-j, split, log ----------------
             {
                 cplx ia[10], ib[10], za[10], zb[10];
 #pragma unroll
-                for (int n2 = 0; n2 < 10; ++n2) {
-                    const cplx16 v = exch[(k1a * 10 + n2) * kSub + f];
-                    ia[n2] = cplx{v.x, v.y};
-                }
+                for (int n2 = 0; n2 < 10; ++n2) ia[n2] = exch[(k1a * 10 + n2) * kSub + f];
 #pragma unroll
-                for (int n2 = 0; n2 < 10; ++n2) {
-                    const cplx16 v = exch[(k1b * 10 + n2) * kSub + f];
-                    ib[n2] = cplx{v.x, v.y};
-                }
-                if (!kSepOut) team_bar(team);   // B: every lane holds its rows; the exchange becomes the out tile
+                for (int n2 = 0; n2 < 10; ++n2) ib[n2] = exch[(k1b * 10 + n2) * kSub + f];
+                team_bar(team);                 // ExchB: every lane holds its rows; the exchange becomes the out tile
                 dft10(ia, za);   // za[k2] = Z[k1a + 20 k2]
                 dft10(ib, zb);   // zb[k2] = Z[k1b + 20 k2]
                 float* orow = ot + f * kOutStride;
-                if (q == 0) {
-                    // the warp that owns role 0 (rows 0 and 10 are their own mirrors): lane-uniform code
-                    // with operand selects, eleven slots
-                    auto loadP = [&](int s) {
-                        const cplx16 t = tabP[(s < 6 ? r : kb_hi) + 20 * (s < 10 ? s : (j0 ? 10 : 0))];
-                        return cplx{t.x, t.y};
-                    };
-                    auto emit = [&](int s, double pk, double pm) {
-                        const int k = (s < 6 ? r : kb_hi) + 20 * s;
-                        const float vk = log_mag((float)pk, hm), vm = log_mag((float)pm, hm);
-                        if (s < 10 || j0) {
-                            orow[200 - k] = vm;         // role 0, slot 0 writes bin "200" into the row padding
-                            orow[k] = vk;               // role 0, slot 5: bin 100 from pk, as the last store
-                        }
-                    };
-                    split_lane(j0, za, zb, loadP, emit);
-                } else {
-#if ASRK_SPEC_PGEN
-                    const cplx16 p0l = tabP[r];
-                    const cplx p0{p0l.x, p0l.y};
-#endif
-#pragma unroll
-                    for (int s = 0; s < 10; ++s) {
-                        const int k = r + 20 * s;
-#if ASRK_SPEC_PGEN
-                        // P[r + 20 s] = P[r] W20^s with W20^s a compile-time constant (constant-bank operands)
-                        constexpr double kC20[10] = {1.0, 0.95105651629515357212, 0.80901699437494742410, 0.58778525229247312917,
-                                                     0.30901699437494742410, 0.0, -0.30901699437494742410,
-                                                     -0.58778525229247312917, -0.80901699437494742410, -0.95105651629515357212};
-                        constexpr double kS20[10] = {0.0, -0.30901699437494742410, -0.58778525229247312917, -0.80901699437494742410,
-                                                     -0.95105651629515357212, -1.0, -0.95105651629515357212,
-                                                     -0.80901699437494742410, -0.58778525229247312917, -0.30901699437494742410};
-                        const cplx t = (s == 0) ? p0 : cmul(p0, cplx{kC20[s], kS20[s]});
-#else
-                        const cplx16 t = tabP[k];
-#endif
-                        double pk, pm;
-                        split_pair(za[s], zb[9 - s], cplx{t.x, t.y}, pk, pm);
-                        orow[200 - k] = log_mag((float)pm, hm);
-                        orow[k] = log_mag((float)pk, hm);
+                const float hm = m.half_mag;
+                auto loadP = [&](int s) { return tabP[(s < 6 ? r : kb_hi) + 20 * (s < 10 ? s : (j0 ? 10 : 0))]; };
+                auto emit = [&](int s, double pk, double pm) {
+                    const int k = (s < 6 ? r : kb_hi) + 20 * s;
+                    const float vk = log_mag((float)pk, hm), vm = log_mag((float)pm, hm);
+                    if (s < 10 || j0) {
+                        orow[200 - k] = vm;         // role 0, slot 0 writes bin "200" into the row padding
+                        orow[k] = vk;               // role 0, slot 5: bin 100 from pk, as the last store
                     }
-                }
+                };
+                split_lane(j0, za, zb, loadP, emit);
             }
-            team_bar(team);                     // C: the out tile is complete
-            // ---------------- copy-out (16-byte accesses) + column sums ----------------
+            team_bar(team);                     // the out tile is complete
+            // ---------------- copy-out by columns + column sums ----------------
             {
-                const int rows = (m_nf - sub * kSub) < kSub ? (m_nf - sub * kSub) : kSub;
-                float* obase = p.out + (size_t)(m_row0 + m.f0 + sub * kSub) * kBins + 4 * co_c4;
-                const float* tbase = ot + 4 * co_c4;
-                if (sub == 0 && co_act) cS = *reinterpret_cast<const float4*>(tbase);
-#pragma unroll 2
-                for (int row = co_ph; row < rows; row += 3) {
-                    const float4 y = *reinterpret_cast<const float4*>(tbase + row * kOutStride);
-                    stg4_hint(obase + (size_t)row * kBins, y, keep);
-                    float d = y.x - cS.x; sS.x += d; qS.x = fmaf(d, d, qS.x);
-                    d = y.y - cS.y; sS.y += d; qS.y = fmaf(d, d, qS.y);
-                    d = y.z - cS.z; sS.z += d; qS.z = fmaf(d, d, qS.z);
-                    d = y.w - cS.w; sS.w += d; qS.w = fmaf(d, d, qS.w);
+                const int rows = (m.nf - sub * kSub) < kSub ? (m.nf - sub * kSub) : kSub;
+                float* obase = p.out + (size_t)(m.row0 + m.f0 + sub * kSub) * kBins;
+                const int colA = 40 * q + lane, colB = 40 * q + 32 + lane;
+                const bool hasB = lane < 8;
+#pragma unroll 4
+                for (int row = 0; row < rows; ++row) {
+                    const float yA = ot[row * kOutStride + colA];
+                    const float yB = hasB ? ot[row * kOutStride + colB] : 0.f;
+                    stg_hint(obase + (size_t)row * kBins + colA, yA, keep);
+                    if (hasB) stg_hint(obase + (size_t)row * kBins + colB, yB, keep);
+                    if (sub == 0 && row == 0) { cA = yA; cB = yB; }
+                    float d = yA - cA;
+                    sA += d;
+                    qA = fmaf(d, d, qA);
+                    d = yB - cB;
+                    sB += d;
+                    qB = fmaf(d, d, qB);
                 }
             }
+            team_bar(team);                     // the out tile has been read: the exchange is free again
         }
         if (want_stats) {
-            // the three row phases of a column group sit in adjacent lanes: fixed-order sums, then the
             // un-shifted sums of the unit in fp64:  sum y = s + n c,  sum y^2 = q + 2 c s + n c^2
-            float sv[4] = {sS.x, sS.y, sS.z, sS.w}, qv[4] = {qS.x, qS.y, qS.z, qS.w};
-            const float cv[4] = {cS.x, cS.y, cS.z, cS.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float s1 = __shfl_down_sync(0xffffffffu, sv[e], 1), s2 = __shfl_down_sync(0xffffffffu, sv[e], 2);
-                const float q1 = __shfl_down_sync(0xffffffffu, qv[e], 1), q2 = __shfl_down_sync(0xffffffffu, qv[e], 2);
-                sv[e] = (sv[e] + s1) + s2;
-                qv[e] = (qv[e] + q1) + q2;
+            const double n = (double)m.nf;
+            {
+                const double c = (double)cA, s1 = (double)sA, q1 = (double)qA;
+                p.partials[(size_t)m.tile * kBins + 40 * q + lane] =
+                    make_double2(fma(n, c, s1), fma(c, fma(n, c, 2.0 * s1), q1));
             }
-            if (co_act && co_ph == 0) {
-                const double n = (double)m_nf;
-                double2* dst = p.partials + (size_t)m.tile * kBins + 4 * co_c4;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const double c = (double)cv[e], s1 = (double)sv[e], q1 = (double)qv[e];
-                    __stcg(dst + e, make_double2(fma(n, c, s1), fma(c, fma(n, c, 2.0 * s1), q1)));
-                }
+            if (lane < 8) {
+                const double c = (double)cB, s1 = (double)sB, q1 = (double)qB;
+                p.partials[(size_t)m.tile * kBins + 40 * q + 32 + lane] =
+                    make_double2(fma(n, c, s1), fma(c, fma(n, c, 2.0 * s1), q1));
             }
-            if (tt == 0) { pub_b = m.b; pub_nt = m.ntiles_b; }
         }
-    }
-    if (zin) {
-        // drain: the team's last unit is published here
-        team_bar(team);
-        publish_count();
-        team_bar(team);
-        const int fin = s_fin[team];
-        if (fin >= 0) finalize_stats(p, tile_off, fin, tt);
     }
 }
 
@@ -720,34 +572,17 @@ __global__ void __launch_bounds__(128) normalize_kernel(Params p) {
     }
 }
 
-template <bool F32, int kTeams, bool kSepOut>
-static void launch_main(const Params& p, int grid, cudaStream_t stream) {
-    using C = Cfg<F32, kTeams, kSepOut>;
-    const size_t smem = C::smem_bytes();
-    cudaFuncSetAttribute(spectrogram_kernel<F32, kTeams, kSepOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spectrogram_kernel<F32, kTeams, kSepOut><<<grid, C::kThreads, smem, stream>>>(p), asrk::note_launch();
+template <bool F32>
+static size_t main_smem_bytes() {
+    return sizeof(double) * kTabDoubles + sizeof(int) * (kMaxBatch + 1) + sizeof(UttCache) +
+           (size_t)kTeams * (200 * kSub * sizeof(cplx) + sizeof(uint32_t) * Cfg<F32>::kPcmWords) + 16;
 }
 
-// Experiment switches (read once): ASRK_SPEC_TEAMS = 2 | 3 teams per CTA, ASRK_SPEC_ZSCORE = kernel | separate
-// (kernel: mean / 1/std finished by the transform kernel; separate: by the statistics kernel of round 1).
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-static int cfg_teams() {
-    static int v = env_int("ASRK_SPEC_TEAMS", 3);
-    return v == 2 ? 2 : 3;
-}
-static int cfg_sepout() {      // int16, three teams: out tile in its own buffer (one team barrier less per sub-tile)
-    static int v = env_int("ASRK_SPEC_SEPOUT", 0);
-    return v;
-}
-static int cfg_zscore_in_kernel() {
-    static int v = [] {
-        const char* e = getenv("ASRK_SPEC_ZSCORE");
-        return (e && e[0] == 's') ? 0 : 1;
-    }();
-    return v;
+template <bool F32>
+static void launch_main(const Params& p, int grid, cudaStream_t stream) {
+    const size_t smem = main_smem_bytes<F32>();
+    cudaFuncSetAttribute(spectrogram_kernel<F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spectrogram_kernel<F32><<<grid, kThreads, smem, stream>>>(p), asrk::note_launch();
 }
 
 }  // namespace spec
@@ -799,15 +634,7 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
     }
     if (!(phases & (ASRK_PHASE_SPEC_MAIN | ASRK_PHASE_SPEC_NORMALIZE))) return launch_status();
 
-    // the z-score runs inside the main kernel when both phases are asked for in one call (the normal
-    // case); a harness that times the phases one by one gets the separate kernels
-    const bool both = (phases & ASRK_PHASE_SPEC_MAIN) && (phases & ASRK_PHASE_SPEC_NORMALIZE);
-    const int teams = cfg_teams();
-    // mean / 1/std are finished inside the transform kernel when both phases come in one call (the normal
-    // case); a harness that times the phases one by one gets the separate statistics kernel
-    const int zin = (mode == ASRK_SPEC_FBANK && both && cfg_zscore_in_kernel()) ? 1 : 0;
-
-    // the kernel locates units through a prefix array in shared memory: at most
+    // the kernel locates tiles through a prefix array in shared memory: at most
     // kMaxBatch utterances per launch, larger batches go in slices
     for (int b0 = 0; b0 < batch; b0 += kMaxBatch) {
         const int nb = (batch - b0) < kMaxBatch ? (batch - b0) : kMaxBatch;
@@ -821,28 +648,20 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         p.out_row_offsets = out_row_offsets ? out_row_offsets + b0 : nullptr;
         p.batch = nb;
         p.mode = mode;
-        p.zscore_in_kernel = zin;
         p.out = out;
         p.counters = reinterpret_cast<int*>(ws + l.counters);
-        p.done = reinterpret_cast<int*>(ws + l.done);
         p.tile_off_g = reinterpret_cast<int*>(ws + l.tile_off);
         p.partials = reinterpret_cast<double2*>(ws + l.partials);
         p.stats = reinterpret_cast<float*>(ws + l.stats) + (size_t)b0 * 3 * kBins;
+        if ((phases & ASRK_PHASE_SPEC_MAIN) &&
+            cudaMemsetAsync(p.counters, 0, sizeof(int) * 4, stream) != cudaSuccess)
+            return ASRK_E_CUDA;
         if (phases & ASRK_PHASE_SPEC_MAIN) {
-            // counters (| done when the statistics are finished in the kernel) start from zero
-            if (cudaMemsetAsync(ws + l.counters, 0, zin ? l.zero_bytes : sizeof(int) * 4, stream) != cudaSuccess)
-                return ASRK_E_CUDA;
-            if (sample_dtype == ASRK_DTYPE_I16) {
-                if (teams == 2) launch_main<false, 2, true>(p, grid, stream);
-                else if (cfg_sepout()) launch_main<false, 3, true>(p, grid, stream);
-                else launch_main<false, 3, false>(p, grid, stream);
-            } else {
-                if (teams == 2) launch_main<true, 2, true>(p, grid, stream);
-                else launch_main<true, 3, false>(p, grid, stream);
-            }
+            if (sample_dtype == ASRK_DTYPE_I16) launch_main<false>(p, grid, stream);
+            else launch_main<true>(p, grid, stream);
         }
         if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE)) {
-            if (!zin) stats_kernel<<<nb, 256, 0, stream>>>(p), asrk::note_launch();
+            stats_kernel<<<nb, 256, 0, stream>>>(p), asrk::note_launch();
             normalize_kernel<<<dim3(32, nb), 128, 0, stream>>>(p), asrk::note_launch();   // small CTAs: they fit next to the CTC kernel
         }
     }

@@ -13,7 +13,7 @@ from asr_dfcnn_transformer_b200 import features  # noqa: E402
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
-pool = [bench.DeviceBatch(bench.make_batch(2000 + i, batch=batch), dev, torch) for i in range(3)]
+pool = [bench.DeviceBatch(bench.make_batch(2000 + i, batch=batch), dev, torch, "c2", "logits") for i in range(3)]
 for mode in os.environ.get("ASRK_TIME_MODES", "fbank,fbank_raw,asrt").split(","):
     for it in range(3):
         db = pool[it % 3]
