@@ -71,7 +71,7 @@ struct Params {
     float* lse;          // [B][T]
     float* rowmax;       // [B][T]
     int* argmax;         // [B][T]
-    float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (log-softmax)
+    float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (softmax probability, linear)
     float* occ;          // [B][T][2 Ls+1] alpha (scaled) then occupancy, lattice order
     double* coff;        // [B][T]        alpha offsets
     double* logp;        // [B]
@@ -385,7 +385,7 @@ __device__ __forceinline__ void rows_body(const Params& p, long long row, int la
         float* dst = p.lpl + bt * (size_t)(p.Ls + 1);
         for (int j = lane; j <= L; j += 32) {
             const int c = (j == 0) ? p.blank : eff[j - 1];
-            dst[j] = (prob ? __logf(x[c] + p.eps) : x[c]) - lse;
+            dst[j] = prob ? (x[c] + p.eps) * __expf(-lse) : __expf(x[c] - lse);     // y_t(l'_j), linear
         }
     }
 }
@@ -541,7 +541,7 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     float* smax = slse + T;                     // [T]
     int* samax = reinterpret_cast<int*>(smax + T);   // [T]
     float* sK = smax + 2 * T;                   // [T] C_t + D_t - log2 p
-    float* slp = sK + T;                        // [T][W] y_t(l'_j)
+    float* slp = sK + T;                        // [T][W] y_t(l'_j), linear
     float* sal = slp + T * W;                   // [T][Ub]
     float* sbe = sal + T * Ub;                  // [T][Ub]
     const int* eff = p.eff_labels + (size_t)b * p.Ls;
@@ -561,7 +561,7 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             // the op's input is log(p + eps): y = (p + eps) / sum(p + eps), no exponentials; slse holds 1 / sum
             const float ssum = row_sum_eps(r, V4, lane, p.eps);
             if (lane == 0) { slse[t] = __fdividef(1.0f, ssum); smax[t] = 0.f; samax[t] = 0; }
-            if (lane < W) slp[t * W + lane] = lg2_fast(xg + p.eps) - lg2_fast(ssum);   // log2 y_t(l'_j)
+            if (lane < W) slp[t * W + lane] = (xg + p.eps) * __fdividef(1.0f, ssum);   // y_t(l'_j)
         } else {
             float m;
             int am;
@@ -569,63 +569,70 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             const float ssum = row_sumexp(r, m);
             const float lse = m + __logf(ssum);
             if (lane == 0) { slse[t] = lse; smax[t] = m; samax[t] = am; }
-            if (lane < W) slp[t * W + lane] = (xg - lse) * 1.4426950408889634f;   // log2 y_t(l'_j)
+            if (lane < W) slp[t * W + lane] = ex2_fast((xg - lse) * 1.4426950408889634f);   // y_t(l'_j)
         }
     }
     __syncthreads();
     ASRK_TICK(1);
 
     // ---- B: alpha || beta || greedy collapse ----------------------------------
-    // Log2-domain recursions in fp32.  Every column is stored relative to a LEVEL kept in
-    // double: column t has the maximum of the stored column t-1 subtracted (one REDUX per
-    // frame on order-preserving bit patterns), so stored values stay within a few tens of
-    // 0 -- no drift with T, no underflow of the states that matter (a linear-domain variant
-    // rescaled by the column maximum was 2x faster per step but crushed low-mass terminal
-    // states into denormals).  Using the PREVIOUS column's maximum takes the reduction off
-    // the recursion's dependency chain (shuffle -> log-sum-exp -> subtract): it runs beside
-    // the next step's log-sum-exp.  The levels are accumulated in the same loop, in double
-    // (T additions of ~10 each: fp32 would lose 1e-2 at T in the hundreds).
-    //   alpha_t(u) = 2^(ahat_t(u) + C_t),  beta_t(u) (excludes y_t, TF) = 2^(bhat_t(u) + D_t)
+    // LINEAR-domain recursions in fp64 (the fp64 pipe is idle in this kernel): a step is one shuffle, two or
+    // three DADD and one DMUL on the dependency chain (~50 cycles) instead of a log-sum-exp with three MUFU
+    // round trips (~280 cycles in round 1: 13 us of a CTA's 48 us with six of its eight warps waiting).
+    // Every column is rescaled by an exact power of two, the top exponent of the PREVIOUS column (one REDUX on
+    // the high words; it meets the chain only at the final multiply, through y 2^-e), so a stored column's
+    // largest value stays in [y_min, 6): nothing drifts with T and no low-mass state is crushed the way a
+    // float32 linear recursion crushed them.  (Taking the exponent two columns back would take the reduction
+    // off the chain entirely, but that control loop is only marginally stable: the column maxima random-walk.)
+    // The accumulated exponents are integers: the levels are exact.
+    //   alpha_t(u) = A_t(u) 2^(C_t),  beta_t(u) (excludes y_t, TF) = B_t(u) 2^(D_t)
+    // Stored for the gradient pass: float32 (A 2^100), (B 2^100) -- 226 binades below the column's top.
     const int i = lane;
     const int lab_i = (i < L) ? eff[i] : -1;
     const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
     const bool skip = (i >= 1 && i < L && lab_i != lab_im1);
     const bool has_blank = (i <= L);
+    constexpr double kStoreScale = 1.2676506002282294e30;     // 2^100
+    auto pow2 = [](int e) { return __hiloint2double((1023 + e) << 20, 0); };
+    auto top_exponent = [](double a, double b) {              // exponent of the largest value of the column (0 if all zero)
+        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a), __double2hiint(b)));
+        return hi ? (int)(hi >> 20) - 1023 : 0;
+    };
     if (warp == 0) {
         // alpha: pair (blank 2i, label 2i+1)
         const bool has_lab = (i < L);
-        float a_b = kNegInf, a_l = kNegInf;
+        double a_b = 0.0, a_l = 0.0;
         if (i == 0) {
-            a_b = slp[0];
-            if (L >= 1) a_l = slp[1];
+            a_b = (double)slp[0];
+            if (L >= 1) a_l = (double)slp[1];
         }
-        float yb_n = 0.f, yl_n = 0.f;            // log2 y of the next frame, loaded ahead of the chain
-        if (T > 1) { yb_n = slp[W]; yl_n = has_lab ? slp[W + 1 + i] : kNegInf; }
-        float m_prev = 0.f;                      // maximum of the stored column t-1
-        double lvl = 0.0;                        // C_t
+        float yb_n = 0.f, yl_n = 0.f;            // y of the next frame, loaded ahead of the chain
+        if (T > 1) { yb_n = slp[W]; yl_n = has_lab ? slp[W + 1 + i] : 0.f; }
+        int e1 = 0;                              // top exponent of column t-1
+        int lvl = 0;                             // C_t
         for (int t = 0; t < T; ++t) {
             if (t > 0) {
-                const float yb = yb_n, yl = yl_n;
-                if (t + 1 < T) { yb_n = slp[(t + 1) * W]; yl_n = has_lab ? slp[(t + 1) * W + 1 + i] : kNegInf; }
-                float p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
-                if (i == 0) p1 = kNegInf;
-                const float nb = yb + lse2_log2(a_b, p1);
-                const float nl = yl + lse3_log2(a_l, a_b, skip ? p1 : kNegInf);
-                a_b = has_blank ? nb - m_prev : kNegInf;
-                a_l = nl - m_prev;
-                lvl += (double)m_prev;
+                const double sc = pow2(-e1);
+                const double yb = (double)yb_n * sc, yl = (double)yl_n * sc;
+                if (t + 1 < T) { yb_n = slp[(t + 1) * W]; yl_n = has_lab ? slp[(t + 1) * W + 1 + i] : 0.f; }
+                double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+                if (i == 0) p1 = 0.0;
+                const double nb = yb * (a_b + p1);
+                const double nl = yl * ((a_l + a_b) + (skip ? p1 : 0.0));
+                a_b = has_blank ? nb : 0.0;
+                a_l = nl;                          // (yl = 0 where the label state does not exist)
+                lvl += e1;
             }
             float* o = sal + t * Ub;
-            if (has_blank) o[2 * i] = a_b;
-            if (has_lab) o[2 * i + 1] = a_l;
-            sC[t] = lvl;                           // every lane, same value
-            const float c = warp_max_redux(fmaxf(a_b, a_l));
-            m_prev = (c == kNegInf) ? 0.f : c;   // all -inf: no valid prefix
+            if (has_blank) o[2 * i] = (float)(a_b * kStoreScale);
+            if (has_lab) o[2 * i + 1] = (float)(a_l * kStoreScale);
+            sC[t] = (double)lvl;                   // every lane, same value
+            e1 = top_exponent(a_b, a_l);
         }
         // mass of the two terminal states at T-1 (relative to the last column's level)
-        const float fb = __shfl_sync(0xffffffffu, a_b, L);
-        const float fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : kNegInf;
-        if (lane == 0) s_fin = (double)lse2_log2(fb, fl);
+        const double fb = __shfl_sync(0xffffffffu, a_b, L);
+        const double fl = (L >= 1) ? __shfl_sync(0xffffffffu, a_l, L - 1) : 0.0;
+        if (lane == 0) s_fin = log2(fb + fl);      // -inf when no alignment exists
 #ifdef ASRK_CTC_TIMING
         if (lane == 0) s_tick[8] = (unsigned long long)clock64();
 #endif
@@ -633,35 +640,35 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         if (p.grad != nullptr) {
             // beta: pair (label 2i-1, blank 2i); excludes y_t
             const bool has_lab = (i >= 1 && i <= L);
-            float b_l = kNegInf, b_b = kNegInf;
+            double b_l = 0.0, b_b = 0.0;
             if (i == L) {
-                b_b = 0.f;
-                if (L >= 1) b_l = 0.f;
+                b_b = 1.0;
+                if (L >= 1) b_l = 1.0;
             }
             float yb_n = 0.f, yl_n = 0.f;
-            if (T > 1) { yb_n = slp[(T - 1) * W]; yl_n = has_lab ? slp[(T - 1) * W + i] : kNegInf; }
-            float m_prev = 0.f;
-            double lvl = 0.0;                    // D_t
+            if (T > 1) { yb_n = slp[(T - 1) * W]; yl_n = has_lab ? slp[(T - 1) * W + i] : 0.f; }
+            int e1 = 0;
+            int lvl = 0;                         // D_t
             for (int t = T - 1; t >= 0; --t) {
                 if (t < T - 1) {
-                    const float yb = yb_n, yl = yl_n;
-                    if (t >= 1) { yb_n = slp[t * W]; yl_n = has_lab ? slp[t * W + i] : kNegInf; }
-                    const float e_b = b_b + yb;
-                    const float e_l = b_l + yl;
-                    float n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
-                    if (i == 31) n1 = kNegInf;
-                    const float nbb = lse2_log2(e_b, n1);
-                    const float nbl = lse3_log2(e_l, e_b, skip ? n1 : kNegInf);
-                    b_b = has_blank ? nbb - m_prev : kNegInf;
-                    b_l = has_lab ? nbl - m_prev : kNegInf;
-                    lvl += (double)m_prev;
+                    const double sc = pow2(-e1);
+                    const double yb = (double)yb_n * sc, yl = (double)yl_n * sc;
+                    if (t >= 1) { yb_n = slp[t * W]; yl_n = has_lab ? slp[t * W + i] : 0.f; }
+                    const double e_b = b_b * yb;
+                    const double e_l = b_l * yl;
+                    double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+                    if (i == 31) n1 = 0.0;
+                    const double nbb = e_b + n1;
+                    const double nbl = (e_l + e_b) + (skip ? n1 : 0.0);
+                    b_b = has_blank ? nbb : 0.0;
+                    b_l = has_lab ? nbl : 0.0;
+                    lvl += e1;
                 }
                 float* o = sbe + t * Ub;
-                if (has_blank) o[2 * i] = b_b;
-                if (has_lab) o[2 * i - 1] = b_l;
-                sD[t] = lvl;                       // every lane, same value: no divergent branch in the chain
-                const float d = warp_max_redux(fmaxf(b_b, b_l));
-                m_prev = (d == kNegInf) ? 0.f : d;
+                if (has_blank) o[2 * i] = (float)(b_b * kStoreScale);
+                if (has_lab) o[2 * i - 1] = (float)(b_l * kStoreScale);
+                sD[t] = (double)lvl;               // every lane, same value: no divergent branch in the chain
+                e1 = top_exponent(b_b, b_l);
             }
         }
 #ifdef ASRK_CTC_TIMING
@@ -714,7 +721,7 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(ahat_t(u) + bhat_t(u) + K_t)
     ASRK_TICK(6);
     if (fix)
-        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = (float)(sC[t] + sD[t] - logp2);
+        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = (float)(sC[t] + sD[t] - logp2 - 200.0);
     __syncthreads();
     ASRK_TICK(3);
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
@@ -745,18 +752,18 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             const float* al = sal + t * Ub;
             const float* be = sbe + t * Ub;
             const float Kt = sK[t];
-            float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;
-            if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);
+            float ob = (lane <= L) ? ex2_fast(lg2_fast(al[2 * lane]) + lg2_fast(be[2 * lane]) + Kt) : 0.f;
+            if (is_blank_lab) ob += ex2_fast(lg2_fast(al[2 * lane + 1]) + lg2_fast(be[2 * lane + 1]) + Kt);
             if (owner) {
                 float o = 0.f;
                 for (unsigned mset = same; mset; mset &= mset - 1) {
                     const int k = __ffs(mset) - 1;
-                    o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
+                    o += ex2_fast(lg2_fast(al[2 * k + 1]) + lg2_fast(be[2 * k + 1]) + Kt);
                 }
-                g[my_lab] = base * (1.0f - __fdividef(o, ex2_fast(slp[t * W + 1 + lane])));
+                g[my_lab] = base * (1.0f - __fdividef(o, slp[t * W + 1 + lane]));
             }
             ob = warp_sum(ob);
-            if (lane == 0) g[p.blank] = base * (1.0f - __fdividef(ob, ex2_fast(slp[t * W])));
+            if (lane == 0) g[p.blank] = base * (1.0f - __fdividef(ob, slp[t * W]));
             continue;
         }
         const float nlse2 = -slse[t] * kLog2e;
@@ -787,18 +794,18 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         const float* al = sal + t * Ub;
         const float* be = sbe + t * Ub;
         const float Kt = sK[t];
-        float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;          // blank states (L <= 31)
-        if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);           // a label equal to the blank index
+        float ob = (lane <= L) ? ex2_fast(lg2_fast(al[2 * lane]) + lg2_fast(be[2 * lane]) + Kt) : 0.f;          // blank states (L <= 31)
+        if (is_blank_lab) ob += ex2_fast(lg2_fast(al[2 * lane + 1]) + lg2_fast(be[2 * lane + 1]) + Kt);           // a label equal to the blank index
         if (owner) {
             float o = 0.f;
             for (unsigned mset = same; mset; mset &= mset - 1) {
                 const int k = __ffs(mset) - 1;
-                o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
+                o += ex2_fast(lg2_fast(al[2 * k + 1]) + lg2_fast(be[2 * k + 1]) + Kt);
             }
-            g[my_lab] = (ex2_fast(slp[t * W + 1 + lane]) - o) * scale;
+            g[my_lab] = (slp[t * W + 1 + lane] - o) * scale;
         }
         ob = warp_sum(ob);
-        if (lane == 0) g[p.blank] = (ex2_fast(slp[t * W]) - ob) * scale;
+        if (lane == 0) g[p.blank] = (slp[t * W] - ob) * scale;
     }
 #ifdef ASRK_CTC_TIMING
     __syncthreads();
@@ -816,18 +823,25 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
 
 // One CTA per utterance; thread i owns the state pair
 //   alpha sweep: (blank 2i, label 2i+1)     beta sweep: (label 2i-1, blank 2i)
-// so that each step needs exactly one neighbour value (the previous / next
-// label state), exchanged through a double-buffered shared array.  alpha is kept
-// for the backward sweep as float32 relative to an offset C_t that is refreshed
-// from the exact column maximum every kRenorm steps.
+// so that each step needs exactly one neighbour value (the previous / next label state): a warp shuffle,
+// and across warps one double per warp through a double-buffered shared array behind the step's only
+// __syncthreads.  LINEAR domain in fp64 (see fused_small_kernel): a step is a shuffle, two or three DADD and
+// one DMUL; every column is rescaled by the exact power of two of the previous column's largest value -- the
+// block-wide maximum rides on the same barrier (one word per warp, reduced by every warp with one REDUX).
+// The probabilities of the next frames and, in the beta sweep, the stored alpha values and levels are fetched
+// kAhead steps ahead, so no global-memory round trip sits inside a step (round 1: 1.1 us per step, all of it L2 latency and
+// log-sum-exp chains; T = 1998 frames x 2 sweeps = 4.5 ms per C3 batch).
+// alpha is kept for the backward sweep as float32 (A 2^100) with its integer level in coff[t].
+constexpr int kAhead = 6;
 __global__ void lattice_kernel(Params p) {
     extern __shared__ double smd[];
     const int b = blockIdx.x;
     const int i = threadIdx.x;
     const int P = blockDim.x;
-    double* xch = smd;                                   // [2][P]
-    float* red = reinterpret_cast<float*>(smd + 2 * P);  // [32]
-    double* fin2 = smd + 2 * P + 16;                     // [2]
+    const int lane = i & 31, warp = i >> 5, nwarp = P >> 5;
+    double* edge = smd;                                       // [2][32] last / first value of every warp
+    unsigned* wtop = reinterpret_cast<unsigned*>(smd + 64);   // [2][32] top high word of every warp's column
+    double* fin2 = smd + 64 + 32;                             // [2]
     const int status = p.row_status[b];
     const int L = p.eff_len[b];
     const int T = p.input_len[b];
@@ -851,48 +865,80 @@ __global__ void lattice_kernel(Params p) {
     const bool has_blank = (i <= L);
     const bool has_lab_a = (i < L);             // alpha pair's label state 2i+1 exists
     const bool has_lab_b = (i >= 1 && i <= L);  // beta pair's label state 2i-1 exists
+    constexpr double kStoreScale = 1.2676506002282294e30;     // 2^100
+    auto pow2 = [](int e) { return __hiloint2double((1023 + e) << 20, 0); };
+    // top exponent of the whole column from the per-warp words written before the step's barrier
+    auto block_top = [&](int buf) {
+        const unsigned w = (lane < nwarp) ? wtop[buf * 32 + lane] : 0u;
+        const unsigned hi = __reduce_max_sync(0xffffffffu, w);
+        return hi ? (int)(hi >> 20) - 1023 : 0;
+    };
+    auto publish = [&](int buf, double a, double c, double edge_val) {
+        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a), __double2hiint(c)));
+        if (lane == 0) wtop[buf * 32 + warp] = hi;
+        edge[buf * 32 + warp] = edge_val;          // (only the edge lane's value is kept: see the callers)
+    };
 
     // ------------------------------ alpha ------------------------------
-    double a_b = ninf, a_l = ninf;
+    double a_b = 0.0, a_l = 0.0;
     if (i == 0) {
         a_b = (double)lpl[0];
         if (L >= 1) a_l = (double)lpl[1];
     }
-    double C = 0.0;
-    if (T >= 1) {
-        const float m = block_max((float)fmax(a_b, a_l), red);
-        if (m > kNegInf) C = (double)m;
+    if (has_blank) occ[2 * i] = (float)(a_b * kStoreScale);
+    if (has_lab_a) occ[2 * i + 1] = (float)(a_l * kStoreScale);
+    if (i == 0) coff[0] = 0.0;
+    {
+        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a_b), __double2hiint(a_l)));
+        if (lane == 0) wtop[warp] = hi;
+        if (lane == 31) edge[warp] = a_l;
     }
-    if (has_blank) occ[2 * i] = (float)(a_b - C);
-    if (has_lab_a) occ[2 * i + 1] = (float)(a_l - C);
-    if (i == 0) coff[0] = C;
-    for (int t = 1; t < T; ++t) {
-        double* xb = xch + (t & 1) * P;
-        xb[i] = a_l;
-        const double lb = (double)lpl[(size_t)t * S];
-        const double ll = has_lab_a ? (double)lpl[(size_t)t * S + 1 + i] : ninf;
-        __syncthreads();
-        const double p1 = (i >= 1) ? xb[i - 1] : ninf;
-        const double nb = lb + lse2(a_b, p1);
-        const double nl = ll + lse3(a_l, a_b, skip ? p1 : ninf);
-        a_b = has_blank ? nb : ninf;
-        a_l = has_lab_a ? nl : ninf;
-        if ((t % kRenorm) == 0) {
-            const float m = block_max((float)(fmax(a_b, a_l) - C), red);
-            if (m > kNegInf) C += (double)m;
+    float yb_q[kAhead], yl_q[kAhead];            // probabilities of frames t .. t + kAhead - 1
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+        const int tt = 1 + k;
+        yb_q[k] = (tt < T) ? lpl[(size_t)tt * S] : 0.f;
+        yl_q[k] = (tt < T && has_lab_a) ? lpl[(size_t)tt * S + 1 + i] : 0.f;
+    }
+    int lvl = 0;
+    for (int t0 = 1; t0 < T; t0 += kAhead) {
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+            const int t = t0 + k;
+            if (t < T) {                                   // uniform over the CTA
+                const int buf = (t - 1) & 1;
+                __syncthreads();                           // column t-1 published (edges, top words)
+                const int e1 = block_top(buf);
+                const double sc = pow2(-e1);
+                const double yb = (double)yb_q[k] * sc, yl = (double)yl_q[k] * sc;
+                const int tn = t + kAhead;                 // refill the slot for frame t + kAhead
+                yb_q[k] = (tn < T) ? lpl[(size_t)tn * S] : 0.f;
+                yl_q[k] = (tn < T && has_lab_a) ? lpl[(size_t)tn * S + 1 + i] : 0.f;
+                double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+                if (lane == 0) p1 = (warp > 0) ? edge[buf * 32 + warp - 1] : 0.0;
+                const double nb = yb * (a_b + p1);
+                const double nl = yl * ((a_l + a_b) + (skip ? p1 : 0.0));
+                a_b = has_blank ? nb : 0.0;
+                a_l = nl;                                  // (yl = 0 where the label state does not exist)
+                lvl += e1;
+                float* o = occ + (size_t)t * U;
+                if (has_blank) o[2 * i] = (float)(a_b * kStoreScale);
+                if (has_lab_a) o[2 * i + 1] = (float)(a_l * kStoreScale);
+                if (i == 0) coff[t] = (double)lvl;
+                const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a_b), __double2hiint(a_l)));
+                if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = hi;
+                if (lane == 31) edge[(buf ^ 1) * 32 + warp] = a_l;
+            }
         }
-        float* o = occ + (size_t)t * U;
-        if (has_blank) o[2 * i] = (float)(a_b - C);
-        if (has_lab_a) o[2 * i + 1] = (float)(a_l - C);
-        if (i == 0) coff[t] = C;
     }
-    // log p = LSE(alpha_{T-1}(2L), alpha_{T-1}(2L-1))
+    // log p = log2( alpha_{T-1}(2L) + alpha_{T-1}(2L-1) ) + C_{T-1}
     __syncthreads();
     if (i == L) fin2[0] = a_b;
     if (i == L - 1) fin2[1] = a_l;
-    if (L == 0 && i == 0) fin2[1] = ninf;
+    if (L == 0 && i == 0) fin2[1] = 0.0;
     __syncthreads();
-    const double logp = lse2(fin2[0], fin2[1]);
+    const double logp2 = (double)lvl + log2(fin2[0] + fin2[1]);
+    const double logp = logp2 * 0.6931471805599453;
     if (i == 0) {
         p.logp[b] = logp;
         p.loss[b] = (float)(-logp);
@@ -902,36 +948,86 @@ __global__ void lattice_kernel(Params p) {
     __syncthreads();
 
     // ------------------------------ beta -------------------------------
-    // beta excludes y_t; e(u) = beta_{t+1}(u) + log y_{t+1}(l'_u)
-    double b_l = ninf, b_b = ninf;
+    // beta excludes y_t; e(u) = beta_{t+1}(u) y_{t+1}(l'_u).  occupancy(t, u) = alpha_t(u) beta_t(u) / p
+    //   = (Fa 2^-100) B 2^(C_t + D_t - logp2):  the integer part of the exponent is applied exactly,
+    //   the fractional part of logp2 is one constant factor per utterance
+    const double lp_floor = floor(logp2);
+    const double frac_scale = exp2(-(logp2 - lp_floor)) / kStoreScale;
+    const int lp_i = (int)lp_floor;
+    double b_l = 0.0, b_b = 0.0;
     if (i == L) {
-        b_b = 0.0;
-        if (L >= 1) b_l = 0.0;
+        b_b = 1.0;
+        if (L >= 1) b_l = 1.0;
     }
-    {
-        const int t = T - 1;
-        float* o = occ + (size_t)t * U;
-        const double off = coff[t] - logp;
-        if (has_blank) o[2 * i] = __expf((float)((double)o[2 * i] + b_b + off));
-        if (has_lab_b) o[2 * i - 1] = __expf((float)((double)o[2 * i - 1] + b_l + off));
+    float ab_q[kAhead], al_q[kAhead];            // stored alpha of frames t .. t - kAhead + 1 (going down)
+    double cf_q[kAhead];                         // ... and their levels C_t
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+        const int tt = T - 1 - k;
+        const float* o = occ + (size_t)(tt < 0 ? 0 : tt) * U;
+        ab_q[k] = (tt >= 0 && has_blank) ? o[2 * i] : 0.f;
+        al_q[k] = (tt >= 0 && has_lab_b) ? o[2 * i - 1] : 0.f;
+        cf_q[k] = (tt >= 0) ? coff[tt] : 0.0;
+        // probabilities of frame tt + 1 (used by the step that produces column tt)
+        yb_q[k] = (tt + 1 < T && tt >= 0) ? lpl[(size_t)(tt + 1) * S] : 0.f;
+        yl_q[k] = (tt + 1 < T && tt >= 0 && has_lab_b) ? lpl[(size_t)(tt + 1) * S + i] : 0.f;   // label i-1 -> slot i
     }
-    for (int t = T - 2; t >= 0; --t) {
-        const double lb = (double)lpl[(size_t)(t + 1) * S];
-        const double ll = has_lab_b ? (double)lpl[(size_t)(t + 1) * S + i] : ninf;   // label i-1 -> slot i
-        const double e_b = b_b + lb;
-        const double e_l = b_l + ll;
-        double* xb = xch + (t & 1) * P;
-        xb[i] = e_l;
-        __syncthreads();
-        const double n1 = (i + 1 < P) ? xb[i + 1] : ninf;   // e of label state 2i+1
-        const double nbb = lse2(e_b, n1);
-        const double nbl = lse3(e_l, e_b, skip ? n1 : ninf);
-        b_b = has_blank ? nbb : ninf;
-        b_l = has_lab_b ? nbl : ninf;
-        float* o = occ + (size_t)t * U;
-        const double off = coff[t] - logp;
-        if (has_blank) o[2 * i] = __expf((float)((double)o[2 * i] + b_b + off));
-        if (has_lab_b) o[2 * i - 1] = __expf((float)((double)o[2 * i - 1] + b_l + off));
+    __syncthreads();                                      // the alpha sweep's last use of edge / wtop is over
+    lvl = 0;
+    for (int t0 = T - 1; t0 >= 0; t0 -= kAhead) {
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+            const int t = t0 - k;
+            if (t >= 0) {                                  // uniform over the CTA
+                const int buf = t & 1;
+                if (t < T - 1) {
+                    __syncthreads();                       // column t+1 published
+                    const int e1 = block_top(buf ^ 1);
+                    const double sc = pow2(-e1);
+                    const double yb = (double)yb_q[k] * sc, yl = (double)yl_q[k] * sc;
+                    const double e_b = b_b * yb;
+                    const double e_l = b_l * yl;
+                    // the neighbour needs e of the NEXT label state (2i+1): lane i+1's e_l
+                    // (e_l is formed from registers only: the cross-warp value was published as b_l, see below)
+                    double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+                    if (lane == 31) {
+                        // first lane of the next warp: its b_l of column t+1, times ITS y_l -- published ready-made
+                        n1 = (warp + 1 < nwarp) ? edge[(buf ^ 1) * 32 + warp + 1] * sc : 0.0;
+                    }
+                    const double nbb = e_b + n1;
+                    const double nbl = (e_l + e_b) + (skip ? n1 : 0.0);
+                    b_b = has_blank ? nbb : 0.0;
+                    b_l = has_lab_b ? nbl : 0.0;
+                    lvl += e1;
+                }
+                // occupancy of column t from the prefetched alpha
+                {
+                    float* o = occ + (size_t)t * U;
+                    const int Kt = (int)cf_q[k] + lvl - lp_i;
+                    const double f = pow2(Kt < -1000 ? -1000 : (Kt > 1000 ? 1000 : Kt)) * frac_scale;
+                    if (has_blank) o[2 * i] = (float)((double)ab_q[k] * b_b * f);
+                    if (has_lab_b) o[2 * i - 1] = (float)((double)al_q[k] * b_l * f);
+                }
+                // refill the look-ahead slots for frame t - kAhead
+                const int tn = t - kAhead;
+                {
+                    const float* o2 = occ + (size_t)(tn < 0 ? 0 : tn) * U;
+                    ab_q[k] = (tn >= 0 && has_blank) ? o2[2 * i] : 0.f;
+                    al_q[k] = (tn >= 0 && has_lab_b) ? o2[2 * i - 1] : 0.f;
+                    cf_q[k] = (tn >= 0) ? coff[tn] : 0.0;
+                    yb_q[k] = (tn >= 0) ? lpl[(size_t)(tn + 1) * S] : 0.f;
+                    yl_q[k] = (tn >= 0 && has_lab_b) ? lpl[(size_t)(tn + 1) * S + i] : 0.f;
+                }
+                // publish column t: top word per warp, and for the previous warp's last lane the product
+                // b_l(first lane) y_t(its label) that it will need as "e of the next label state"
+                const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(b_b), __double2hiint(b_l)));
+                if (lane == 0) {
+                    wtop[buf * 32 + warp] = hi;
+                    // y_t of label i-1: what this thread itself uses in the next step, already in its look-ahead queue
+                    edge[buf * 32 + warp] = b_l * (double)yl_q[(k + 1) % kAhead];
+                }
+            }
+        }
     }
 }
 
@@ -987,11 +1083,11 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
             else if (fst[j]) {
                 float o = 0.f;
                 for (int k = j; k >= 0; k = nxt[k]) o += occ[2 * k + 1];
-                g[eff[j]] = base * (1.0f - o / __expf(lpl[1 + j]));
+                g[eff[j]] = base * (1.0f - o / lpl[1 + j]);
             }
         }
         ob = warp_sum(ob);
-        if (lane == 0) g[p.blank] = base * (1.0f - ob / __expf(lpl[0]));
+        if (lane == 0) g[p.blank] = base * (1.0f - ob / lpl[0]);
         return;
     }
     if constexpr (NV4 > 0) {
@@ -1039,7 +1135,7 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
             for (int k = j; k >= 0; k = nxt[k]) o += occ[2 * k + 1];
             const int c = eff[j];
             // a label equal to the blank index is folded into the blank entry below
-            if (c != p.blank) g[c] = (__expf(lpl[1 + j]) - o) * scale;
+            if (c != p.blank) g[c] = (lpl[1 + j] - o) * scale;
         }
     }
     // labels that coincide with the blank index (pathological but legal input)
@@ -1047,7 +1143,7 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
     for (int j = lane; j < L; j += 32)
         if (eff[j] == p.blank) extra += occ[2 * j + 1];
     extra = warp_sum(extra);
-    if (lane == 0) g[p.blank] = (__expf(lpl[0]) - (ob + extra)) * scale;
+    if (lane == 0) g[p.blank] = (lpl[0] - (ob + extra)) * scale;
 }
 
 template <int NV4>
@@ -1353,7 +1449,7 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
     if (phases & ASRK_PHASE_CTC_LATTICE)
-        lattice_kernel<<<B, P, sizeof(double) * (2 * P + 16 + 2), stream>>>(p), asrk::note_launch();
+        lattice_kernel<<<B, P, sizeof(double) * (64 + 32 + 2), stream>>>(p), asrk::note_launch();
     if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
     if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p), asrk::note_launch();
     return launch_status();
