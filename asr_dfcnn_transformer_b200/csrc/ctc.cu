@@ -448,6 +448,17 @@ __device__ __forceinline__ float lse3_log2(float a, float b, float c) {
     const float ms = (m == kNegInf) ? 0.f : m;
     return m + lg2_fast(ex2_fast(a - ms) + ex2_fast(b - ms) + ex2_fast(c - ms));
 }
+// log2 of a non-negative double as a float: exponent + lg2.approx of the mantissa (absolute error 2^-22 on the
+// mantissa part).  This is how lattice columns are STORED for the gradient pass: the recursions run in the linear
+// domain, but a column spans hundreds of binades between the states that carry its mass and the states the
+// backward sweep will favour (T = 1998, L = 300: 2^-290 and worse), which no scaled float can hold.
+__device__ __forceinline__ float log2_store(double a) {
+    const unsigned hi = (unsigned)__double2hiint(a), lo = (unsigned)__double2loint(a);
+    const float e = (float)((int)(hi >> 20) - 1023);
+    const float m = __uint_as_float(0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29));
+    return (hi < 0x00100000u) ? kNegInf : e + lg2_fast(m);
+}
+
 // warp maximum of arbitrary-sign floats with ONE REDUX: floats order like the unsigned
 // patterns  bits ^ (sign ? 0xffffffff : 0x80000000)
 __device__ __forceinline__ float warp_max_redux(float v) {
@@ -586,13 +597,12 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     // off the chain entirely, but that control loop is only marginally stable: the column maxima random-walk.)
     // The accumulated exponents are integers: the levels are exact.
     //   alpha_t(u) = A_t(u) 2^(C_t),  beta_t(u) (excludes y_t, TF) = B_t(u) 2^(D_t)
-    // Stored for the gradient pass: float32 (A 2^100), (B 2^100) -- 226 binades below the column's top.
+    // Stored for the gradient pass: float32 log2 A, log2 B (log2_store: unlimited range below the column's top).
     const int i = lane;
     const int lab_i = (i < L) ? eff[i] : -1;
     const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
     const bool skip = (i >= 1 && i < L && lab_i != lab_im1);
     const bool has_blank = (i <= L);
-    constexpr double kStoreScale = 1.2676506002282294e30;     // 2^100
     auto pow2 = [](int e) { return __hiloint2double((1023 + e) << 20, 0); };
     auto top_exponent = [](double a, double b) {              // exponent of the largest value of the column (0 if all zero)
         const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a), __double2hiint(b)));
@@ -624,8 +634,8 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
                 lvl += e1;
             }
             float* o = sal + t * Ub;
-            if (has_blank) o[2 * i] = (float)(a_b * kStoreScale);
-            if (has_lab) o[2 * i + 1] = (float)(a_l * kStoreScale);
+            if (has_blank) o[2 * i] = log2_store(a_b);
+            if (has_lab) o[2 * i + 1] = log2_store(a_l);
             sC[t] = (double)lvl;                   // every lane, same value
             e1 = top_exponent(a_b, a_l);
         }
@@ -665,8 +675,8 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
                     lvl += e1;
                 }
                 float* o = sbe + t * Ub;
-                if (has_blank) o[2 * i] = (float)(b_b * kStoreScale);
-                if (has_lab) o[2 * i - 1] = (float)(b_l * kStoreScale);
+                if (has_blank) o[2 * i] = log2_store(b_b);
+                if (has_lab) o[2 * i - 1] = log2_store(b_l);
                 sD[t] = (double)lvl;               // every lane, same value: no divergent branch in the chain
                 e1 = top_exponent(b_b, b_l);
             }
@@ -720,8 +730,9 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     const bool fix = (logp != ninf) && (status == ASRK_ROW_OK);   // TF: no valid path -> dy = y
     // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(ahat_t(u) + bhat_t(u) + K_t)
     ASRK_TICK(6);
+    // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(log2 A + log2 B + K_t),  K_t = C_t + D_t - log2 p
     if (fix)
-        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = (float)(sC[t] + sD[t] - logp2 - 200.0);
+        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = (float)(sC[t] + sD[t] - logp2);
     __syncthreads();
     ASRK_TICK(3);
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
@@ -752,13 +763,13 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             const float* al = sal + t * Ub;
             const float* be = sbe + t * Ub;
             const float Kt = sK[t];
-            float ob = (lane <= L) ? ex2_fast(lg2_fast(al[2 * lane]) + lg2_fast(be[2 * lane]) + Kt) : 0.f;
-            if (is_blank_lab) ob += ex2_fast(lg2_fast(al[2 * lane + 1]) + lg2_fast(be[2 * lane + 1]) + Kt);
+            float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;
+            if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);
             if (owner) {
                 float o = 0.f;
                 for (unsigned mset = same; mset; mset &= mset - 1) {
                     const int k = __ffs(mset) - 1;
-                    o += ex2_fast(lg2_fast(al[2 * k + 1]) + lg2_fast(be[2 * k + 1]) + Kt);
+                    o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
                 }
                 g[my_lab] = base * (1.0f - __fdividef(o, slp[t * W + 1 + lane]));
             }
@@ -794,13 +805,13 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         const float* al = sal + t * Ub;
         const float* be = sbe + t * Ub;
         const float Kt = sK[t];
-        float ob = (lane <= L) ? ex2_fast(lg2_fast(al[2 * lane]) + lg2_fast(be[2 * lane]) + Kt) : 0.f;          // blank states (L <= 31)
-        if (is_blank_lab) ob += ex2_fast(lg2_fast(al[2 * lane + 1]) + lg2_fast(be[2 * lane + 1]) + Kt);           // a label equal to the blank index
+        float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;          // blank states (L <= 31)
+        if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);           // a label equal to the blank index
         if (owner) {
             float o = 0.f;
             for (unsigned mset = same; mset; mset &= mset - 1) {
                 const int k = __ffs(mset) - 1;
-                o += ex2_fast(lg2_fast(al[2 * k + 1]) + lg2_fast(be[2 * k + 1]) + Kt);
+                o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
             }
             g[my_lab] = (slp[t * W + 1 + lane] - o) * scale;
         }
@@ -829,10 +840,11 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
 // one DMUL; every column is rescaled by the exact power of two of the previous column's largest value -- the
 // block-wide maximum rides on the same barrier (one word per warp, reduced by every warp with one REDUX).
 // The probabilities of the next frames and, in the beta sweep, the stored alpha values and levels are fetched
-// kAhead steps ahead, so no global-memory round trip sits inside a step (round 1: 1.1 us per step, all of it L2 latency and
+// kRing - 1 steps ahead with cp.async into a shared-memory ring, so no global-memory round trip sits inside a step (round 1: 1.1 us per step, all of it L2 latency and
 // log-sum-exp chains; T = 1998 frames x 2 sweeps = 4.5 ms per C3 batch).
-// alpha is kept for the backward sweep as float32 (A 2^100) with its integer level in coff[t].
-constexpr int kAhead = 6;
+// alpha is kept for the backward sweep as float32 log2 A (log2_store) with its integer level in coff[t].
+constexpr int kRing = 8;
+__host__ __device__ inline int lattice_slot_floats(int P) { return 4 + 3 * P; }   // coff(2) yb(1) pad(1) | yl | ab | al
 __global__ void lattice_kernel(Params p) {
     extern __shared__ double smd[];
     const int b = blockIdx.x;
@@ -842,6 +854,8 @@ __global__ void lattice_kernel(Params p) {
     double* edge = smd;                                       // [2][32] last / first value of every warp
     unsigned* wtop = reinterpret_cast<unsigned*>(smd + 64);   // [2][32] top high word of every warp's column
     double* fin2 = smd + 64 + 32;                             // [2]
+    float* ring = reinterpret_cast<float*>(smd + 64 + 32 + 2);   // [kRing][slot]: look-ahead frames, filled by cp.async
+    const int SF = lattice_slot_floats(P);
     const int status = p.row_status[b];
     const int L = p.eff_len[b];
     const int T = p.input_len[b];
@@ -865,7 +879,6 @@ __global__ void lattice_kernel(Params p) {
     const bool has_blank = (i <= L);
     const bool has_lab_a = (i < L);             // alpha pair's label state 2i+1 exists
     const bool has_lab_b = (i >= 1 && i <= L);  // beta pair's label state 2i-1 exists
-    constexpr double kStoreScale = 1.2676506002282294e30;     // 2^100
     auto pow2 = [](int e) { return __hiloint2double((1023 + e) << 20, 0); };
     // top exponent of the whole column from the per-warp words written before the step's barrier
     auto block_top = [&](int buf) {
@@ -873,64 +886,58 @@ __global__ void lattice_kernel(Params p) {
         const unsigned hi = __reduce_max_sync(0xffffffffu, w);
         return hi ? (int)(hi >> 20) - 1023 : 0;
     };
-    auto publish = [&](int buf, double a, double c, double edge_val) {
-        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a), __double2hiint(c)));
-        if (lane == 0) wtop[buf * 32 + warp] = hi;
-        edge[buf * 32 + warp] = edge_val;          // (only the edge lane's value is kept: see the callers)
-    };
+    auto slot = [&](int frame) { return ring + (size_t)((frame % kRing + kRing) % kRing) * SF; };
 
     // ------------------------------ alpha ------------------------------
+    // look-ahead: y of frame f (blank, this thread's label) -> slot(f); a register prefetch does not work here
+    // (six scoreboards per warp: waiting for the oldest load waits for the newest too)
+    auto fetch_a = [&](int f) {
+        float* s = slot(f);
+        const bool in = (f >= 1 && f < T);
+        if (i == 0) cp_async4(s + 2, lpl + (size_t)(in ? f : 0) * S, in ? 4 : 0);
+        cp_async4(s + 4 + i, lpl + (size_t)(in ? f : 0) * S + 1 + (has_lab_a ? i : 0), (in && has_lab_a) ? 4 : 0);
+        cp_async_commit();
+    };
     double a_b = 0.0, a_l = 0.0;
     if (i == 0) {
         a_b = (double)lpl[0];
         if (L >= 1) a_l = (double)lpl[1];
     }
-    if (has_blank) occ[2 * i] = (float)(a_b * kStoreScale);
-    if (has_lab_a) occ[2 * i + 1] = (float)(a_l * kStoreScale);
+    if (has_blank) occ[2 * i] = log2_store(a_b);
+    if (has_lab_a) occ[2 * i + 1] = log2_store(a_l);
     if (i == 0) coff[0] = 0.0;
     {
         const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a_b), __double2hiint(a_l)));
         if (lane == 0) wtop[warp] = hi;
         if (lane == 31) edge[warp] = a_l;
     }
-    float yb_q[kAhead], yl_q[kAhead];            // probabilities of frames t .. t + kAhead - 1
-#pragma unroll
-    for (int k = 0; k < kAhead; ++k) {
-        const int tt = 1 + k;
-        yb_q[k] = (tt < T) ? lpl[(size_t)tt * S] : 0.f;
-        yl_q[k] = (tt < T && has_lab_a) ? lpl[(size_t)tt * S + 1 + i] : 0.f;
-    }
+    for (int k = 0; k < kRing - 1; ++k) fetch_a(1 + k);
     int lvl = 0;
-    for (int t0 = 1; t0 < T; t0 += kAhead) {
-#pragma unroll
-        for (int k = 0; k < kAhead; ++k) {
-            const int t = t0 + k;
-            if (t < T) {                                   // uniform over the CTA
-                const int buf = (t - 1) & 1;
-                __syncthreads();                           // column t-1 published (edges, top words)
-                const int e1 = block_top(buf);
-                const double sc = pow2(-e1);
-                const double yb = (double)yb_q[k] * sc, yl = (double)yl_q[k] * sc;
-                const int tn = t + kAhead;                 // refill the slot for frame t + kAhead
-                yb_q[k] = (tn < T) ? lpl[(size_t)tn * S] : 0.f;
-                yl_q[k] = (tn < T && has_lab_a) ? lpl[(size_t)tn * S + 1 + i] : 0.f;
-                double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
-                if (lane == 0) p1 = (warp > 0) ? edge[buf * 32 + warp - 1] : 0.0;
-                const double nb = yb * (a_b + p1);
-                const double nl = yl * ((a_l + a_b) + (skip ? p1 : 0.0));
-                a_b = has_blank ? nb : 0.0;
-                a_l = nl;                                  // (yl = 0 where the label state does not exist)
-                lvl += e1;
-                float* o = occ + (size_t)t * U;
-                if (has_blank) o[2 * i] = (float)(a_b * kStoreScale);
-                if (has_lab_a) o[2 * i + 1] = (float)(a_l * kStoreScale);
-                if (i == 0) coff[t] = (double)lvl;
-                const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a_b), __double2hiint(a_l)));
-                if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = hi;
-                if (lane == 31) edge[(buf ^ 1) * 32 + warp] = a_l;
-            }
-        }
+    for (int t = 1; t < T; ++t) {
+        const int buf = (t - 1) & 1;
+        cp_async_wait<kRing - 2>();                // this thread's copies of frame t have landed
+        __syncthreads();                           // ... everybody's; column t-1 is published (edges, top words)
+        fetch_a(t + kRing - 1);                    // (into the slot frame t-1 used: everyone has read it)
+        const float* sl = slot(t);
+        const int e1 = block_top(buf);
+        const double sc = pow2(-e1);
+        const double yb = (double)sl[2] * sc, yl = (double)sl[4 + i] * sc;
+        double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+        if (lane == 0) p1 = (warp > 0) ? edge[buf * 32 + warp - 1] : 0.0;
+        const double nb = yb * (a_b + p1);
+        const double nl = yl * ((a_l + a_b) + (skip ? p1 : 0.0));
+        a_b = has_blank ? nb : 0.0;
+        a_l = nl;                                  // (yl = 0 where the label state does not exist)
+        lvl += e1;
+        float* o = occ + (size_t)t * U;
+        if (has_blank) o[2 * i] = log2_store(a_b);
+        if (has_lab_a) o[2 * i + 1] = log2_store(a_l);
+        if (i == 0) coff[t] = (double)lvl;
+        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a_b), __double2hiint(a_l)));
+        if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = hi;
+        if (lane == 31) edge[(buf ^ 1) * 32 + warp] = a_l;
     }
+    cp_async_wait<0>();
     // log p = log2( alpha_{T-1}(2L) + alpha_{T-1}(2L-1) ) + C_{T-1}
     __syncthreads();
     if (i == L) fin2[0] = a_b;
@@ -945,90 +952,72 @@ __global__ void lattice_kernel(Params p) {
         if (logp == ninf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
     }
     if (p.grad == nullptr || logp == ninf) return;   // uniform over the CTA
-    __syncthreads();
+    __syncthreads();                                  // (the alpha columns written by other threads are visible)
 
     // ------------------------------ beta -------------------------------
     // beta excludes y_t; e(u) = beta_{t+1}(u) y_{t+1}(l'_u).  occupancy(t, u) = alpha_t(u) beta_t(u) / p
-    //   = (Fa 2^-100) B 2^(C_t + D_t - logp2):  the integer part of the exponent is applied exactly,
-    //   the fractional part of logp2 is one constant factor per utterance
-    const double lp_floor = floor(logp2);
-    const double frac_scale = exp2(-(logp2 - lp_floor)) / kStoreScale;
-    const int lp_i = (int)lp_floor;
+    //   = 2^(log2 A + log2 B + (C_t + D_t - logp2))
+    // look-ahead for the step that produces column f: y of frame f + 1, the stored alpha column f and its level
+    auto fetch_b = [&](int f) {
+        float* s = slot(f);
+        const bool in = (f >= 0 && f < T);
+        const bool iny = in && (f + 1 < T);
+        const float* o = occ + (size_t)(in ? f : 0) * U;
+        if (i == 0) {
+            cp_async8(s, coff + (in ? f : 0), in ? 8 : 0);
+            cp_async4(s + 2, lpl + (size_t)(iny ? f + 1 : 0) * S, iny ? 4 : 0);
+        }
+        cp_async4(s + 4 + i, lpl + (size_t)(iny ? f + 1 : 0) * S + (has_lab_b ? i : 0), (iny && has_lab_b) ? 4 : 0);   // label i-1 -> slot i
+        cp_async4(s + 4 + P + i, o + (has_blank ? 2 * i : 0), (in && has_blank) ? 4 : 0);
+        cp_async4(s + 4 + 2 * P + i, o + (has_lab_b ? 2 * i - 1 : 0), (in && has_lab_b) ? 4 : 0);
+        cp_async_commit();
+    };
     double b_l = 0.0, b_b = 0.0;
     if (i == L) {
         b_b = 1.0;
         if (L >= 1) b_l = 1.0;
     }
-    float ab_q[kAhead], al_q[kAhead];            // stored alpha of frames t .. t - kAhead + 1 (going down)
-    double cf_q[kAhead];                         // ... and their levels C_t
-#pragma unroll
-    for (int k = 0; k < kAhead; ++k) {
-        const int tt = T - 1 - k;
-        const float* o = occ + (size_t)(tt < 0 ? 0 : tt) * U;
-        ab_q[k] = (tt >= 0 && has_blank) ? o[2 * i] : 0.f;
-        al_q[k] = (tt >= 0 && has_lab_b) ? o[2 * i - 1] : 0.f;
-        cf_q[k] = (tt >= 0) ? coff[tt] : 0.0;
-        // probabilities of frame tt + 1 (used by the step that produces column tt)
-        yb_q[k] = (tt + 1 < T && tt >= 0) ? lpl[(size_t)(tt + 1) * S] : 0.f;
-        yl_q[k] = (tt + 1 < T && tt >= 0 && has_lab_b) ? lpl[(size_t)(tt + 1) * S + i] : 0.f;   // label i-1 -> slot i
-    }
-    __syncthreads();                                      // the alpha sweep's last use of edge / wtop is over
+    for (int k = 0; k < kRing - 1; ++k) fetch_b(T - 1 - k);
     lvl = 0;
-    for (int t0 = T - 1; t0 >= 0; t0 -= kAhead) {
-#pragma unroll
-        for (int k = 0; k < kAhead; ++k) {
-            const int t = t0 - k;
-            if (t >= 0) {                                  // uniform over the CTA
-                const int buf = t & 1;
-                if (t < T - 1) {
-                    __syncthreads();                       // column t+1 published
-                    const int e1 = block_top(buf ^ 1);
-                    const double sc = pow2(-e1);
-                    const double yb = (double)yb_q[k] * sc, yl = (double)yl_q[k] * sc;
-                    const double e_b = b_b * yb;
-                    const double e_l = b_l * yl;
-                    // the neighbour needs e of the NEXT label state (2i+1): lane i+1's e_l
-                    // (e_l is formed from registers only: the cross-warp value was published as b_l, see below)
-                    double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
-                    if (lane == 31) {
-                        // first lane of the next warp: its b_l of column t+1, times ITS y_l -- published ready-made
-                        n1 = (warp + 1 < nwarp) ? edge[(buf ^ 1) * 32 + warp + 1] * sc : 0.0;
-                    }
-                    const double nbb = e_b + n1;
-                    const double nbl = (e_l + e_b) + (skip ? n1 : 0.0);
-                    b_b = has_blank ? nbb : 0.0;
-                    b_l = has_lab_b ? nbl : 0.0;
-                    lvl += e1;
-                }
-                // occupancy of column t from the prefetched alpha
-                {
-                    float* o = occ + (size_t)t * U;
-                    const int Kt = (int)cf_q[k] + lvl - lp_i;
-                    const double f = pow2(Kt < -1000 ? -1000 : (Kt > 1000 ? 1000 : Kt)) * frac_scale;
-                    if (has_blank) o[2 * i] = (float)((double)ab_q[k] * b_b * f);
-                    if (has_lab_b) o[2 * i - 1] = (float)((double)al_q[k] * b_l * f);
-                }
-                // refill the look-ahead slots for frame t - kAhead
-                const int tn = t - kAhead;
-                {
-                    const float* o2 = occ + (size_t)(tn < 0 ? 0 : tn) * U;
-                    ab_q[k] = (tn >= 0 && has_blank) ? o2[2 * i] : 0.f;
-                    al_q[k] = (tn >= 0 && has_lab_b) ? o2[2 * i - 1] : 0.f;
-                    cf_q[k] = (tn >= 0) ? coff[tn] : 0.0;
-                    yb_q[k] = (tn >= 0) ? lpl[(size_t)(tn + 1) * S] : 0.f;
-                    yl_q[k] = (tn >= 0 && has_lab_b) ? lpl[(size_t)(tn + 1) * S + i] : 0.f;
-                }
-                // publish column t: top word per warp, and for the previous warp's last lane the product
-                // b_l(first lane) y_t(its label) that it will need as "e of the next label state"
-                const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(b_b), __double2hiint(b_l)));
-                if (lane == 0) {
-                    wtop[buf * 32 + warp] = hi;
-                    // y_t of label i-1: what this thread itself uses in the next step, already in its look-ahead queue
-                    edge[buf * 32 + warp] = b_l * (double)yl_q[(k + 1) % kAhead];
-                }
-            }
+    for (int t = T - 1; t >= 0; --t) {
+        const int buf = t & 1;
+        cp_async_wait<kRing - 3>();                // frames t and t-1 have landed (t-1: the edge value below)
+        __syncthreads();                           // ... everybody's; column t+1 is published
+        fetch_b(t - (kRing - 1));                  // (into the slot frame t+1 used: everyone has read it)
+        const float* sl = slot(t);
+        if (t < T - 1) {
+            const int e1 = block_top(buf ^ 1);
+            const double sc = pow2(-e1);
+            const double yb = (double)sl[2] * sc, yl = (double)sl[4 + i] * sc;
+            const double e_b = b_b * yb;
+            const double e_l = b_l * yl;
+            // the pair needs e of the NEXT label state (2i+1): lane i+1's e_l; across warps the first lane
+            // of the next warp published b_l y_l (unscaled) with its column
+            double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+            if (lane == 31) n1 = (warp + 1 < nwarp) ? edge[(buf ^ 1) * 32 + warp + 1] * sc : 0.0;
+            const double nbb = e_b + n1;
+            const double nbl = (e_l + e_b) + (skip ? n1 : 0.0);
+            b_b = has_blank ? nbb : 0.0;
+            b_l = has_lab_b ? nbl : 0.0;
+            lvl += e1;
+        }
+        // occupancy of column t from the look-ahead alpha
+        {
+            float* o = occ + (size_t)t * U;
+            const double ct = *reinterpret_cast<const double*>(sl);
+            const float Kt = (float)(ct + (double)lvl - logp2);
+            if (has_blank) o[2 * i] = ex2_fast(sl[4 + P + i] + log2_store(b_b) + Kt);
+            if (has_lab_b) o[2 * i - 1] = ex2_fast(sl[4 + 2 * P + i] + log2_store(b_l) + Kt);
+        }
+        // publish column t: top word per warp, and for the previous warp's last lane the product
+        // b_l(first lane) y_t(its label): what it needs as "e of the next label state" in the next step
+        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(b_b), __double2hiint(b_l)));
+        if (lane == 0) {
+            wtop[buf * 32 + warp] = hi;
+            edge[buf * 32 + warp] = b_l * (double)slot(t - 1)[4 + i];      // y_t of label i-1 (this thread's own copy)
         }
     }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------
@@ -1448,8 +1437,11 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (p.small_only) return launch_status();
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
-    if (phases & ASRK_PHASE_CTC_LATTICE)
-        lattice_kernel<<<B, P, sizeof(double) * (64 + 32 + 2), stream>>>(p), asrk::note_launch();
+    if (phases & ASRK_PHASE_CTC_LATTICE) {
+        const size_t lsm = sizeof(double) * (64 + 32 + 2) + sizeof(float) * kRing * lattice_slot_floats(P);
+        cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+        lattice_kernel<<<B, P, lsm, stream>>>(p), asrk::note_launch();
+    }
     if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
     if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p), asrk::note_launch();
     return launch_status();

@@ -13,7 +13,7 @@ import bench  # noqa: E402
 from asr_dfcnn_transformer_b200 import ctc  # noqa: E402
 
 dev = torch.device("cuda", 0)
-db = bench.DeviceBatch(bench.make_batch(2000), dev, torch)
+db = bench.DeviceBatch(bench.make_batch(2000), dev, torch, "c2", "logits")
 for it in range(4):
     r = ctc.ctc_loss_grad(db.logits, db.labels, db.label_len, db.input_len, bench.V - 1, grad_scale=db.grad_scale,
                           grad_out=db.grad, decode=True, bounds=db.ctc_bounds)
