@@ -249,16 +249,19 @@ __device__ __forceinline__ void issue_row(float4* rb, const float* row, int V4, 
                                           uint64_t* bar) {
     if (lane == 0) tma_load_1d(rb, row, (unsigned)V4 * 16u, bar, policy);
 }
-// The bulk copy writes through the async proxy, which is not ordered after shared-memory LOADS
-// that were merely issued: before the buffer is handed back, every lane consumes what it loaded
-// (a register dependence on all of its LDS results), then the warp converges.  Measured: without
-// this a few rows in 10^4 were overwritten under the reader in the L2-hit gradient pass.
+// The bulk copy writes through the async proxy, which is not ordered after generic-proxy accesses of the same
+// shared memory: before the buffer is handed back to the TMA, every lane has consumed what it loaded (a register
+// dependence on all of its LDS results), issues the cross-proxy fence the architecture specifies for this
+// (fence.proxy.async.shared::cta), and the warp converges.  Round 1 relied on the register dependence alone; with
+// the shorter lattice phase of round 2 a handful of gradient rows per 10^4 were again overwritten under the reader
+// (tests/test_gpu_ctc.py::test_full_size_c2_batch_properties) until the fence went in.
 template <int NV4>
 __device__ __forceinline__ void release_row(const float4 (&v)[NV4]) {
     unsigned dep = 0;
 #pragma unroll
     for (int k = 0; k < NV4; ++k) dep |= __float_as_uint(v[k].w);
     asm volatile("" ::"r"(dep) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
 }
 
