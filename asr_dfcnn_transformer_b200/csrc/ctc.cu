@@ -71,7 +71,7 @@ struct Params {
     float* lse;          // [B][T]
     float* rowmax;       // [B][T]
     int* argmax;         // [B][T]
-    float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (softmax probability, linear)
+    float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (log2 of the softmax probability)
     float* occ;          // [B][T][2 Ls+1] alpha (scaled) then occupancy, lattice order
     double* coff;        // [B][T]        alpha offsets
     double* logp;        // [B]
@@ -388,7 +388,7 @@ __device__ __forceinline__ void rows_body(const Params& p, long long row, int la
         float* dst = p.lpl + bt * (size_t)(p.Ls + 1);
         for (int j = lane; j <= L; j += 32) {
             const int c = (j == 0) ? p.blank : eff[j - 1];
-            dst[j] = prob ? (x[c] + p.eps) * __expf(-lse) : __expf(x[c] - lse);     // y_t(l'_j), linear
+            dst[j] = ((prob ? __logf(x[c] + p.eps) : x[c]) - lse) * kLog2e;         // log2 y_t(l'_j)
         }
     }
 }
@@ -451,17 +451,6 @@ __device__ __forceinline__ float lse3_log2(float a, float b, float c) {
     const float ms = (m == kNegInf) ? 0.f : m;
     return m + lg2_fast(ex2_fast(a - ms) + ex2_fast(b - ms) + ex2_fast(c - ms));
 }
-// log2 of a non-negative double as a float: exponent + lg2.approx of the mantissa (absolute error 2^-22 on the
-// mantissa part).  This is how lattice columns are STORED for the gradient pass: the recursions run in the linear
-// domain, but a column spans hundreds of binades between the states that carry its mass and the states the
-// backward sweep will favour (T = 1998, L = 300: 2^-290 and worse), which no scaled float can hold.
-__device__ __forceinline__ float log2_store(double a) {
-    const unsigned hi = (unsigned)__double2hiint(a), lo = (unsigned)__double2loint(a);
-    const float e = (float)((int)(hi >> 20) - 1023);
-    const float m = __uint_as_float(0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29));
-    return (hi < 0x00100000u) ? kNegInf : e + lg2_fast(m);
-}
-
 // warp maximum of arbitrary-sign floats with ONE REDUX: floats order like the unsigned
 // patterns  bits ^ (sign ? 0xffffffff : 0x80000000)
 __device__ __forceinline__ float warp_max_redux(float v) {
@@ -600,7 +589,10 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     // off the chain entirely, but that control loop is only marginally stable: the column maxima random-walk.)
     // The accumulated exponents are integers: the levels are exact.
     //   alpha_t(u) = A_t(u) 2^(C_t),  beta_t(u) (excludes y_t, TF) = B_t(u) 2^(D_t)
-    // Stored for the gradient pass: float32 log2 A, log2 B (log2_store: unlimited range below the column's top).
+    // Stored for the gradient pass: the HIGH WORD of A and of B (sign, 11-bit exponent, 20 mantissa bits): no
+    // conversion instruction in the recursion loop, the whole fp64 range, 2^-20 relative precision.  (A lattice that
+    // fits this kernel -- T <= 200 -- spans ~100 binades per column; the generic kernel's T = 1998 columns span more
+    // than fp64 has and stay in the log domain.)
     const int i = lane;
     const int lab_i = (i < L) ? eff[i] : -1;
     const int lab_im1 = (i >= 1 && i <= L) ? eff[i - 1] : -2;
@@ -637,8 +629,8 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
                 lvl += e1;
             }
             float* o = sal + t * Ub;
-            if (has_blank) o[2 * i] = log2_store(a_b);
-            if (has_lab) o[2 * i + 1] = log2_store(a_l);
+            if (has_blank) o[2 * i] = __int_as_float(__double2hiint(a_b));
+            if (has_lab) o[2 * i + 1] = __int_as_float(__double2hiint(a_l));
             sC[t] = (double)lvl;                   // every lane, same value
             e1 = top_exponent(a_b, a_l);
         }
@@ -678,8 +670,8 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
                     lvl += e1;
                 }
                 float* o = sbe + t * Ub;
-                if (has_blank) o[2 * i] = log2_store(b_b);
-                if (has_lab) o[2 * i - 1] = log2_store(b_l);
+                if (has_blank) o[2 * i] = __int_as_float(__double2hiint(b_b));
+                if (has_lab) o[2 * i - 1] = __int_as_float(__double2hiint(b_l));
                 sD[t] = (double)lvl;               // every lane, same value: no divergent branch in the chain
                 e1 = top_exponent(b_b, b_l);
             }
@@ -733,9 +725,18 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     const bool fix = (logp != ninf) && (status == ASRK_ROW_OK);   // TF: no valid path -> dy = y
     // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(ahat_t(u) + bhat_t(u) + K_t)
     ASRK_TICK(6);
-    // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(log2 A + log2 B + K_t),  K_t = C_t + D_t - log2 p
-    if (fix)
-        for (int t = tid; t < T; t += kRowWarps * 32) sK[t] = (float)(sC[t] + sD[t] - logp2);
+    // occupancy(t, u) = alpha_t(u) beta_t(u) / p = A B 2^(C_t + D_t - log2 p), formed in double: the integer part of
+    // the exponent is exact, the fraction of log2 p one factor per utterance.  sD[t] becomes that factor.
+    if (fix) {
+        const double lpf = floor(logp2);
+        const double fr = exp2(-(logp2 - lpf));
+        const int lpi = (int)lpf;
+        for (int t = tid; t < T; t += kRowWarps * 32) {
+            int K = (int)(sC[t] + sD[t]) - lpi;
+            K = K < -1022 ? -1022 : (K > 1023 ? 1023 : K);
+            sD[t] = __hiloint2double((1023 + K) << 20, 0) * fr;
+        }
+    }
     __syncthreads();
     ASRK_TICK(3);
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
@@ -765,14 +766,14 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
             __syncwarp();
             const float* al = sal + t * Ub;
             const float* be = sbe + t * Ub;
-            const float Kt = sK[t];
-            float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;
-            if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);
+            const double Kt = sD[t];
+            float ob = (lane <= L) ? (float)(__hiloint2double(__float_as_int(al[2 * lane]), 0) * __hiloint2double(__float_as_int(be[2 * lane]), 0) * Kt) : 0.f;
+            if (is_blank_lab) ob += (float)(__hiloint2double(__float_as_int(al[2 * lane + 1]), 0) * __hiloint2double(__float_as_int(be[2 * lane + 1]), 0) * Kt);
             if (owner) {
                 float o = 0.f;
                 for (unsigned mset = same; mset; mset &= mset - 1) {
                     const int k = __ffs(mset) - 1;
-                    o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
+                    o += (float)(__hiloint2double(__float_as_int(al[2 * k + 1]), 0) * __hiloint2double(__float_as_int(be[2 * k + 1]), 0) * Kt);
                 }
                 g[my_lab] = base * (1.0f - __fdividef(o, slp[t * W + 1 + lane]));
             }
@@ -807,14 +808,14 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
         __syncwarp();
         const float* al = sal + t * Ub;
         const float* be = sbe + t * Ub;
-        const float Kt = sK[t];
-        float ob = (lane <= L) ? ex2_fast(al[2 * lane] + be[2 * lane] + Kt) : 0.f;          // blank states (L <= 31)
-        if (is_blank_lab) ob += ex2_fast(al[2 * lane + 1] + be[2 * lane + 1] + Kt);           // a label equal to the blank index
+        const double Kt = sD[t];
+        float ob = (lane <= L) ? (float)(__hiloint2double(__float_as_int(al[2 * lane]), 0) * __hiloint2double(__float_as_int(be[2 * lane]), 0) * Kt) : 0.f;          // blank states (L <= 31)
+        if (is_blank_lab) ob += (float)(__hiloint2double(__float_as_int(al[2 * lane + 1]), 0) * __hiloint2double(__float_as_int(be[2 * lane + 1]), 0) * Kt);           // a label equal to the blank index
         if (owner) {
             float o = 0.f;
             for (unsigned mset = same; mset; mset &= mset - 1) {
                 const int k = __ffs(mset) - 1;
-                o += ex2_fast(al[2 * k + 1] + be[2 * k + 1] + Kt);
+                o += (float)(__hiloint2double(__float_as_int(al[2 * k + 1]), 0) * __hiloint2double(__float_as_int(be[2 * k + 1]), 0) * Kt);
             }
             g[my_lab] = (slp[t * W + 1 + lane] - o) * scale;
         }
@@ -838,26 +839,34 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
 // One CTA per utterance; thread i owns the state pair
 //   alpha sweep: (blank 2i, label 2i+1)     beta sweep: (label 2i-1, blank 2i)
 // so that each step needs exactly one neighbour value (the previous / next label state): a warp shuffle,
-// and across warps one double per warp through a double-buffered shared array behind the step's only
-// __syncthreads.  LINEAR domain in fp64 (see fused_small_kernel): a step is a shuffle, two or three DADD and
-// one DMUL; every column is rescaled by the exact power of two of the previous column's largest value -- the
-// block-wide maximum rides on the same barrier (one word per warp, reduced by every warp with one REDUX).
+// and across warps one float per warp through a double-buffered shared array behind the step's only
+// __syncthreads.  Log2 domain in fp32, every column stored relative to a LEVEL kept in double (the block-wide
+// maximum of the previous column is subtracted each step; it rides on the same barrier: one word per warp,
+// reduced by every warp with one REDUX).  A linear-domain fp64 recursion with one scale per column -- what the
+// fused kernel uses for its short lattices -- is 4x shorter per step but cannot hold these columns: at T = 1998,
+// L = 300 the states that carry the occupancy sit 2^-1020 below the column's largest value (measured on the
+// C3 batch: tools/debug_c3.py), beyond fp64's normal range.
 // The probabilities of the next frames and, in the beta sweep, the stored alpha values and levels are fetched
-// kRing - 1 steps ahead with cp.async into a shared-memory ring, so no global-memory round trip sits inside a step (round 1: 1.1 us per step, all of it L2 latency and
-// log-sum-exp chains; T = 1998 frames x 2 sweeps = 4.5 ms per C3 batch).
-// alpha is kept for the backward sweep as float32 log2 A (log2_store) with its integer level in coff[t].
+// kRing - 1 steps ahead with cp.async into a shared-memory ring, so no global-memory round trip sits inside a
+// step (a register look-ahead does not work: six scoreboards per warp, waiting for the oldest load waits for the
+// newest too).  Round 1: 1.1 us per step, all of it L2 latency; T = 1998 frames x 2 sweeps = 4.5 ms per C3 batch.
 constexpr int kRing = 8;
 __host__ __device__ inline int lattice_slot_floats(int P) { return 4 + 3 * P; }   // coff(2) yb(1) pad(1) | yl | ab | al
+__device__ __forceinline__ unsigned float_key(float v) {      // order-preserving bit pattern
+    const unsigned b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned m) { return __uint_as_float(m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu)); }
 __global__ void lattice_kernel(Params p) {
     extern __shared__ double smd[];
     const int b = blockIdx.x;
     const int i = threadIdx.x;
     const int P = blockDim.x;
     const int lane = i & 31, warp = i >> 5, nwarp = P >> 5;
-    double* edge = smd;                                       // [2][32] last / first value of every warp
-    unsigned* wtop = reinterpret_cast<unsigned*>(smd + 64);   // [2][32] top high word of every warp's column
-    double* fin2 = smd + 64 + 32;                             // [2]
-    float* ring = reinterpret_cast<float*>(smd + 64 + 32 + 2);   // [kRing][slot]: look-ahead frames, filled by cp.async
+    float* edge = reinterpret_cast<float*>(smd);              // [2][32] last / first value of every warp
+    unsigned* wtop = reinterpret_cast<unsigned*>(smd + 32);   // [2][32] key of every warp's column maximum
+    float* fin2 = reinterpret_cast<float*>(smd + 64);         // [2]
+    float* ring = reinterpret_cast<float*>(smd + 66);         // [kRing][slot]: look-ahead frames, filled by cp.async
     const int SF = lattice_slot_floats(P);
     const int status = p.row_status[b];
     const int L = p.eff_len[b];
@@ -882,18 +891,16 @@ __global__ void lattice_kernel(Params p) {
     const bool has_blank = (i <= L);
     const bool has_lab_a = (i < L);             // alpha pair's label state 2i+1 exists
     const bool has_lab_b = (i >= 1 && i <= L);  // beta pair's label state 2i-1 exists
-    auto pow2 = [](int e) { return __hiloint2double((1023 + e) << 20, 0); };
-    // top exponent of the whole column from the per-warp words written before the step's barrier
-    auto block_top = [&](int buf) {
+    // maximum of the whole column from the per-warp keys written before the step's barrier (0 if all -inf)
+    auto block_max = [&](int buf) {
         const unsigned w = (lane < nwarp) ? wtop[buf * 32 + lane] : 0u;
-        const unsigned hi = __reduce_max_sync(0xffffffffu, w);
-        return hi ? (int)(hi >> 20) - 1023 : 0;
+        const float m = key_float(__reduce_max_sync(0xffffffffu, w));
+        return (m == kNegInf) ? 0.f : m;
     };
     auto slot = [&](int frame) { return ring + (size_t)((frame % kRing + kRing) % kRing) * SF; };
 
     // ------------------------------ alpha ------------------------------
-    // look-ahead: y of frame f (blank, this thread's label) -> slot(f); a register prefetch does not work here
-    // (six scoreboards per warp: waiting for the oldest load waits for the newest too)
+    // look-ahead: log2 y of frame f (blank, this thread's label) -> slot(f)
     auto fetch_a = [&](int f) {
         float* s = slot(f);
         const bool in = (f >= 1 && f < T);
@@ -901,53 +908,52 @@ __global__ void lattice_kernel(Params p) {
         cp_async4(s + 4 + i, lpl + (size_t)(in ? f : 0) * S + 1 + (has_lab_a ? i : 0), (in && has_lab_a) ? 4 : 0);
         cp_async_commit();
     };
-    double a_b = 0.0, a_l = 0.0;
+    float a_b = kNegInf, a_l = kNegInf;
     if (i == 0) {
-        a_b = (double)lpl[0];
-        if (L >= 1) a_l = (double)lpl[1];
+        a_b = lpl[0];
+        if (L >= 1) a_l = lpl[1];
     }
-    if (has_blank) occ[2 * i] = log2_store(a_b);
-    if (has_lab_a) occ[2 * i + 1] = log2_store(a_l);
+    if (has_blank) occ[2 * i] = a_b;
+    if (has_lab_a) occ[2 * i + 1] = a_l;
     if (i == 0) coff[0] = 0.0;
     {
-        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a_b), __double2hiint(a_l)));
-        if (lane == 0) wtop[warp] = hi;
+        const float c = warp_max_redux(fmaxf(a_b, a_l));
+        if (lane == 0) wtop[warp] = float_key(c);
         if (lane == 31) edge[warp] = a_l;
     }
     for (int k = 0; k < kRing - 1; ++k) fetch_a(1 + k);
-    int lvl = 0;
+    double lvl = 0.0;
     for (int t = 1; t < T; ++t) {
         const int buf = (t - 1) & 1;
         cp_async_wait<kRing - 2>();                // this thread's copies of frame t have landed
-        __syncthreads();                           // ... everybody's; column t-1 is published (edges, top words)
+        __syncthreads();                           // ... everybody's; column t-1 is published (edges, maxima)
         fetch_a(t + kRing - 1);                    // (into the slot frame t-1 used: everyone has read it)
         const float* sl = slot(t);
-        const int e1 = block_top(buf);
-        const double sc = pow2(-e1);
-        const double yb = (double)sl[2] * sc, yl = (double)sl[4 + i] * sc;
-        double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
-        if (lane == 0) p1 = (warp > 0) ? edge[buf * 32 + warp - 1] : 0.0;
-        const double nb = yb * (a_b + p1);
-        const double nl = yl * ((a_l + a_b) + (skip ? p1 : 0.0));
-        a_b = has_blank ? nb : 0.0;
-        a_l = nl;                                  // (yl = 0 where the label state does not exist)
-        lvl += e1;
+        const float m_prev = block_max(buf);
+        const float yb = sl[2], yl = has_lab_a ? sl[4 + i] : kNegInf;
+        float p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+        if (lane == 0) p1 = (warp > 0) ? edge[buf * 32 + warp - 1] : kNegInf;
+        const float nb = yb + lse2_log2(a_b, p1);
+        const float nl = yl + lse3_log2(a_l, a_b, skip ? p1 : kNegInf);
+        a_b = has_blank ? nb - m_prev : kNegInf;
+        a_l = nl - m_prev;
+        lvl += (double)m_prev;
         float* o = occ + (size_t)t * U;
-        if (has_blank) o[2 * i] = log2_store(a_b);
-        if (has_lab_a) o[2 * i + 1] = log2_store(a_l);
-        if (i == 0) coff[t] = (double)lvl;
-        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(a_b), __double2hiint(a_l)));
-        if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = hi;
+        if (has_blank) o[2 * i] = a_b;
+        if (has_lab_a) o[2 * i + 1] = a_l;
+        if (i == 0) coff[t] = lvl;
+        const float c = warp_max_redux(fmaxf(a_b, a_l));
+        if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = float_key(c);
         if (lane == 31) edge[(buf ^ 1) * 32 + warp] = a_l;
     }
     cp_async_wait<0>();
-    // log p = log2( alpha_{T-1}(2L) + alpha_{T-1}(2L-1) ) + C_{T-1}
+    // log2 p = C_{T-1} + log2( 2^ahat_{T-1}(2L) + 2^ahat_{T-1}(2L-1) )
     __syncthreads();
     if (i == L) fin2[0] = a_b;
     if (i == L - 1) fin2[1] = a_l;
-    if (L == 0 && i == 0) fin2[1] = 0.0;
+    if (L == 0 && i == 0) fin2[1] = kNegInf;
     __syncthreads();
-    const double logp2 = (double)lvl + log2(fin2[0] + fin2[1]);
+    const double logp2 = lvl + (double)lse2_log2(fin2[0], fin2[1]);
     const double logp = logp2 * 0.6931471805599453;
     if (i == 0) {
         p.logp[b] = logp;
@@ -958,8 +964,8 @@ __global__ void lattice_kernel(Params p) {
     __syncthreads();                                  // (the alpha columns written by other threads are visible)
 
     // ------------------------------ beta -------------------------------
-    // beta excludes y_t; e(u) = beta_{t+1}(u) y_{t+1}(l'_u).  occupancy(t, u) = alpha_t(u) beta_t(u) / p
-    //   = 2^(log2 A + log2 B + (C_t + D_t - logp2))
+    // beta excludes y_t; e(u) = beta_{t+1}(u) + log2 y_{t+1}(l'_u).  occupancy(t, u) = alpha_t(u) beta_t(u) / p
+    //   = 2^(ahat + bhat + (C_t + D_t - log2 p))
     // look-ahead for the step that produces column f: y of frame f + 1, the stored alpha column f and its level
     auto fetch_b = [&](int f) {
         float* s = slot(f);
@@ -975,13 +981,13 @@ __global__ void lattice_kernel(Params p) {
         cp_async4(s + 4 + 2 * P + i, o + (has_lab_b ? 2 * i - 1 : 0), (in && has_lab_b) ? 4 : 0);
         cp_async_commit();
     };
-    double b_l = 0.0, b_b = 0.0;
+    float b_l = kNegInf, b_b = kNegInf;
     if (i == L) {
-        b_b = 1.0;
-        if (L >= 1) b_l = 1.0;
+        b_b = 0.f;
+        if (L >= 1) b_l = 0.f;
     }
     for (int k = 0; k < kRing - 1; ++k) fetch_b(T - 1 - k);
-    lvl = 0;
+    lvl = 0.0;
     for (int t = T - 1; t >= 0; --t) {
         const int buf = t & 1;
         cp_async_wait<kRing - 3>();                // frames t and t-1 have landed (t-1: the edge value below)
@@ -989,35 +995,34 @@ __global__ void lattice_kernel(Params p) {
         fetch_b(t - (kRing - 1));                  // (into the slot frame t+1 used: everyone has read it)
         const float* sl = slot(t);
         if (t < T - 1) {
-            const int e1 = block_top(buf ^ 1);
-            const double sc = pow2(-e1);
-            const double yb = (double)sl[2] * sc, yl = (double)sl[4 + i] * sc;
-            const double e_b = b_b * yb;
-            const double e_l = b_l * yl;
+            const float m_prev = block_max(buf ^ 1);
+            const float yb = sl[2], yl = has_lab_b ? sl[4 + i] : kNegInf;
+            const float e_b = b_b + yb;
+            const float e_l = b_l + yl;
             // the pair needs e of the NEXT label state (2i+1): lane i+1's e_l; across warps the first lane
-            // of the next warp published b_l y_l (unscaled) with its column
-            double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
-            if (lane == 31) n1 = (warp + 1 < nwarp) ? edge[(buf ^ 1) * 32 + warp + 1] * sc : 0.0;
-            const double nbb = e_b + n1;
-            const double nbl = (e_l + e_b) + (skip ? n1 : 0.0);
-            b_b = has_blank ? nbb : 0.0;
-            b_l = has_lab_b ? nbl : 0.0;
-            lvl += e1;
+            // of the next warp published b_l + log2 y_l with its column
+            float n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+            if (lane == 31) n1 = (warp + 1 < nwarp) ? edge[(buf ^ 1) * 32 + warp + 1] : kNegInf;
+            const float nbb = lse2_log2(e_b, n1);
+            const float nbl = lse3_log2(e_l, e_b, skip ? n1 : kNegInf);
+            b_b = has_blank ? nbb - m_prev : kNegInf;
+            b_l = has_lab_b ? nbl - m_prev : kNegInf;
+            lvl += (double)m_prev;
         }
         // occupancy of column t from the look-ahead alpha
         {
             float* o = occ + (size_t)t * U;
             const double ct = *reinterpret_cast<const double*>(sl);
-            const float Kt = (float)(ct + (double)lvl - logp2);
-            if (has_blank) o[2 * i] = ex2_fast(sl[4 + P + i] + log2_store(b_b) + Kt);
-            if (has_lab_b) o[2 * i - 1] = ex2_fast(sl[4 + 2 * P + i] + log2_store(b_l) + Kt);
+            const float Kt = (float)(ct + lvl - logp2);
+            if (has_blank) o[2 * i] = ex2_fast(sl[4 + P + i] + b_b + Kt);
+            if (has_lab_b) o[2 * i - 1] = ex2_fast(sl[4 + 2 * P + i] + b_l + Kt);
         }
-        // publish column t: top word per warp, and for the previous warp's last lane the product
-        // b_l(first lane) y_t(its label): what it needs as "e of the next label state" in the next step
-        const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)max(__double2hiint(b_b), __double2hiint(b_l)));
+        // publish column t: maximum per warp, and for the previous warp's last lane the sum
+        // b_l(first lane) + log2 y_t(its label): what it needs as "e of the next label state" in the next step
+        const float c = warp_max_redux(fmaxf(b_b, b_l));
         if (lane == 0) {
-            wtop[buf * 32 + warp] = hi;
-            edge[buf * 32 + warp] = b_l * (double)slot(t - 1)[4 + i];      // y_t of label i-1 (this thread's own copy)
+            wtop[buf * 32 + warp] = float_key(c);
+            edge[buf * 32 + warp] = has_lab_b ? b_l + slot(t - 1)[4 + i] : kNegInf;   // y_t of label i-1 (this thread's own copy)
         }
     }
     cp_async_wait<0>();
@@ -1075,11 +1080,11 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
             else if (fst[j]) {
                 float o = 0.f;
                 for (int k = j; k >= 0; k = nxt[k]) o += occ[2 * k + 1];
-                g[eff[j]] = base * (1.0f - o / lpl[1 + j]);
+                g[eff[j]] = base * (1.0f - o / ex2_fast(lpl[1 + j]));
             }
         }
         ob = warp_sum(ob);
-        if (lane == 0) g[p.blank] = base * (1.0f - ob / lpl[0]);
+        if (lane == 0) g[p.blank] = base * (1.0f - ob / ex2_fast(lpl[0]));
         return;
     }
     if constexpr (NV4 > 0) {
@@ -1127,7 +1132,7 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
             for (int k = j; k >= 0; k = nxt[k]) o += occ[2 * k + 1];
             const int c = eff[j];
             // a label equal to the blank index is folded into the blank entry below
-            if (c != p.blank) g[c] = (lpl[1 + j] - o) * scale;
+            if (c != p.blank) g[c] = (ex2_fast(lpl[1 + j]) - o) * scale;
         }
     }
     // labels that coincide with the blank index (pathological but legal input)
@@ -1135,7 +1140,7 @@ __device__ __forceinline__ void grad_body(const Params& p, long long row, int la
     for (int j = lane; j < L; j += 32)
         if (eff[j] == p.blank) extra += occ[2 * j + 1];
     extra = warp_sum(extra);
-    if (lane == 0) g[p.blank] = (lpl[0] - (ob + extra)) * scale;
+    if (lane == 0) g[p.blank] = (ex2_fast(lpl[0]) - (ob + extra)) * scale;
 }
 
 template <int NV4>
@@ -1441,7 +1446,7 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
     if (phases & ASRK_PHASE_CTC_LATTICE) {
-        const size_t lsm = sizeof(double) * (64 + 32 + 2) + sizeof(float) * kRing * lattice_slot_floats(P);
+        const size_t lsm = sizeof(double) * 66 + sizeof(float) * kRing * lattice_slot_floats(P);
         cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
         lattice_kernel<<<B, P, lsm, stream>>>(p), asrk::note_launch();
     }

@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+rm -f gpurun_out/parity.json
+timeout 2700 python -m pytest tests -x -q -m gpu > gpurun_out/r2_t10.log 2>&1
+echo "pytest exit $?" >> gpurun_out/r2_t10.log
+for w in c2 c3 c5; do
+  timeout 900 python bench.py --steps 20 --warmup 5 --workload $w --no-cpu-baseline > gpurun_out/r2_bench10_$w.json 2> gpurun_out/r2_bench10_$w.err
+done
+ASRK_LIB_SUFFIX=_tim timeout 300 python tools/ctc_phase_times.py > gpurun_out/r2_ctcphase10.log 2>&1
+echo done
