@@ -451,6 +451,21 @@ __device__ __forceinline__ float lse3_log2(float a, float b, float c) {
     const float ms = (m == kNegInf) ? 0.f : m;
     return m + lg2_fast(ex2_fast(a - ms) + ex2_fast(b - ms) + ex2_fast(c - ms));
 }
+// log2(2^a + 2^b [+ 2^c]) with the running values in DOUBLE and the transcendentals in fp32: the exp arguments are
+// differences <= 0 and the log argument is in [1, 3], so the absolute error per step is ~3e-7 whatever the magnitude
+// of the running values -- fp32 running values drift: at T = 1998 the states that carry the occupancy sit ~1000
+// binades below the column maximum, where a float has 6e-5 of resolution per step.
+__device__ __forceinline__ double lse2_log2d(double a, double b) {
+    const double m = fmax(a, b);
+    const double ms = (m == (double)kNegInf) ? 0.0 : m;
+    return m + (double)lg2_fast(ex2_fast((float)(a - ms)) + ex2_fast((float)(b - ms)));
+}
+__device__ __forceinline__ double lse3_log2d(double a, double b, double c) {
+    const double m = fmax(fmax(a, b), c);
+    const double ms = (m == (double)kNegInf) ? 0.0 : m;
+    return m + (double)lg2_fast(ex2_fast((float)(a - ms)) + ex2_fast((float)(b - ms)) + ex2_fast((float)(c - ms)));
+}
+
 // warp maximum of arbitrary-sign floats with ONE REDUX: floats order like the unsigned
 // patterns  bits ^ (sign ? 0xffffffff : 0x80000000)
 __device__ __forceinline__ float warp_max_redux(float v) {
@@ -863,10 +878,10 @@ __global__ void lattice_kernel(Params p) {
     const int i = threadIdx.x;
     const int P = blockDim.x;
     const int lane = i & 31, warp = i >> 5, nwarp = P >> 5;
-    float* edge = reinterpret_cast<float*>(smd);              // [2][32] last / first value of every warp
-    unsigned* wtop = reinterpret_cast<unsigned*>(smd + 32);   // [2][32] key of every warp's column maximum
-    float* fin2 = reinterpret_cast<float*>(smd + 64);         // [2]
-    float* ring = reinterpret_cast<float*>(smd + 66);         // [kRing][slot]: look-ahead frames, filled by cp.async
+    float* edge = reinterpret_cast<float*>(smd);              // [2][32] doubles: last / first value of every warp
+    unsigned* wtop = reinterpret_cast<unsigned*>(smd + 64);   // [2][32] key of every warp's column maximum
+    float* fin2 = reinterpret_cast<float*>(smd + 96);         // [2] doubles
+    float* ring = reinterpret_cast<float*>(smd + 98);         // [kRing][slot]: look-ahead frames, filled by cp.async
     const int SF = lattice_slot_floats(P);
     const int status = p.row_status[b];
     const int L = p.eff_len[b];
@@ -908,52 +923,57 @@ __global__ void lattice_kernel(Params p) {
         cp_async4(s + 4 + i, lpl + (size_t)(in ? f : 0) * S + 1 + (has_lab_a ? i : 0), (in && has_lab_a) ? 4 : 0);
         cp_async_commit();
     };
-    float a_b = kNegInf, a_l = kNegInf;
+    // running values: absolute log2 alpha in double (exchanged as such); STORED as float32 relative to the level C
+    // (double, the same in every thread: it follows the block-wide maximum of the previous column)
+    double* edged = reinterpret_cast<double*>(edge);   // one double per warp and buffer
+    double a_b = ninf, a_l = ninf;
     if (i == 0) {
-        a_b = lpl[0];
-        if (L >= 1) a_l = lpl[1];
+        a_b = (double)lpl[0];
+        if (L >= 1) a_l = (double)lpl[1];
     }
-    if (has_blank) occ[2 * i] = a_b;
-    if (has_lab_a) occ[2 * i + 1] = a_l;
-    if (i == 0) coff[0] = 0.0;
+    double lvl = 0.0;                             // C_t
     {
-        const float c = warp_max_redux(fmaxf(a_b, a_l));
+        const float rb = (float)a_b, rl = (float)a_l;
+        if (has_blank) occ[2 * i] = rb;
+        if (has_lab_a) occ[2 * i + 1] = rl;
+        if (i == 0) coff[0] = 0.0;
+        const float c = warp_max_redux(fmaxf(rb, rl));
         if (lane == 0) wtop[warp] = float_key(c);
-        if (lane == 31) edge[warp] = a_l;
+        if (lane == 31) edged[warp] = a_l;
     }
     for (int k = 0; k < kRing - 1; ++k) fetch_a(1 + k);
-    double lvl = 0.0;
     for (int t = 1; t < T; ++t) {
         const int buf = (t - 1) & 1;
         cp_async_wait<kRing - 2>();                // this thread's copies of frame t have landed
         __syncthreads();                           // ... everybody's; column t-1 is published (edges, maxima)
         fetch_a(t + kRing - 1);                    // (into the slot frame t-1 used: everyone has read it)
         const float* sl = slot(t);
-        const float m_prev = block_max(buf);
-        const float yb = sl[2], yl = has_lab_a ? sl[4 + i] : kNegInf;
-        float p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
-        if (lane == 0) p1 = (warp > 0) ? edge[buf * 32 + warp - 1] : kNegInf;
-        const float nb = yb + lse2_log2(a_b, p1);
-        const float nl = yl + lse3_log2(a_l, a_b, skip ? p1 : kNegInf);
-        a_b = has_blank ? nb - m_prev : kNegInf;
-        a_l = nl - m_prev;
-        lvl += (double)m_prev;
+        lvl += (double)block_max(buf);
+        const double yb = (double)sl[2], yl = has_lab_a ? (double)sl[4 + i] : ninf;
+        double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+        if (lane == 0) p1 = (warp > 0) ? edged[buf * 32 + warp - 1] : ninf;
+        const double nb = yb + lse2_log2d(a_b, p1);
+        const double nl = yl + lse3_log2d(a_l, a_b, skip ? p1 : ninf);
+        a_b = has_blank ? nb : ninf;
+        a_l = nl;
+        const float rb = (float)(a_b - lvl), rl = (float)(a_l - lvl);
         float* o = occ + (size_t)t * U;
-        if (has_blank) o[2 * i] = a_b;
-        if (has_lab_a) o[2 * i + 1] = a_l;
+        if (has_blank) o[2 * i] = rb;
+        if (has_lab_a) o[2 * i + 1] = rl;
         if (i == 0) coff[t] = lvl;
-        const float c = warp_max_redux(fmaxf(a_b, a_l));
+        const float c = warp_max_redux(fmaxf(rb, rl));
         if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = float_key(c);
-        if (lane == 31) edge[(buf ^ 1) * 32 + warp] = a_l;
+        if (lane == 31) edged[(buf ^ 1) * 32 + warp] = a_l;
     }
     cp_async_wait<0>();
-    // log2 p = C_{T-1} + log2( 2^ahat_{T-1}(2L) + 2^ahat_{T-1}(2L-1) )
+    // log2 p = log2( alpha_{T-1}(2L) + alpha_{T-1}(2L-1) )
+    double* fin2d = reinterpret_cast<double*>(fin2);
     __syncthreads();
-    if (i == L) fin2[0] = a_b;
-    if (i == L - 1) fin2[1] = a_l;
-    if (L == 0 && i == 0) fin2[1] = kNegInf;
+    if (i == L) fin2d[0] = a_b;
+    if (i == L - 1) fin2d[1] = a_l;
+    if (L == 0 && i == 0) fin2d[1] = ninf;
     __syncthreads();
-    const double logp2 = lvl + (double)lse2_log2(fin2[0], fin2[1]);
+    const double logp2 = lse2_log2d(fin2d[0], fin2d[1]);
     const double logp = logp2 * 0.6931471805599453;
     if (i == 0) {
         p.logp[b] = logp;
@@ -965,7 +985,7 @@ __global__ void lattice_kernel(Params p) {
 
     // ------------------------------ beta -------------------------------
     // beta excludes y_t; e(u) = beta_{t+1}(u) + log2 y_{t+1}(l'_u).  occupancy(t, u) = alpha_t(u) beta_t(u) / p
-    //   = 2^(ahat + bhat + (C_t + D_t - log2 p))
+    //   = 2^(ahat + (C_t - log2 p) + beta)  with beta absolute in double
     // look-ahead for the step that produces column f: y of frame f + 1, the stored alpha column f and its level
     auto fetch_b = [&](int f) {
         float* s = slot(f);
@@ -981,13 +1001,12 @@ __global__ void lattice_kernel(Params p) {
         cp_async4(s + 4 + 2 * P + i, o + (has_lab_b ? 2 * i - 1 : 0), (in && has_lab_b) ? 4 : 0);
         cp_async_commit();
     };
-    float b_l = kNegInf, b_b = kNegInf;
+    double b_l = ninf, b_b = ninf;
     if (i == L) {
-        b_b = 0.f;
-        if (L >= 1) b_l = 0.f;
+        b_b = 0.0;
+        if (L >= 1) b_l = 0.0;
     }
     for (int k = 0; k < kRing - 1; ++k) fetch_b(T - 1 - k);
-    lvl = 0.0;
     for (int t = T - 1; t >= 0; --t) {
         const int buf = t & 1;
         cp_async_wait<kRing - 3>();                // frames t and t-1 have landed (t-1: the edge value below)
@@ -995,35 +1014,28 @@ __global__ void lattice_kernel(Params p) {
         fetch_b(t - (kRing - 1));                  // (into the slot frame t+1 used: everyone has read it)
         const float* sl = slot(t);
         if (t < T - 1) {
-            const float m_prev = block_max(buf ^ 1);
-            const float yb = sl[2], yl = has_lab_b ? sl[4 + i] : kNegInf;
-            const float e_b = b_b + yb;
-            const float e_l = b_l + yl;
+            const double yb = (double)sl[2], yl = has_lab_b ? (double)sl[4 + i] : ninf;
+            const double e_b = b_b + yb;
+            const double e_l = b_l + yl;
             // the pair needs e of the NEXT label state (2i+1): lane i+1's e_l; across warps the first lane
-            // of the next warp published b_l + log2 y_l with its column
-            float n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
-            if (lane == 31) n1 = (warp + 1 < nwarp) ? edge[(buf ^ 1) * 32 + warp + 1] : kNegInf;
-            const float nbb = lse2_log2(e_b, n1);
-            const float nbl = lse3_log2(e_l, e_b, skip ? n1 : kNegInf);
-            b_b = has_blank ? nbb - m_prev : kNegInf;
-            b_l = has_lab_b ? nbl - m_prev : kNegInf;
-            lvl += (double)m_prev;
+            // of the next warp published b_l + log2 y_l (absolute, double) with its column
+            double n1 = __shfl_down_sync(0xffffffffu, e_l, 1);
+            if (lane == 31) n1 = (warp + 1 < nwarp) ? edged[(buf ^ 1) * 32 + warp + 1] : ninf;
+            const double nbb = lse2_log2d(e_b, n1);
+            const double nbl = lse3_log2d(e_l, e_b, skip ? n1 : ninf);
+            b_b = has_blank ? nbb : ninf;
+            b_l = has_lab_b ? nbl : ninf;
         }
         // occupancy of column t from the look-ahead alpha
         {
             float* o = occ + (size_t)t * U;
-            const double ct = *reinterpret_cast<const double*>(sl);
-            const float Kt = (float)(ct + lvl - logp2);
-            if (has_blank) o[2 * i] = ex2_fast(sl[4 + P + i] + b_b + Kt);
-            if (has_lab_b) o[2 * i - 1] = ex2_fast(sl[4 + 2 * P + i] + b_l + Kt);
+            const double kt = *reinterpret_cast<const double*>(sl) - logp2;      // C_t - log2 p
+            if (has_blank) o[2 * i] = ex2_fast((float)((double)sl[4 + P + i] + kt + b_b));
+            if (has_lab_b) o[2 * i - 1] = ex2_fast((float)((double)sl[4 + 2 * P + i] + kt + b_l));
         }
-        // publish column t: maximum per warp, and for the previous warp's last lane the sum
-        // b_l(first lane) + log2 y_t(its label): what it needs as "e of the next label state" in the next step
-        const float c = warp_max_redux(fmaxf(b_b, b_l));
-        if (lane == 0) {
-            wtop[buf * 32 + warp] = float_key(c);
-            edge[buf * 32 + warp] = has_lab_b ? b_l + slot(t - 1)[4 + i] : kNegInf;   // y_t of label i-1 (this thread's own copy)
-        }
+        // publish column t for the previous warp's last lane: b_l(first lane) + log2 y_t(its label), what it
+        // needs as "e of the next label state" in the next step
+        if (lane == 0) edged[buf * 32 + warp] = has_lab_b ? b_l + (double)slot(t - 1)[4 + i] : ninf;   // y_t of label i-1 (own copy)
     }
     cp_async_wait<0>();
 }
@@ -1446,7 +1458,7 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (phases & ASRK_PHASE_CTC_ROWS) launch_rows<true>(p, nv4, stream);
     int P = ((label_stride + 1) + 31) / 32 * 32;
     if (phases & ASRK_PHASE_CTC_LATTICE) {
-        const size_t lsm = sizeof(double) * 66 + sizeof(float) * kRing * lattice_slot_floats(P);
+        const size_t lsm = sizeof(double) * 98 + sizeof(float) * kRing * lattice_slot_floats(P);
         cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
         lattice_kernel<<<B, P, lsm, stream>>>(p), asrk::note_launch();
     }
