@@ -532,32 +532,36 @@ __global__ void __launch_bounds__(256) stats_kernel(Params p) {
 // ---------------------------------------------------------------------------
 // z-score: out = (y - mean) / std, in place; grid (x, utterance), pure streaming
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) normalize_kernel(Params p) {
+// 32 registers per thread on purpose: in the step this kernel runs NEXT TO the fused CTC kernel, whose two CTAs per
+// SM leave ~8 K registers and ~11 KB of shared memory; at 48 registers one 128-thread CTA fitted there (8 KB in
+// flight per SM, ~1.2 TB/s chip-wide, and 2/3 of the z-score was still to do when the CTC kernel had finished), at
+// 32 two do.
+__global__ void __launch_bounds__(128, 16) normalize_kernel(Params p) {
     // newest utterances first: their rows are the ones the main kernel's evict-last stores still hold in L2
     const int b = (int)gridDim.y - 1 - (int)blockIdx.y;
     __shared__ __align__(16) float s_stat[3 * kBins];
     for (int k = threadIdx.x; k < 3 * kBins; k += blockDim.x) s_stat[k] = p.stats[(size_t)b * 3 * kBins + k];
     __syncthreads();
     const long long fo = p.frame_offsets[b];
-    const long long nfr = p.frame_offsets[b + 1] - fo;
+    const int nfr = (int)(p.frame_offsets[b + 1] - fo);
     const long long row0 = p.out_row_offsets ? p.out_row_offsets[b] : fo;
     float4* base = reinterpret_cast<float4*>(p.out + (size_t)row0 * kBins);
-    const long long n4 = nfr * (kBins / 4);
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int n4 = nfr * (kBins / 4);
+    const int stride = (int)(gridDim.x * blockDim.x);
     constexpr int kU = 4;
     const uint64_t drop = l2_policy_evict_first();
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += kU * stride) {
+    for (int i0 = (int)(blockIdx.x * blockDim.x + threadIdx.x); i0 < n4; i0 += kU * stride) {
         float4 v[kU];
 #pragma unroll
         for (int e = 0; e < kU; ++e) {
-            const long long i = i0 + e * stride;
+            const int i = i0 + e * stride;
             if (i < n4) v[e] = ldg_hint(base + i, drop);
         }
 #pragma unroll
         for (int e = 0; e < kU; ++e) {
-            const long long i = i0 + e * stride;
+            const int i = i0 + e * stride;
             if (i < n4) {
-                const int k = (int)(i % (kBins / 4)) * 4;
+                const int k = (i % (kBins / 4)) * 4;
                 const float4 mh = *reinterpret_cast<const float4*>(s_stat + k);
                 const float4 ml = *reinterpret_cast<const float4*>(s_stat + kBins + k);
                 const float4 iv = *reinterpret_cast<const float4*>(s_stat + 2 * kBins + k);
