@@ -60,6 +60,23 @@ class HotPathStep:
         self._ev_join2 = torch.cuda.Event()
         self._ev_main = torch.cuda.Event()
 
+    def capture(self, *args, loss_acc=None, **kw):
+        """Capture one step on fixed device buffers (same arguments as ``__call__``; pass ``feat_out`` / ``grad_out``)
+        into a CUDA graph: the steady state of a training loop replays it without any host-side enqueue between
+        its kernels.  ``loss_acc`` (float64 [2] device tensor): the per-step [sum loss, n] is ADDED to it inside the
+        graph (``ctc.loss_sum(..., accumulate=True)``).  Returns (graph, features, CtcResult); ``graph.replay()``
+        runs the step on the current stream."""
+        torch = self.torch
+        # workspaces, function attributes and the streams' pools exist before the capture starts
+        self(*args, **kw)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            feats, res = self(*args, **kw)
+            if loss_acc is not None:
+                ctc.loss_sum(res.loss, res.row_status, out=loss_acc, accumulate=True)
+        return g, feats, res
+
     def from_host(self, h_samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
                   h_logits, h_labels, label_len, input_len, blank=None, logits_dev=None, **kw):
         """The same step with the per-step inputs in PINNED HOST memory: PCM and labels are copied
