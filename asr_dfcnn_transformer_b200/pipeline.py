@@ -60,6 +60,13 @@ class HotPathStep:
         self._ev_join2 = torch.cuda.Event()
         self._ev_main = torch.cuda.Event()
 
+    def reserve(self, batch, total_frames, T, label_stride):
+        """Size the scratch buffers of both streams for the largest step that will be captured: the grow-only
+        workspaces must not be re-allocated once a graph holds their addresses."""
+        L = _lib.lib()
+        features.workspace(L.asrk_spectrogram_workspace_bytes(int(batch), int(total_frames)), self.device, "spec", self.side)
+        features.workspace(L.asrk_ctc_workspace_bytes(int(T), int(batch), int(label_stride)), self.device, "ctc", self.hi)
+
     def capture(self, *args, loss_acc=None, **kw):
         """Capture one step on fixed device buffers (same arguments as ``__call__``; pass ``feat_out`` / ``grad_out``)
         into a CUDA graph: the steady state of a training loop replays it without any host-side enqueue between
@@ -121,10 +128,12 @@ class HotPathStep:
             self._ev_join2.record(self.hi)
         cur.wait_event(self._ev_join)
         cur.wait_event(self._ev_join2)
-        # (the tensors were allocated / are used on other streams than the caller's: tell the allocator)
-        for t in (feats, res.loss, res.grad, res.row_status, res.tokens, res.token_len, res.neg_sum_logits):
-            if t is not None:
-                t.record_stream(cur)
+        # (the tensors were allocated / are used on other streams than the caller's: tell the allocator -- not under a
+        # graph capture, where the graph's private pool owns them)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (feats, res.loss, res.grad, res.row_status, res.tokens, res.token_len, res.neg_sum_logits):
+                if t is not None:
+                    t.record_stream(cur)
         return feats, res
 
 

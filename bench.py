@@ -532,6 +532,8 @@ def main():
     use_graph = (not args.no_graph) and args.surface == "logits" and args.workload in ("c2", "c3", "c5")
     launches_per_step = None
     if use_graph:
+        hot_path(dev).reserve(BATCH, max(d.total_frames for d in pool), max(d.logits.shape[0] for d in pool),
+                              pool[0].labels.shape[1])
         for db in pool:
             n0 = L.asrk_launch_count()
             db.graph, _, db.res = hot_path(dev).capture(
