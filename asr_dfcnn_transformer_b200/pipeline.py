@@ -49,16 +49,15 @@ class HotPathStep:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.feature_ctas = int(feature_ctas)
         self.side = torch.cuda.Stream(device=self.device)
-        # the CTC kernels go on a HIGH-priority stream: when the persistent feature kernel's CTAs retire, the CTC
-        # CTAs (two per SM) are dispatched before the thousands of small z-score CTAs that became eligible at the
-        # same moment; the z-score then runs in the registers / shared memory the CTC kernel leaves over and takes
-        # the whole chip when it has gone.  With equal priorities the z-score kernel (enqueued first) filled every SM
-        # and the two HBM-bound kernels ran one after the other (measured: features 166 us + CTC 60 us = step 226 us).
-        self.hi = torch.cuda.Stream(device=self.device, priority=-1)
+        # the CTC kernels go on a second stream of their own (fixed streams keep the scratch buffers' addresses fixed
+        # for graph capture).  Measured and dropped: a HIGH-priority stream for the CTC kernel, gated behind the
+        # transform kernel, so that its CTAs are dispatched before the z-score CTAs -- the two HBM-bound kernels
+        # overlap by no more than ~18 us however they are ordered (tools/time_tail.py), and the extra event and
+        # launch cost 4 us per step.
+        self.hi = torch.cuda.Stream(device=self.device)
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
         self._ev_join2 = torch.cuda.Event()
-        self._ev_main = torch.cuda.Event()
 
     def reserve(self, batch, total_frames, T, label_stride):
         """Size the scratch buffers of both streams for the largest step that will be captured: the grow-only
@@ -109,18 +108,10 @@ class HotPathStep:
         self.side.wait_event(self._ev_fork)
         self.hi.wait_event(self._ev_fork)
         with torch.cuda.stream(self.side):
-            # transform kernel, then (behind an event the CTC stream waits for) the z-score kernels: the CTC kernel
-            # must not become eligible before the transform kernel owns the SMs, or -- having priority -- it would
-            # run first and the transform would trail it
             feats = features.spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch,
                                                 total_frames, mode, out=feat_out, cta_limit=self.feature_ctas,
-                                                stream=self.side,
-                                                phases=_lib.PHASE_SPEC_SETUP | _lib.PHASE_SPEC_MAIN)
-            self._ev_main.record(self.side)
-            features.spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
-                                        mode, out=feats, stream=self.side, phases=_lib.PHASE_SPEC_NORMALIZE)
+                                                stream=self.side)
             self._ev_join.record(self.side)
-        self.hi.wait_event(self._ev_main)
         with torch.cuda.stream(self.hi):
             res = ctc.ctc_loss_grad(logits, labels, label_len, input_len, blank, layout=layout,
                                     grad_scale=grad_scale, grad_out=grad_out, decode=decode, bounds=ctc_bounds,
