@@ -77,7 +77,8 @@ class HotPathStep:
         self(*args, **kw)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: other threads of the process (NCCL's watchdog polls CUDA events) must not invalidate the capture
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             feats, res = self(*args, **kw)
             if loss_acc is not None:
                 ctc.loss_sum(res.loss, res.row_status, out=loss_acc, accumulate=True)

@@ -459,6 +459,9 @@ def main():
                                   str(args.gpus), "--master-addr", "127.0.0.1", "--master-port", str(port),
                                   os.path.abspath(__file__)] + sys.argv[1:])
 
+    if os.environ.get("ASRK_BENCH_WATCHDOG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["ASRK_BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
