@@ -10,12 +10,14 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
-decode = len(sys.argv) > 3 and sys.argv[3] == "decode"
+workload = sys.argv[2] if len(sys.argv) > 2 else "c2"
+surface = sys.argv[3] if len(sys.argv) > 3 else "logits"
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
-db = bench.DeviceBatch(bench.make_batch(2000, batch=batch), dev, torch)
+w = bench.WORKLOADS[workload]
+db = bench.DeviceBatch(bench.make_batch(2000, w["batch"], workload), dev, torch, workload, surface)
 for _ in range(steps):
-    r = bench.run_step(db)
+    r = bench.run_step(db, surface)
 torch.cuda.synchronize()
-print("loss sum", float(r.loss.sum()), "status max", int(r.row_status.max()))
+if r is not None:
+    print("loss sum", float(r.loss.sum()), "status max", int(r.row_status.max()))
