@@ -72,8 +72,10 @@ struct Params {
     float* rowmax;       // [B][T]
     int* argmax;         // [B][T]
     float* lpl;          // [B][T][Ls+1]   slot 0 = blank, slot 1+j = label j (log2 of the softmax probability)
-    float* occ;          // [B][T][2 Ls+1] alpha (scaled) then occupancy, lattice order
-    double* coff;        // [B][T]        alpha offsets
+    float* occ;          // [B][T][2 Ls+1] log2 alpha relative to the column's level, lattice order
+    double* coff;        // [B][T]        alpha levels C_t
+    float* beta;         // [B][T][2 Ls+1] log2 beta relative to the column's level
+    double* coffb;       // [B][T]        beta levels D_t
     double* logp;        // [B]
     int* need_generic;   // [1] set by prep when some utterance does not fit the fused kernel
     int Ls;              // label_stride
@@ -93,7 +95,7 @@ __host__ __device__ __forceinline__ bool small_lattice(int L, int T) {
 }
 
 struct WsLayout {
-    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, coff, logp, flag, total;
+    size_t eff_labels, eff_len, chain_next, chain_first, lse, rowmax, argmax, lpl, occ, coff, beta, coffb, logp, flag, total;
 };
 
 static WsLayout ws_layout(int T, int B, int Ls) {
@@ -110,6 +112,8 @@ static WsLayout ws_layout(int T, int B, int Ls) {
     l.lpl = o;         o = align_up(o + sizeof(float) * BT * (size_t)(Ls + 1), 256);
     l.occ = o;         o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
     l.coff = o;        o = align_up(o + sizeof(double) * BT, 256);
+    l.beta = o;        o = align_up(o + sizeof(float) * BT * (size_t)(2 * Ls + 1), 256);
+    l.coffb = o;       o = align_up(o + sizeof(double) * BT, 256);
     l.logp = o;        o = align_up(o + sizeof(double) * (size_t)B, 256);
     l.flag = o;        o = align_up(o + sizeof(int), 256);
     l.total = o;
@@ -455,6 +459,21 @@ __device__ __forceinline__ float lse3_log2(float a, float b, float c) {
 // differences <= 0 and the log argument is in [1, 3], so the absolute error per step is ~3e-7 whatever the magnitude
 // of the running values -- fp32 running values drift: at T = 1998 the states that carry the occupancy sit ~1000
 // binades below the column maximum, where a float has 6e-5 of resolution per step.
+#ifndef ASRK_LSE_V1
+// The step of the generic lattice is bound by the conversion / special-function unit (16 lanes per clock and SM):
+// the largest term of the sum is exactly 1, so only the OTHER terms are converted and exponentiated.
+__device__ __forceinline__ double lse2_log2d(double a, double b) {
+    const double m = fmax(a, b), n = fmin(a, b);
+    const double ms = (m == (double)kNegInf) ? 0.0 : m;
+    return m + (double)lg2_fast(1.0f + ex2_fast((float)(n - ms)));
+}
+__device__ __forceinline__ double lse3_log2d(double a, double b, double c) {
+    const double hi = fmax(a, b), lo = fmin(a, b);
+    const double m = fmax(hi, c), x = fmin(hi, c);        // m the largest; x and lo the other two
+    const double ms = (m == (double)kNegInf) ? 0.0 : m;
+    return m + (double)lg2_fast((1.0f + ex2_fast((float)(x - ms))) + ex2_fast((float)(lo - ms)));
+}
+#else
 __device__ __forceinline__ double lse2_log2d(double a, double b) {
     const double m = fmax(a, b);
     const double ms = (m == (double)kNegInf) ? 0.0 : m;
@@ -465,6 +484,7 @@ __device__ __forceinline__ double lse3_log2d(double a, double b, double c) {
     const double ms = (m == (double)kNegInf) ? 0.0 : m;
     return m + (double)lg2_fast(ex2_fast((float)(a - ms)) + ex2_fast((float)(b - ms)) + ex2_fast((float)(c - ms)));
 }
+#endif
 
 // warp maximum of arbitrary-sign floats with ONE REDUX: floats order like the unsigned
 // patterns  bits ^ (sign ? 0xffffffff : 0x80000000)
@@ -866,21 +886,27 @@ __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
 // step (a register look-ahead does not work: six scoreboards per warp, waiting for the oldest load waits for the
 // newest too).  Round 1: 1.1 us per step, all of it L2 latency; T = 1998 frames x 2 sweeps = 4.5 ms per C3 batch.
 constexpr int kRing = 8;
-__host__ __device__ inline int lattice_slot_floats(int P) { return 4 + 3 * P; }   // coff(2) yb(1) pad(1) | yl | ab | al
+__host__ __device__ inline int lattice_slot_floats(int P) { return 4 + P; }   // pad(2) yb(1) pad(1) | yl[P]
 __device__ __forceinline__ unsigned float_key(float v) {      // order-preserving bit pattern
     const unsigned b = __float_as_uint(v);
     return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
 }
 __device__ __forceinline__ float key_float(unsigned m) { return __uint_as_float(m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu)); }
+// grid (B, 2): CTA (b, 0) runs the alpha sweep of utterance b and CTA (b, 1) -- launched only when a gradient is
+// wanted -- its beta sweep AT THE SAME TIME on another SM (the two recursions are independent; round 2's first
+// version ran them back to back in one CTA, the beta sweep forming the occupancies from the stored alpha: 2 T
+// dependent steps instead of T).  Both store their columns as float32 relative to their own per-column level
+// (double); grad_kernel forms occupancy(t, u) = 2^(ahat + bhat + C_t + D_t - log2 p) when it stages a frame.
 __global__ void lattice_kernel(Params p) {
     extern __shared__ double smd[];
     const int b = blockIdx.x;
+    const bool beta = (blockIdx.y == 1);
     const int i = threadIdx.x;
     const int P = blockDim.x;
     const int lane = i & 31, warp = i >> 5, nwarp = P >> 5;
-    float* edge = reinterpret_cast<float*>(smd);              // [2][32] doubles: last / first value of every warp
+    double* edged = smd;                                      // [2][32] last / first running value of every warp
     unsigned* wtop = reinterpret_cast<unsigned*>(smd + 64);   // [2][32] key of every warp's column maximum
-    float* fin2 = reinterpret_cast<float*>(smd + 96);         // [2] doubles
+    double* fin2d = smd + 96;                                 // [2]
     float* ring = reinterpret_cast<float*>(smd + 98);         // [kRing][slot]: look-ahead frames, filled by cp.async
     const int SF = lattice_slot_floats(P);
     const int status = p.row_status[b];
@@ -888,15 +914,13 @@ __global__ void lattice_kernel(Params p) {
     const int T = p.input_len[b];
     const double ninf = (double)kNegInf;
     if (status == ASRK_ROW_BAD_LENGTH) {
-        if (i == 0) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
+        if (i == 0 && !beta) { p.loss[b] = __int_as_float(0x7fc00000); p.logp[b] = ninf; }
         return;
     }
     if (p.fused && small_lattice(L, T)) return;   // handled by fused_small_kernel
     const int S = p.Ls + 1;
     const int U = 2 * p.Ls + 1;
     const float* lpl = p.lpl + (size_t)b * p.T * S;
-    float* occ = p.occ + (size_t)b * p.T * U;
-    double* coff = p.coff + (size_t)b * p.T;
     const int* eff = p.eff_labels + (size_t)b * p.Ls;
 
     const int lab_i = (i < L) ? eff[i] : -1;                     // label index i   (state 2i+1)
@@ -914,91 +938,86 @@ __global__ void lattice_kernel(Params p) {
     };
     auto slot = [&](int frame) { return ring + (size_t)((frame % kRing + kRing) % kRing) * SF; };
 
-    // ------------------------------ alpha ------------------------------
-    // look-ahead: log2 y of frame f (blank, this thread's label) -> slot(f)
-    auto fetch_a = [&](int f) {
-        float* s = slot(f);
-        const bool in = (f >= 1 && f < T);
-        if (i == 0) cp_async4(s + 2, lpl + (size_t)(in ? f : 0) * S, in ? 4 : 0);
-        cp_async4(s + 4 + i, lpl + (size_t)(in ? f : 0) * S + 1 + (has_lab_a ? i : 0), (in && has_lab_a) ? 4 : 0);
-        cp_async_commit();
-    };
-    // running values: absolute log2 alpha in double (exchanged as such); STORED as float32 relative to the level C
-    // (double, the same in every thread: it follows the block-wide maximum of the previous column)
-    double* edged = reinterpret_cast<double*>(edge);   // one double per warp and buffer
-    double a_b = ninf, a_l = ninf;
-    if (i == 0) {
-        a_b = (double)lpl[0];
-        if (L >= 1) a_l = (double)lpl[1];
+    if (!beta) {
+        // ------------------------------ alpha ------------------------------
+        float* occ = p.occ + (size_t)b * p.T * U;
+        double* coff = p.coff + (size_t)b * p.T;
+        // look-ahead: log2 y of frame f (blank, this thread's label) -> slot(f)
+        auto fetch_a = [&](int f) {
+            float* s = slot(f);
+            const bool in = (f >= 1 && f < T);
+            if (i == 0) cp_async4(s + 2, lpl + (size_t)(in ? f : 0) * S, in ? 4 : 0);
+            cp_async4(s + 4 + i, lpl + (size_t)(in ? f : 0) * S + 1 + (has_lab_a ? i : 0), (in && has_lab_a) ? 4 : 0);
+            cp_async_commit();
+        };
+        // running values: absolute log2 alpha in double (exchanged as such); STORED as float32 relative to the level C
+        // (double, the same in every thread: it follows the block-wide maximum of the previous column)
+        double a_b = ninf, a_l = ninf;
+        if (i == 0) {
+            a_b = (double)lpl[0];
+            if (L >= 1) a_l = (double)lpl[1];
+        }
+        double lvl = 0.0;                             // C_t
+        {
+            const float rb = (float)a_b, rl = (float)a_l;
+            if (has_blank) occ[2 * i] = rb;
+            if (has_lab_a) occ[2 * i + 1] = rl;
+            if (i == 0) coff[0] = 0.0;
+            const float c = warp_max_redux(fmaxf(rb, rl));
+            if (lane == 0) wtop[warp] = float_key(c);
+            if (lane == 31) edged[warp] = a_l;
+        }
+        for (int k = 0; k < kRing - 1; ++k) fetch_a(1 + k);
+        for (int t = 1; t < T; ++t) {
+            const int buf = (t - 1) & 1;
+            cp_async_wait<kRing - 2>();                // this thread's copies of frame t have landed
+            __syncthreads();                           // ... everybody's; column t-1 is published (edges, maxima)
+            fetch_a(t + kRing - 1);                    // (into the slot frame t-1 used: everyone has read it)
+            const float* sl = slot(t);
+            lvl += (double)block_max(buf);
+            const double yb = (double)sl[2], yl = has_lab_a ? (double)sl[4 + i] : ninf;
+            double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
+            if (lane == 0) p1 = (warp > 0) ? edged[buf * 32 + warp - 1] : ninf;
+            const double nb = yb + lse2_log2d(a_b, p1);
+            const double nl = yl + lse3_log2d(a_l, a_b, skip ? p1 : ninf);
+            a_b = has_blank ? nb : ninf;
+            a_l = nl;
+            const float rb = (float)(a_b - lvl), rl = (float)(a_l - lvl);
+            float* o = occ + (size_t)t * U;
+            if (has_blank) o[2 * i] = rb;
+            if (has_lab_a) o[2 * i + 1] = rl;
+            if (i == 0) coff[t] = lvl;
+            const float c = warp_max_redux(fmaxf(rb, rl));
+            if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = float_key(c);
+            if (lane == 31) edged[(buf ^ 1) * 32 + warp] = a_l;
+        }
+        cp_async_wait<0>();
+        // log2 p = log2( alpha_{T-1}(2L) + alpha_{T-1}(2L-1) )
+        __syncthreads();
+        if (i == L) fin2d[0] = a_b;
+        if (i == L - 1) fin2d[1] = a_l;
+        if (L == 0 && i == 0) fin2d[1] = ninf;
+        __syncthreads();
+        const double logp2 = lse2_log2d(fin2d[0], fin2d[1]);
+        const double logp = logp2 * 0.6931471805599453;
+        if (i == 0) {
+            p.logp[b] = logp;
+            p.loss[b] = (float)(-logp);
+            if (logp == ninf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
+        }
+        return;
     }
-    double lvl = 0.0;                             // C_t
-    {
-        const float rb = (float)a_b, rl = (float)a_l;
-        if (has_blank) occ[2 * i] = rb;
-        if (has_lab_a) occ[2 * i + 1] = rl;
-        if (i == 0) coff[0] = 0.0;
-        const float c = warp_max_redux(fmaxf(rb, rl));
-        if (lane == 0) wtop[warp] = float_key(c);
-        if (lane == 31) edged[warp] = a_l;
-    }
-    for (int k = 0; k < kRing - 1; ++k) fetch_a(1 + k);
-    for (int t = 1; t < T; ++t) {
-        const int buf = (t - 1) & 1;
-        cp_async_wait<kRing - 2>();                // this thread's copies of frame t have landed
-        __syncthreads();                           // ... everybody's; column t-1 is published (edges, maxima)
-        fetch_a(t + kRing - 1);                    // (into the slot frame t-1 used: everyone has read it)
-        const float* sl = slot(t);
-        lvl += (double)block_max(buf);
-        const double yb = (double)sl[2], yl = has_lab_a ? (double)sl[4 + i] : ninf;
-        double p1 = __shfl_up_sync(0xffffffffu, a_l, 1);
-        if (lane == 0) p1 = (warp > 0) ? edged[buf * 32 + warp - 1] : ninf;
-        const double nb = yb + lse2_log2d(a_b, p1);
-        const double nl = yl + lse3_log2d(a_l, a_b, skip ? p1 : ninf);
-        a_b = has_blank ? nb : ninf;
-        a_l = nl;
-        const float rb = (float)(a_b - lvl), rl = (float)(a_l - lvl);
-        float* o = occ + (size_t)t * U;
-        if (has_blank) o[2 * i] = rb;
-        if (has_lab_a) o[2 * i + 1] = rl;
-        if (i == 0) coff[t] = lvl;
-        const float c = warp_max_redux(fmaxf(rb, rl));
-        if (lane == 0) wtop[(buf ^ 1) * 32 + warp] = float_key(c);
-        if (lane == 31) edged[(buf ^ 1) * 32 + warp] = a_l;
-    }
-    cp_async_wait<0>();
-    // log2 p = log2( alpha_{T-1}(2L) + alpha_{T-1}(2L-1) )
-    double* fin2d = reinterpret_cast<double*>(fin2);
-    __syncthreads();
-    if (i == L) fin2d[0] = a_b;
-    if (i == L - 1) fin2d[1] = a_l;
-    if (L == 0 && i == 0) fin2d[1] = ninf;
-    __syncthreads();
-    const double logp2 = lse2_log2d(fin2d[0], fin2d[1]);
-    const double logp = logp2 * 0.6931471805599453;
-    if (i == 0) {
-        p.logp[b] = logp;
-        p.loss[b] = (float)(-logp);
-        if (logp == ninf && status == ASRK_ROW_OK) p.row_status[b] = ASRK_ROW_INFEASIBLE;
-    }
-    if (p.grad == nullptr || logp == ninf) return;   // uniform over the CTA
-    __syncthreads();                                  // (the alpha columns written by other threads are visible)
 
     // ------------------------------ beta -------------------------------
-    // beta excludes y_t; e(u) = beta_{t+1}(u) + log2 y_{t+1}(l'_u).  occupancy(t, u) = alpha_t(u) beta_t(u) / p
-    //   = 2^(ahat + (C_t - log2 p) + beta)  with beta absolute in double
-    // look-ahead for the step that produces column f: y of frame f + 1, the stored alpha column f and its level
+    // beta excludes y_t (TensorFlow's convention); e(u) = beta_{t+1}(u) + log2 y_{t+1}(l'_u).
+    // look-ahead for the step that produces column f: y of frame f + 1 -> slot(f)
+    float* bet = p.beta + (size_t)b * p.T * U;
+    double* coffb = p.coffb + (size_t)b * p.T;
     auto fetch_b = [&](int f) {
         float* s = slot(f);
-        const bool in = (f >= 0 && f < T);
-        const bool iny = in && (f + 1 < T);
-        const float* o = occ + (size_t)(in ? f : 0) * U;
-        if (i == 0) {
-            cp_async8(s, coff + (in ? f : 0), in ? 8 : 0);
-            cp_async4(s + 2, lpl + (size_t)(iny ? f + 1 : 0) * S, iny ? 4 : 0);
-        }
+        const bool iny = (f >= 0 && f + 1 < T);
+        if (i == 0) cp_async4(s + 2, lpl + (size_t)(iny ? f + 1 : 0) * S, iny ? 4 : 0);
         cp_async4(s + 4 + i, lpl + (size_t)(iny ? f + 1 : 0) * S + (has_lab_b ? i : 0), (iny && has_lab_b) ? 4 : 0);   // label i-1 -> slot i
-        cp_async4(s + 4 + P + i, o + (has_blank ? 2 * i : 0), (in && has_blank) ? 4 : 0);
-        cp_async4(s + 4 + 2 * P + i, o + (has_lab_b ? 2 * i - 1 : 0), (in && has_lab_b) ? 4 : 0);
         cp_async_commit();
     };
     double b_l = ninf, b_b = ninf;
@@ -1006,6 +1025,7 @@ __global__ void lattice_kernel(Params p) {
         b_b = 0.0;
         if (L >= 1) b_l = 0.0;
     }
+    double lvl = 0.0;                                 // D_t
     for (int k = 0; k < kRing - 1; ++k) fetch_b(T - 1 - k);
     for (int t = T - 1; t >= 0; --t) {
         const int buf = t & 1;
@@ -1014,6 +1034,7 @@ __global__ void lattice_kernel(Params p) {
         fetch_b(t - (kRing - 1));                  // (into the slot frame t+1 used: everyone has read it)
         const float* sl = slot(t);
         if (t < T - 1) {
+            lvl += (double)block_max(buf ^ 1);
             const double yb = (double)sl[2], yl = has_lab_b ? (double)sl[4 + i] : ninf;
             const double e_b = b_b + yb;
             const double e_l = b_l + yl;
@@ -1026,13 +1047,13 @@ __global__ void lattice_kernel(Params p) {
             b_b = has_blank ? nbb : ninf;
             b_l = has_lab_b ? nbl : ninf;
         }
-        // occupancy of column t from the look-ahead alpha
-        {
-            float* o = occ + (size_t)t * U;
-            const double kt = *reinterpret_cast<const double*>(sl) - logp2;      // C_t - log2 p
-            if (has_blank) o[2 * i] = ex2_fast((float)((double)sl[4 + P + i] + kt + b_b));
-            if (has_lab_b) o[2 * i - 1] = ex2_fast((float)((double)sl[4 + 2 * P + i] + kt + b_l));
-        }
+        const float rb = (float)(b_b - lvl), rl = (float)(b_l - lvl);
+        float* o = bet + (size_t)t * U;
+        if (has_blank) o[2 * i] = rb;
+        if (has_lab_b) o[2 * i - 1] = rl;
+        if (i == 0) coffb[t] = lvl;
+        const float c = warp_max_redux(fmaxf(rb, rl));
+        if (lane == 0) wtop[buf * 32 + warp] = float_key(c);
         // publish column t for the previous warp's last lane: b_l(first lane) + log2 y_t(its label), what it
         // needs as "e of the next label state" in the next step
         if (lane == 0) edged[buf * 32 + warp] = has_lab_b ? b_l + (double)slot(t - 1)[4 + i] : ninf;   // y_t of label i-1 (own copy)
@@ -1049,10 +1070,15 @@ __global__ void lattice_kernel(Params p) {
 // memory.  (Round 1 mapped warps to rows in (t, b) order and walked the label list, the chains and the occupancies
 // in global memory: ~30 dependent L2 round trips per row, 1.0 ms per C3 batch at 26 % of the HBM bandwidth.)
 constexpr int kGradFrames = 64;
+// Every gradient row is written ONCE, 16 bytes per lane: the occupancies of the lattice classes are scattered into a
+// per-warp shared-memory row of V floats (zero elsewhere) BEFORE the row is formed, and cleared again afterwards.
+// (The first version streamed y * scale out and then patched the lattice classes with 4-byte stores: with ~300
+// labels per utterance nearly every 32-byte sector of the row was written twice, and `ncu` counted 1.06 GB of DRAM
+// writes and 1.27 GB of reads for a 0.73 GB gradient.)
 template <int NV4>
 __global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
     if (p.fused && *p.need_generic == 0) return;
-    extern __shared__ int gsm[];
+    extern __shared__ __align__(16) int gsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kGradFrames;
@@ -1063,10 +1089,17 @@ __global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
     if (p.fused && (status == ASRK_ROW_BAD_LENGTH || small_lattice(L, tl))) return;
     const int Ls = p.Ls;
     const int U = 2 * Ls + 1;
-    int* s_eff = gsm;                 // [Ls]
-    int* s_nxt = gsm + Ls;            // [Ls]
-    int* s_fst = gsm + 2 * Ls;        // [Ls]
-    float* s_occ = reinterpret_cast<float*>(gsm + 3 * Ls) + (size_t)warp * (U + Ls + 1);   // [U] occupancies | [Ls + 1] log2 y
+    const int Vfix = (NV4 > 0) ? V : 0;                     // (V is a multiple of 4 on the vector path)
+    float* s_fix = reinterpret_cast<float*>(gsm) + (size_t)warp * Vfix;   // [V] occupancy (or occupancy / y) per class
+    int* s_eff = gsm + kRowWarps * Vfix;   // [Ls]
+    int* s_nxt = s_eff + Ls;               // [Ls]
+    int* s_fst = s_eff + 2 * Ls;           // [Ls]
+    // per warp: [Ls] occupancies of the label states | [Ls + 1] log2 y of the lattice classes (staged only where the
+    // row pass does not produce y itself: probabilities in, or the scalar path)
+    const bool need_lpl = (NV4 == 0) || p.prob;
+    const int per_warp = Ls + (need_lpl ? Ls + 1 : 0);
+    float* s_lab = reinterpret_cast<float*>(s_eff + 3 * Ls) + (size_t)warp * per_warp;
+    float* s_lpl = s_lab + Ls;
     const bool live = (status == ASRK_ROW_OK) && (t0 < tl);
     if (live) {
         for (int j = threadIdx.x; j < L; j += blockDim.x) {
@@ -1075,6 +1108,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
             s_fst[j] = p.chain_first[(size_t)b * Ls + j];
         }
     }
+    for (int k = threadIdx.x; k < kRowWarps * Vfix; k += blockDim.x) reinterpret_cast<float*>(gsm)[k] = 0.f;
     __syncthreads();
     const float scale = p.grad_scale ? p.grad_scale[b] : 1.0f;
     for (int t = t0 + warp; t < t0 + kGradFrames && t < p.T; t += kRowWarps) {
@@ -1091,75 +1125,106 @@ __global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
         }
         const float* x = p.logits + (size_t)t * p.stride_t + (size_t)b * p.stride_b;
         const size_t bt = (size_t)b * p.T + t;
-        const float lse = p.lse[bt];
-        // the frame's occupancies and log2-probabilities of the lattice classes: requested now, used after the row
-        const bool fix = (status == ASRK_ROW_OK);
-        if (fix) {
-            const float* occ = p.occ + bt * (size_t)U;
-            const float* lpl = p.lpl + bt * (size_t)(Ls + 1);
-            for (int k = lane; k < 2 * L + 1; k += 32) s_occ[k] = __ldcs(occ + k);
-            for (int k = lane; k <= L; k += 32) s_occ[U + k] = __ldcs(lpl + k);
-        }
-        float base = 0.f;
-        if (p.prob) {
-            // gradient w.r.t. the probabilities (see fused_small_kernel): scale / S everywhere, lattice classes fixed
-            base = scale * __expf(-lse);
-            if constexpr (NV4 > 0) {
-                float4* g4 = reinterpret_cast<float4*>(g);
-                const float4 bv = make_float4(base, base, base, base);
-                for (int i = lane; i < (V >> 2); i += 32) stg_stream(g4 + i, bv);
-            } else {
-                for (int i = lane; i < V; i += 32) g[i] = base;
-            }
-        } else {
-            const float nlse2 = -lse * kLog2e;
-            if constexpr (NV4 > 0) {
+        // the row itself first (the longest latency), then the frame's lattice columns
+        [[maybe_unused]] float4 v[(NV4 > 0 ? NV4 : 1)];
+        if constexpr (NV4 > 0) {
+            if (!p.prob) {
                 const float4* x4 = reinterpret_cast<const float4*>(x);
-                float4* g4 = reinterpret_cast<float4*>(g);
-                const int V4 = V >> 2;
-                float4 v[(NV4 > 0 ? NV4 : 1)];
 #pragma unroll
                 for (int k = 0; k < NV4; ++k) {
                     const int i = lane + 32 * k;
-                    if (i < V4) v[k] = ldg_stream(x4 + i);
+                    if (i < (V >> 2)) v[k] = ldg_stream(x4 + i);
                 }
-#pragma unroll
-                for (int k = 0; k < NV4; ++k) {
-                    const int i = lane + 32 * k;
-                    if (i < V4) {
-                        float4 y;
-                        y.x = ex2_fast(fmaf(v[k].x, kLog2e, nlse2)) * scale;
-                        y.y = ex2_fast(fmaf(v[k].y, kLog2e, nlse2)) * scale;
-                        y.z = ex2_fast(fmaf(v[k].z, kLog2e, nlse2)) * scale;
-                        y.w = ex2_fast(fmaf(v[k].w, kLog2e, nlse2)) * scale;
-                        stg_stream(g4 + i, y);
+            }
+        }
+        const float lse = p.lse[bt];
+        const bool fix = (status == ASRK_ROW_OK);   // TF: no valid path -> dy = y
+        float ob = 0.f;                             // blank occupancy: even states (+ labels equal to the blank index)
+        if (fix) {
+            // occupancy(t, u) = alpha_t(u) beta_t(u) / p = 2^(ahat + bhat + (C_t + D_t - log2 p)): the two sweeps stored
+            // their columns relative to their own levels
+            const float* al = p.occ + bt * (size_t)U;
+            const float* be = p.beta + bt * (size_t)U;
+            const double kt = (p.coff[bt] + p.coffb[bt]) - p.logp[b] * 1.4426950408889634;
+            for (int k = lane; k < 2 * L + 1; k += 32) {
+                // (the sum in double: the three terms are ~1000 binades each and cancel to the occupancy's exponent)
+                const float o = ex2_fast((float)(((double)__ldcs(al + k) + (double)__ldcs(be + k)) + kt));
+                if (k & 1) s_lab[k >> 1] = o;      // label state 2j+1
+                else ob += o;                      // blank state
+            }
+            if (need_lpl) {
+                const float* lpl = p.lpl + bt * (size_t)(Ls + 1);
+                for (int k = lane; k <= L; k += 32) s_lpl[k] = __ldcs(lpl + k);
+            }
+        }
+        const float base = p.prob ? scale * __expf(-lse) : 0.f;   // gradient w.r.t. the probabilities: scale / S
+        if constexpr (NV4 == 0) {
+            // scalar path (V not a multiple of 4, unaligned rows or a very large vocabulary): row, then patches
+            if (p.prob) for (int i = lane; i < V; i += 32) g[i] = base;
+            else for (int i = lane; i < V; i += 32) g[i] = __expf(x[i] - lse) * scale;
+        }
+        __syncwarp();
+        // the lattice occupancies per class: blank = sum over even states (+ labels equal to the blank index); every
+        // distinct label = sum over its chain of positions, in a fixed order
+        if (fix) {
+            for (int j = lane; j < L; j += 32) {
+                const int c = s_eff[j];
+                if (c == p.blank) {
+                    ob += s_lab[j];
+                } else if (s_fst[j]) {
+                    float o = 0.f;
+                    for (int k = j; k >= 0; k = s_nxt[k]) o += s_lab[k];
+                    if constexpr (NV4 > 0) {
+                        s_fix[c] = p.prob ? __fdividef(o, ex2_fast(s_lpl[1 + j])) : o;
+                    } else {
+                        const float y = ex2_fast(s_lpl[1 + j]);
+                        g[c] = p.prob ? base * (1.0f - o / y) : (y - o) * scale;
                     }
                 }
-            } else {
-                for (int i = lane; i < V; i += 32) g[i] = __expf(x[i] - lse) * scale;
+            }
+            ob = warp_sum(ob);
+            if (lane == 0) {
+                if constexpr (NV4 > 0) {
+                    s_fix[p.blank] = p.prob ? __fdividef(ob, ex2_fast(s_lpl[0])) : ob;
+                } else {
+                    const float y = ex2_fast(s_lpl[0]);
+                    g[p.blank] = p.prob ? base * (1.0f - ob / y) : (y - ob) * scale;
+                }
             }
         }
-        if (!fix) continue;                  // TF: no valid path -> dy = y
-        __syncwarp();
-        // subtract the lattice occupancies: blank = sum over even states (+ labels equal to the blank index); every
-        // distinct label = sum over its chain of positions, in a fixed order
-        float ob = 0.f;
-        for (int j = lane; j <= L; j += 32) ob += s_occ[2 * j];
-        for (int j = lane; j < L; j += 32) {
-            const int c = s_eff[j];
-            if (c == p.blank) {
-                ob += s_occ[2 * j + 1];
-            } else if (s_fst[j]) {
-                float o = 0.f;
-                for (int k = j; k >= 0; k = s_nxt[k]) o += s_occ[2 * k + 1];
-                const float y = ex2_fast(s_occ[U + 1 + j]);
-                g[c] = p.prob ? base * (1.0f - o / y) : (y - o) * scale;
+        if constexpr (NV4 > 0) {
+            __syncwarp();
+            const float nlse2 = -lse * kLog2e;
+            float4* g4 = reinterpret_cast<float4*>(g);
+            const float4* f4 = reinterpret_cast<const float4*>(s_fix);
+#pragma unroll
+            for (int k = 0; k < NV4; ++k) {
+                const int i = lane + 32 * k;
+                if (i < (V >> 2)) {
+                    const float4 f = f4[i];
+                    float4 y;
+                    if (p.prob) {
+                        y.x = base * (1.0f - f.x);
+                        y.y = base * (1.0f - f.y);
+                        y.z = base * (1.0f - f.z);
+                        y.w = base * (1.0f - f.w);
+                    } else {
+                        y.x = (ex2_fast(fmaf(v[k].x, kLog2e, nlse2)) - f.x) * scale;
+                        y.y = (ex2_fast(fmaf(v[k].y, kLog2e, nlse2)) - f.y) * scale;
+                        y.z = (ex2_fast(fmaf(v[k].z, kLog2e, nlse2)) - f.z) * scale;
+                        y.w = (ex2_fast(fmaf(v[k].w, kLog2e, nlse2)) - f.w) * scale;
+                    }
+                    stg_stream(g4 + i, y);
+                }
             }
-        }
-        ob = warp_sum(ob);
-        if (lane == 0) {
-            const float y = ex2_fast(s_occ[U]);
-            g[p.blank] = p.prob ? base * (1.0f - ob / y) : (y - ob) * scale;
+            __syncwarp();
+            if (fix) {                           // clear the classes this row touched
+                for (int j = lane; j < L; j += 32) {
+                    const int c = s_eff[j];
+                    if (c != p.blank && s_fst[j]) s_fix[c] = 0.f;
+                }
+                if (lane == 0) s_fix[p.blank] = 0.f;
+            }
         }
         __syncwarp();                        // the warp's staging rows are free again
     }
@@ -1235,6 +1300,14 @@ __global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const 
         else { out2[0] = s_sum[0]; out2[1] = (double)s_cnt[0]; }
     }
 }
+
+// CTAs per SM of the two zero-copy staging kernels.  PCIe needs ~100 KB in flight per direction; one CTA per SM (8
+// warps x 3 KB) holds 3.5 MB.  With 8 and 4 CTAs per SM (round 2's first version) the two kernels filled every thread
+// slot of the chip and ran one after the other instead of side by side: 59 GB/s for both directions together against
+// 50 + 50 for two DMA copies (tools/pcie_ceiling.py).
+#ifndef ASRK_STAGE_CTAS_PER_SM
+#define ASRK_STAGE_CTAS_PER_SM 1
+#endif
 
 // Device -> host return of the gradient without its padding: the mirror of stage_logits_kernel.  Rows
 // t < input_len[b] are written straight into (mapped, pinned) host memory by the SMs with 16-byte stores;
@@ -1342,7 +1415,9 @@ static void launch_fused(const Params& p, int nv4, cudaStream_t stream) {
 
 static void launch_grad(const Params& p, int nv4, cudaStream_t stream) {
     const dim3 grid((unsigned)((p.T + kGradFrames - 1) / kGradFrames), (unsigned)p.B);
-    const size_t smem = sizeof(int) * 3 * (size_t)p.Ls + sizeof(float) * kRowWarps * (size_t)(3 * p.Ls + 2);
+    const bool need_lpl = (nv4 == 0) || p.prob;
+    const size_t smem = sizeof(int) * 3 * (size_t)p.Ls + sizeof(float) * kRowWarps * (size_t)(p.Ls + (need_lpl ? p.Ls + 1 : 0)) +
+                        (nv4 > 0 ? sizeof(float) * kRowWarps * (size_t)p.V : 0);
     switch (nv4) {
 #define ASRK_GRAD_CASE(N)                                                                                   \
     case N:                                                                                                 \
@@ -1393,6 +1468,8 @@ static void bind_workspace(Params& p, void* workspace, const WsLayout& l) {
     p.lpl = reinterpret_cast<float*>(ws + l.lpl);
     p.occ = reinterpret_cast<float*>(ws + l.occ);
     p.coff = reinterpret_cast<double*>(ws + l.coff);
+    p.beta = reinterpret_cast<float*>(ws + l.beta);
+    p.coffb = reinterpret_cast<double*>(ws + l.coffb);
     p.logp = reinterpret_cast<double*>(ws + l.logp);
     p.need_generic = reinterpret_cast<int*>(ws + l.flag);
 }
@@ -1467,7 +1544,7 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (phases & ASRK_PHASE_CTC_LATTICE) {
         const size_t lsm = sizeof(double) * 98 + sizeof(float) * kRing * lattice_slot_floats(P);
         cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-        lattice_kernel<<<B, P, lsm, stream>>>(p), asrk::note_launch();
+        lattice_kernel<<<dim3((unsigned)B, grad ? 2u : 1u), P, lsm, stream>>>(p), asrk::note_launch();
     }
     if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
     if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p), asrk::note_launch();
@@ -1554,7 +1631,7 @@ extern "C" int asrk_ctc_unstage_rows_run(const float* src, long long src_stride_
     if (!src || !dst || !input_len) return ASRK_E_BADARG;
     if (V % 4 != 0 || (src_stride_t % 4) || (src_stride_b % 4) || (dst_stride_t % 4) || (dst_stride_b % 4)) return ASRK_E_SHAPE;
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return ASRK_E_ALIGN;
-    unstage_rows_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+    unstage_rows_kernel<<<sm_count() * ASRK_STAGE_CTAS_PER_SM, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
         src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, T, B, V), asrk::note_launch();
     return launch_status();
 }
@@ -1567,7 +1644,7 @@ extern "C" int asrk_ctc_stage_logits_run(const float* src, long long src_stride_
     if (!src || !dst || !input_len) return ASRK_E_BADARG;
     if (V % 4 != 0 || (src_stride_t % 4) || (src_stride_b % 4) || (dst_stride_t % 4) || (dst_stride_b % 4)) return ASRK_E_SHAPE;
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return ASRK_E_ALIGN;
-    stage_logits_kernel<<<sm_count() * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+    stage_logits_kernel<<<sm_count() * ASRK_STAGE_CTAS_PER_SM, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
         src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, T, B, V), asrk::note_launch();
     return launch_status();
 }

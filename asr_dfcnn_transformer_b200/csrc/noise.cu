@@ -12,9 +12,12 @@
 // combined along the recursion n -> (n/2 rounded down to a multiple of 8, rest)),
 // then float32 divide / sqrt / multiply.
 //
-// One CTA per utterance.  Eight lanes own the eight interleaved accumulators of
-// one leaf block (32-byte coalesced sectors); leaf sums land in a shared-memory
-// heap that mirrors the recursion tree and are folded bottom-up.
+// One CTA per utterance.  TWO lanes own one leaf block: lane h holds accumulators 4h .. 4h+3 of numpy's eight and
+// reads its half of every 32-byte group with one 16-byte load (all of a leaf's <= 16 loads are issued before the
+// first add: 8 KB in flight per warp).  A warp folds its 16 leaves through four levels of the recursion tree with
+// shuffles (siblings are neighbours); what is left of the tree lives in a small shared-memory heap, folded bottom-up.
+// (Round 1 gave a leaf to eight lanes with 4-byte loads in a dependent loop and kept the whole tree in 144 KB of
+// shared memory: one 1024-thread CTA per SM, 1.7 waves, 1.8 TB/s.)
 #include <math.h>
 
 #include "asrk_common.cuh"
@@ -22,40 +25,52 @@
 namespace asrk {
 namespace noise {
 
-constexpr int kThreads = 1024;
-constexpr int kMaxDepth = 13;                 // up to 128 * 2^13 = 1,048,576 samples
-constexpr int kHeap = 1 << (kMaxDepth + 1);   // heap slots (index 1 = root)
+constexpr int kThreads = 128;
+constexpr int kMaxDepth = 15;                 // up to 128 * 2^15 = 4,194,304 samples
+constexpr int kWarpLevels = 4;                // 16 leaves per warp and pass
+constexpr int kHeap = 1 << (kMaxDepth - kWarpLevels + 1);   // heap slots above the warps' sub-trees (index 1 = root)
 constexpr int kBlock = 128;                   // numpy PW_BLOCKSIZE
 
-__device__ __forceinline__ float leaf_sum8(const float* a, long long len, int j) {
-    // lanes j = 0..7 of a group: r[j] = a[j] + a[8+j] + ... ; combined as
-    // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); remainder added one by one (lane 0).
-    float res;
-    if (len < 8) {
-        res = 0.f;
-        if (j == 0)
-            for (long long i = 0; i < len; ++i) res = __fadd_rn(res, __fmul_rn(a[i], a[i]));
-        return res;
+// sum of squares of a[0 .. len) in numpy's leaf order (len <= 128), for the lane pair (h = 0 / 1) that owns the leaf;
+// the result is valid in lane h == 0.  `vec`: a is 16-byte aligned.
+__device__ __forceinline__ float leaf_sum(const float* a, int len, int h, bool vec) {
+    const int ngrp = len >> 3;                 // full groups of eight (<= 16); none: numpy's plain loop from 0
+    float r = 0.f;
+    if (ngrp > 0) {
+        float4 v[16];
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+            if (g < ngrp) {
+                const float* q = a + 8 * g + 4 * h;
+                if (vec) v[g] = __ldcs(reinterpret_cast<const float4*>(q));
+                else v[g] = make_float4(__ldcs(q), __ldcs(q + 1), __ldcs(q + 2), __ldcs(q + 3));
+            }
+        }
+        float r0 = __fmul_rn(v[0].x, v[0].x), r1 = __fmul_rn(v[0].y, v[0].y);
+        float r2 = __fmul_rn(v[0].z, v[0].z), r3 = __fmul_rn(v[0].w, v[0].w);
+#pragma unroll
+        for (int g = 1; g < 16; ++g) {
+            if (g < ngrp) {
+                r0 = __fadd_rn(r0, __fmul_rn(v[g].x, v[g].x));
+                r1 = __fadd_rn(r1, __fmul_rn(v[g].y, v[g].y));
+                r2 = __fadd_rn(r2, __fmul_rn(v[g].z, v[g].z));
+                r3 = __fadd_rn(r3, __fmul_rn(v[g].w, v[g].w));
+            }
+        }
+        r = __fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3));
     }
-    const long long nfull = len - (len % 8);
-    float r = __fmul_rn(a[j], a[j]);
-    for (long long i = 8; i < nfull; i += 8) {
-        const float v = a[i + j];
-        r = __fadd_rn(r, __fmul_rn(v, v));
-    }
+    // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); the remainder one by one.  (Every lane of the warp executes the shuffle.)
     r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
-    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
-    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-    if (j == 0)
-        for (long long i = nfull; i < len; ++i) r = __fadd_rn(r, __fmul_rn(a[i], a[i]));
+    if (h == 0)
+        for (int i = ngrp << 3; i < len; ++i) r = __fadd_rn(r, __fmul_rn(a[i], a[i]));
     return r;
 }
 
-__global__ void __launch_bounds__(kThreads) snr2k_kernel(const float* signal, const float* noise,
+__global__ void __launch_bounds__(kThreads, 4) snr2k_kernel(const float* signal, const float* noise,
                                                           const long long* sample_offsets,
                                                           const long long* sample_counts,
                                                           const int* snr_db, float* gain_out) {
-    extern __shared__ float heap[];            // [2][kHeap] values
+    __shared__ float heap[2][kHeap];
     __shared__ unsigned char present[kHeap];
     const int b = blockIdx.x;
     const long long s0 = sample_offsets[b];
@@ -79,15 +94,20 @@ __global__ void __launch_bounds__(kThreads) snr2k_kernel(const float* signal, co
         if (tid == 0) gain_out[b] = __int_as_float(0x7fc00000);
         return;
     }
-    for (int i = tid; i < kHeap; i += kThreads) present[i] = 0;
+    const int wl = D < kWarpLevels ? D : kWarpLevels;      // levels folded inside a warp
+    const int Dh = D - wl;                                  // depth of the heap's bottom level
+    for (int i = tid; i < (2 << Dh); i += kThreads) present[i] = 0;
     __syncthreads();
-    const int group = tid >> 3, j = tid & 7;
+    const float* sig = signal + s0;
+    const float* noi = noise + s0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(sig) | reinterpret_cast<uintptr_t>(noi)) & 15) == 0;
+    const int lane = tid & 31;
+    const int q = lane >> 1, h = lane & 1;      // leaf of the warp, half of the leaf
     const int n_slots = 1 << D;
-    for (int base = 0; base < n_slots; base += kThreads / 8) {
-        const int idx = base + group;
+    for (int base = 0; base < n_slots; base += kThreads / 2) {
+        const int idx = base + (tid >> 5) * 16 + q;
         bool valid = idx < n_slots;
         long long start = 0, len = n;
-        int node = 1;
         if (valid) {
             for (int level = 0; level < D; ++level) {
                 if (len <= kBlock) {
@@ -99,26 +119,39 @@ __global__ void __launch_bounds__(kThreads) snr2k_kernel(const float* signal, co
                 n2 -= n2 % 8;
                 const int bit = (idx >> (D - 1 - level)) & 1;
                 if (bit) { start += n2; len -= n2; } else { len = n2; }
-                node = 2 * node + bit;
             }
         }
-        // all 8 lanes of a group share `valid`; groups of one warp may differ, so
-        // keep the shuffles inside leaf_sum8 converged by running it for everyone
-        const float es = leaf_sum8(signal + s0 + (valid ? start : 0), valid ? len : 8, j);
-        const float en = leaf_sum8(noise + s0 + (valid ? start : 0), valid ? len : 8, j);
-        if (valid && j == 0) {
-            heap[node] = es;
-            heap[kHeap + node] = en;
+        // both lanes of a pair share `valid`; pairs of one warp may differ, so keep the shuffles converged by running
+        // the leaf for everyone (an invalid pair reads nothing: len 0)
+        float es = leaf_sum(sig + (valid ? start : 0), valid ? (int)len : 0, h, vec);
+        float en = leaf_sum(noi + (valid ? start : 0), valid ? (int)len : 0, h, vec);
+        // fold the warp's 16 leaves: the left sibling takes left + right when the right one exists (a leaf above the
+        // bottom level sits in the leftmost slot of its sub-tree, the other slots are absent)
+        bool here = valid;
+        for (int s = 1; s < (1 << wl); s <<= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, es, 2 * s);
+            const float on = __shfl_xor_sync(0xffffffffu, en, 2 * s);
+            const bool oh = __shfl_xor_sync(0xffffffffu, (int)here, 2 * s) != 0;
+            if ((q & s) == 0 && oh) {
+                es = __fadd_rn(es, os);
+                en = __fadd_rn(en, on);
+            }
+        }
+        if (here && h == 0 && (q & ((1 << wl) - 1)) == 0) {
+            const int node = (1 << Dh) + (idx >> wl);
+            heap[0][node] = es;
+            heap[1][node] = en;
             present[node] = 1;
         }
     }
     __syncthreads();
-    for (int level = D - 1; level >= 0; --level) {
+    for (int level = Dh - 1; level >= 0; --level) {
         const int first = 1 << level;
         for (int i = first + tid; i < 2 * first; i += kThreads) {
-            if (present[2 * i] && present[2 * i + 1]) {
-                heap[i] = __fadd_rn(heap[2 * i], heap[2 * i + 1]);
-                heap[kHeap + i] = __fadd_rn(heap[kHeap + 2 * i], heap[kHeap + 2 * i + 1]);
+            if (present[2 * i]) {
+                const bool both = present[2 * i + 1] != 0;
+                heap[0][i] = both ? __fadd_rn(heap[0][2 * i], heap[0][2 * i + 1]) : heap[0][2 * i];
+                heap[1][i] = both ? __fadd_rn(heap[1][2 * i], heap[1][2 * i + 1]) : heap[1][2 * i];
                 present[i] = 1;
             }
         }
@@ -126,8 +159,8 @@ __global__ void __launch_bounds__(kThreads) snr2k_kernel(const float* signal, co
     }
     if (tid == 0) {
         const float fn = (float)n;
-        const float es = __fdiv_rn(heap[1], fn);
-        const float en = __fdiv_rn(heap[kHeap + 1], fn);
+        const float es = __fdiv_rn(heap[0][1], fn);
+        const float en = __fdiv_rn(heap[1][1], fn);
         const float ratio = __fsqrt_rn(__fdiv_rn(es, en));
         const float factor = (float)pow(10.0, -(double)snr_db[b] / 20.0);
         gain_out[b] = __fmul_rn(ratio, factor);
@@ -146,9 +179,7 @@ extern "C" int asrk_snr2k_run(const float* signal, const float* noise, const lon
     if (batch == 0) return ASRK_OK;
     if (!signal || !noise || !sample_offsets || !sample_counts || !snr_db || !gain_out)
         return ASRK_E_BADARG;
-    const size_t smem = sizeof(float) * 2 * kHeap;
-    cudaFuncSetAttribute(snr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    snr2k_kernel<<<batch, kThreads, smem, stream>>>(signal, noise, sample_offsets, sample_counts,
-                                                       snr_db, gain_out), asrk::note_launch();
+    snr2k_kernel<<<batch, kThreads, 0, stream>>>(signal, noise, sample_offsets, sample_counts,
+                                                    snr_db, gain_out), asrk::note_launch();
     return asrk::launch_status();
 }

@@ -134,9 +134,15 @@ class HostRoundTrip:
     of step k+1 go host -> device on a copy-in stream and the results of step k-1 come back on a
     copy-out stream (PCIe is full duplex).  Per step:
 
-      in   PCM + labels (DMA from pinned memory), logits without their padding (``ctc.stage_logits``)
+      in   PCM, labels and the padded logits tensor (DMA from pinned memory)
       out  per-utterance loss, the features (DMA into pinned memory) and the gradient without its
-           all-zero padding rows (``ctc.unstage_rows``)
+           all-zero padding rows (``ctc.unstage_rows``: the SMs write the mapped host buffer)
+
+    ``logits_in="zero_copy"`` pulls the logits without their padding with ``ctc.stage_logits`` instead (29 % fewer
+    bytes for a C2 batch).  Measured on the B200 box (tools/pcie_ceiling.py, profiles/r2_e2e.md): SM reads of host
+    memory and any concurrent device -> host traffic serialise (60 GB/s for both directions together against
+    100 GB/s for two DMA copies), SM *writes* to host memory next to a host -> device DMA do not, so the default
+    moves the padded tensor by DMA: 3.8 ms per C2 step instead of 4.6.
 
     ``submit`` returns a slot; ``wait(slot)`` blocks until that step's results are in its host buffers
     (``slot.h_loss / h_feat / h_grad``).  A slot's buffers are reused by the submit after next."""
@@ -145,7 +151,10 @@ class HostRoundTrip:
         pass
 
     def __init__(self, step, total_frames_max, samples_max, sample_dtype, T, B, V, label_stride, slots=2,
-                 return_outputs=True):
+                 return_outputs=True, logits_in="dma"):
+        if logits_in not in ("dma", "zero_copy"):
+            raise ValueError("logits_in must be 'dma' or 'zero_copy'")
+        self.logits_in = logits_in
         torch = step.torch
         self.step, self.torch = step, torch
         dev = step.device
@@ -170,9 +179,11 @@ class HostRoundTrip:
         self.k = 0
 
     def submit(self, h_samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames, h_logits,
-               h_labels, label_len, input_len, blank=None, grad_scale=None, ctc_bounds=None):
+               h_labels, label_len, input_len, blank=None, grad_scale=None, ctc_bounds=None, valid_rows=None):
         """Host tensors are pinned; offsets / lengths are device tensors (they are a few KB and belong to the
-        batch description).  Returns the slot (h2d_bytes / d2h_bytes attributes say what crossed PCIe)."""
+        batch description).  Returns the slot; its h2d_bytes / d2h_bytes attributes say what crossed PCIe
+        (``valid_rows`` = sum of the input lengths, a host int: the rows the zero-copy kernels move; without it
+        those legs are counted at the padded size)."""
         torch = self.torch
         s = self.slots[self.k % len(self.slots)]
         self.k += 1
@@ -183,7 +194,10 @@ class HostRoundTrip:
         with torch.cuda.stream(self.s_in):
             s.samples[:n].copy_(h_samples, non_blocking=True)
             s.labels.copy_(h_labels, non_blocking=True)
-            ctc.stage_logits(h_logits, input_len, out=s.logits, stream=self.s_in)
+            if self.logits_in == "dma":
+                s.logits[:h_logits.shape[0]].copy_(h_logits, non_blocking=True)
+            else:
+                ctc.stage_logits(h_logits, input_len, out=s.logits, stream=self.s_in)
             s.ev_in.record(self.s_in)
         cur.wait_event(s.ev_in)
         feats, res = self.step(s.samples[:n], sample_offsets, sample_counts, frame_offsets, batch, total_frames,
@@ -198,8 +212,11 @@ class HostRoundTrip:
                 ctc.unstage_rows(s.grad, input_len, s.h_grad, stream=self.s_out)
             s.ev_out.record(self.s_out)
         s.res, s.total_frames, s.busy = res, total_frames, True
-        s.h2d_bytes = n * h_samples.element_size() + h_labels.numel() * 4
-        s.d2h_bytes = s.h_loss.numel() * 4 + (total_frames * 800 if self.return_outputs else 0)
+        row_bytes = 4 * h_logits.shape[-1]
+        padded = h_logits.numel() * 4
+        moved = padded if valid_rows is None else int(valid_rows) * row_bytes
+        s.h2d_bytes = n * h_samples.element_size() + h_labels.numel() * 4 + (padded if self.logits_in == "dma" else moved)
+        s.d2h_bytes = s.h_loss.numel() * 4 + ((total_frames * 800 + moved) if self.return_outputs else 0)
         return s
 
     def wait(self, s):

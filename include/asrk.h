@@ -108,7 +108,7 @@ int asrk_spectrogram_run(const void* samples,               /* device, int16 or 
 
 /* Mix gains only (noise.py:48-52 SNR2K on the device, float32 numpy semantics):
  * gain_out[b] = fl32(sqrt(es/en)) * fl32(10^(-dB/20)).  Utterances longer than
- * 2^20 samples get a NaN gain (pass explicit gains for those). */
+ * 2^22 samples get a NaN gain (pass explicit gains for those). */
 int asrk_snr2k_run(const float* signal, const float* noise, const long long* sample_offsets,
                    const long long* sample_counts, const int* snr_db, int batch, float* gain_out,
                    asrk_stream_t stream);

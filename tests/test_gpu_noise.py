@@ -94,3 +94,42 @@ def test_add_noise_in_memory_branch(tmp_path):
         ref = fbank_ref.mix_noise(sig, nz, snr)
         assert np.abs(out[k] - ref).max() <= 1e-5
     assert noise.add_noise("/nonexistent/dir") == 0 and noise.add_noise([path], type_noise="3") == 0
+
+
+def test_snr2k_bit_exact_every_tree_shape():
+    """noise.py:48-52: the gain equals numpy's float32 pairwise sums bit for bit for every shape of the recursion tree
+    the kernel distinguishes: plain loop (n < 8), one leaf, remainders, fewer leaves than one warp's sixteen, leaves
+    above the bottom level (n just over a power of two), several passes per CTA, more than 2^20 samples; through the
+    C ABI in ONE ragged batch, with 16-byte aligned and with unaligned utterance starts (scalar loads)."""
+    import torch
+    from asr_dfcnn_transformer_b200 import _lib
+    rng = np.random.default_rng(48)
+    lens = [1, 5, 8, 9, 127, 128, 129, 135, 255, 257, 1000, 1023, 1024, 1025, 2047, 2049, 4097, 16240, 65537, 79999,
+            80000, 80001, 131072, 131073, 1048576 + 3, 3000001]
+    sig = [(rng.standard_normal(n) * 0.1).astype(np.float32) for n in lens]
+    noi = [rng.standard_normal(n).astype(np.float32) for n in lens]
+    dbs = rng.integers(5, 11, len(lens)).astype(np.int32)
+    for pad in (4, 3):                       # utterance starts: multiples of 4 floats / not
+        offs = np.zeros(len(lens), dtype=np.int64)
+        o = 0 if pad == 4 else 1
+        for i, n in enumerate(lens):
+            offs[i] = o
+            o += (n + 3) // 4 * 4 + (0 if pad == 4 else 3)
+        s = np.zeros(o + 8, np.float32)
+        z = np.zeros(o + 8, np.float32)
+        for i, n in enumerate(lens):
+            s[offs[i]:offs[i] + n] = sig[i]
+            z[offs[i]:offs[i] + n] = noi[i]
+        dev = torch.device("cuda", 0)
+        ds, dz = torch.as_tensor(s).to(dev), torch.as_tensor(z).to(dev)
+        doff = torch.as_tensor(offs).to(dev)
+        dcnt = torch.as_tensor(np.array(lens, dtype=np.int64)).to(dev)
+        ddb = torch.as_tensor(dbs).to(dev)
+        gain = torch.empty(len(lens), dtype=torch.float32, device=dev)
+        rc = _lib.lib().asrk_snr2k_run(_lib.ptr(ds), _lib.ptr(dz), _lib.ptr(doff), _lib.ptr(dcnt), _lib.ptr(ddb),
+                                       len(lens), _lib.ptr(gain), _lib.stream_ptr(None))
+        _lib.check(rc, "asrk_snr2k_run")
+        got = gain.cpu().numpy()
+        for i, n in enumerate(lens):
+            ref = fbank_ref.snr2k(sig[i], noi[i], int(dbs[i]))
+            assert got[i] == np.float32(ref), (pad, n, got[i], ref)
