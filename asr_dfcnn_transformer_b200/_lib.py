@@ -46,7 +46,7 @@ SIGNATURES = {
     "asrk_ctc_stage_logits_run": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _i, _i, _i, _vp]),
     "asrk_ctc_loss_sum_run": (_i, [_vp, _vp, _i, _vp, _vp]),
     "asrk_ctc_loss_sum_acc_run": (_i, [_vp, _vp, _i, _vp, _vp]),
-    "asrk_ctc_unstage_rows_run": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _i, _i, _i, _vp]),
+    "asrk_ctc_unstage_rows_run": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _vp]),
     "asrk_color_noise_workspace_bytes": (_sz, [_i, _ll]),
     "asrk_color_noise_run": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "asrk_logfbank_run": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, ctypes.c_double, _i, _vp, _vp]),

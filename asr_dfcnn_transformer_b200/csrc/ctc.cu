@@ -1075,8 +1075,11 @@ constexpr int kGradFrames = 64;
 // (The first version streamed y * scale out and then patched the lattice classes with 4-byte stores: with ~300
 // labels per utterance nearly every 32-byte sector of the row was written twice, and `ncu` counted 1.06 GB of DRAM
 // writes and 1.27 GB of reads for a 0.73 GB gradient.)
+#ifndef ASRK_GRAD_MIN_CTAS
+#define ASRK_GRAD_MIN_CTAS 3      // 80 registers: three CTAs per SM (the whole row in registers took 117: two)
+#endif
 template <int NV4>
-__global__ void __launch_bounds__(kRowWarps * 32) grad_kernel(Params p) {
+__global__ void __launch_bounds__(kRowWarps * 32, ASRK_GRAD_MIN_CTAS) grad_kernel(Params p) {
     if (p.fused && *p.need_generic == 0) return;
     extern __shared__ __align__(16) int gsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1314,15 +1317,20 @@ __global__ void __launch_bounds__(256) loss_sum_kernel(const float* loss, const 
 // rows t >= input_len[b] (all zeros by definition) never cross PCIe.
 __global__ void __launch_bounds__(256) unstage_rows_kernel(const float* src, long long sst, long long ssb, float* dst,
                                                            long long dst_t, long long dst_b, const int* input_len,
-                                                           int T, int B, int V) {
+                                                           int* stale_len, int T, int B, int V) {
     const int lane = threadIdx.x & 31;
     const long long rows = (long long)T * B;
     const int V4 = V >> 2;
     for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
         const int t = (int)(row / B), b = (int)(row % B);
-        if (t >= input_len[b]) continue;
-        const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)t * sst + (size_t)b * ssb);
         float4* d4 = reinterpret_cast<float4*>(dst + (size_t)t * dst_t + (size_t)b * dst_b);
+        if (t >= input_len[b]) {
+            // a row the buffer's previous occupant wrote and this batch does not: back to zero
+            if (stale_len != nullptr && t < stale_len[b])
+                for (int i = lane; i < V4; i += 32) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)t * sst + (size_t)b * ssb);
         for (int i0 = lane; i0 < V4; i0 += 32 * 6) {
             float4 v[6];
 #pragma unroll
@@ -1333,6 +1341,12 @@ __global__ void __launch_bounds__(256) unstage_rows_kernel(const float* src, lon
                 if (i0 + 32 * e < V4) d4[i0 + 32 * e] = v[e];
         }
     }
+}
+
+// stale_len <- input_len once every row of the copy above has been decided (a separate launch: stream order)
+__global__ void copy_lengths_kernel(const int* input_len, int* stale_len, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) stale_len[b] = input_len[b];
 }
 
 // Host -> device staging of the logits without their padding: rows t < input_len[b] only are pulled
@@ -1625,14 +1639,18 @@ extern "C" int asrk_ctc_loss_sum_acc_run(const float* loss, const int* row_statu
 
 extern "C" int asrk_ctc_unstage_rows_run(const float* src, long long src_stride_t, long long src_stride_b,
                                          float* dst, long long dst_stride_t, long long dst_stride_b,
-                                         const int* input_len, int T, int B, int V, asrk_stream_t stream_) {
+                                         const int* input_len, int* stale_len, int T, int B, int V,
+                                         asrk_stream_t stream_) {
     if (T < 0 || B < 0 || V < 1) return ASRK_E_BADARG;
     if (T == 0 || B == 0) return ASRK_OK;
     if (!src || !dst || !input_len) return ASRK_E_BADARG;
     if (V % 4 != 0 || (src_stride_t % 4) || (src_stride_b % 4) || (dst_stride_t % 4) || (dst_stride_b % 4)) return ASRK_E_SHAPE;
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return ASRK_E_ALIGN;
-    unstage_rows_kernel<<<sm_count() * ASRK_STAGE_CTAS_PER_SM, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-        src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, T, B, V), asrk::note_launch();
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    unstage_rows_kernel<<<sm_count() * ASRK_STAGE_CTAS_PER_SM, 256, 0, stream>>>(
+        src, src_stride_t, src_stride_b, dst, dst_stride_t, dst_stride_b, input_len, stale_len, T, B, V), asrk::note_launch();
+    if (stale_len != nullptr)
+        copy_lengths_kernel<<<(B + 255) / 256, 256, 0, stream>>>(input_len, stale_len, B), asrk::note_launch();
     return launch_status();
 }
 

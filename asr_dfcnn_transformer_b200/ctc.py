@@ -166,16 +166,18 @@ def loss_sum(loss, row_status=None, out=None, stream=None, accumulate=False):
     return out
 
 
-def unstage_rows(dev_tensor, input_len, host_out, layout="tbv", stream=None):
+def unstage_rows(dev_tensor, input_len, host_out, layout="tbv", stream=None, stale_len=None):
     """Device -> host copy of a ``[T,B,V]`` / ``[B,T,V]`` tensor (the gradient) WITHOUT its padding: only rows
-    t < input_len[b] cross PCIe, written by the SMs into the pinned host tensor ``host_out`` (rows past
-    input_len keep what the buffer held: zeros if it was cleared once)."""
+    t < input_len[b] cross PCIe, written by the SMs into the pinned host tensor ``host_out``.  ``stale_len`` (int32
+    device tensor [B], updated in place; start it at zero over a cleared buffer): the lengths of the batch that used
+    ``host_out`` before -- the rows it wrote and this batch does not are set back to zero, so the buffer always equals
+    the device tensor.  Without it the padding rows keep what the buffer held."""
     if not host_out.is_pinned():
         raise ValueError("unstage_rows needs pinned (page-locked) host memory")
     T, B, V, st, sb = _strides(dev_tensor, layout)
     _, _, _, dt, db = _strides(host_out, layout)
     rc = _lib.lib().asrk_ctc_unstage_rows_run(_lib.ptr(dev_tensor), st, sb, ctypes.c_void_p(host_out.data_ptr()), dt, db,
-                                              _lib.ptr(input_len), T, B, V, _lib.stream_ptr(stream))
+                                              _lib.ptr(input_len), _lib.ptr(stale_len), T, B, V, _lib.stream_ptr(stream))
     _lib.check(rc, "asrk_ctc_unstage_rows_run")
     return host_out
 

@@ -151,7 +151,9 @@ class HostRoundTrip:
         pass
 
     def __init__(self, step, total_frames_max, samples_max, sample_dtype, T, B, V, label_stride, slots=2,
-                 return_outputs=True, logits_in="dma"):
+                 return_outputs=True, logits_in=None):
+        if logits_in is None:      # SM reads of host memory only hurt next to device -> host traffic
+            logits_in = "dma" if return_outputs else "zero_copy"
         if logits_in not in ("dma", "zero_copy"):
             raise ValueError("logits_in must be 'dma' or 'zero_copy'")
         self.logits_in = logits_in
@@ -173,6 +175,7 @@ class HostRoundTrip:
             if return_outputs:
                 s.h_feat = torch.empty((total_frames_max, 200), dtype=torch.float32).pin_memory()
                 s.h_grad = torch.zeros((T, B, V), dtype=torch.float32).pin_memory()
+                s.stale_len = torch.zeros(B, dtype=torch.int32, device=dev)   # lengths of the buffer's previous batch
             s.ev_in, s.ev_done, s.ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
             s.busy = False
             self.slots.append(s)
@@ -209,7 +212,7 @@ class HostRoundTrip:
             s.h_loss.copy_(res.loss, non_blocking=True)
             if self.return_outputs:
                 s.h_feat[:total_frames].copy_(feats, non_blocking=True)
-                ctc.unstage_rows(s.grad, input_len, s.h_grad, stream=self.s_out)
+                ctc.unstage_rows(s.grad, input_len, s.h_grad, stream=self.s_out, stale_len=s.stale_len)
             s.ev_out.record(self.s_out)
         s.res, s.total_frames, s.busy = res, total_frames, True
         row_bytes = 4 * h_logits.shape[-1]

@@ -191,11 +191,14 @@ int asrk_ctc_stage_logits_run(const float* src, long long src_stride_t, long lon
                               asrk_stream_t stream);
 
 /* The way back: rows t < input_len[b] of the device tensor `src` (the gradient) are written into the caller's
- * pinned, device-mapped HOST tensor `dst` by the SMs; the all-zero rows t >= input_len[b] are not transferred
- * (the host buffer keeps whatever it held there: clear it once).  Same layout rules as the staging call. */
+ * pinned, device-mapped HOST tensor `dst` by the SMs; the all-zero rows t >= input_len[b] are not transferred.
+ * `stale_len` (device int32 [B], may be NULL): the input lengths of the batch that used `dst` before -- rows
+ * input_len[b] <= t < stale_len[b] are set back to zero, and stale_len becomes input_len for the next call (start
+ * it at 0 over a cleared buffer).  Without it the host buffer keeps whatever it held in the padding rows.  Same
+ * layout rules as the staging call. */
 int asrk_ctc_unstage_rows_run(const float* src, long long src_stride_t, long long src_stride_b,
                               float* dst, long long dst_stride_t, long long dst_stride_b,
-                              const int* input_len /* device int32 [B] */, int T, int B, int V,
+                              const int* input_len /* device int32 [B] */, int* stale_len, int T, int B, int V,
                               asrk_stream_t stream);
 
 /* Batch reduction feeding the path's only collective (tf.reduce_mean(self.loss),
