@@ -19,7 +19,7 @@ LABELS_BY_LENGTH, LABELS_DROP_ZEROS = 0, 1
 PHASE_ALL = 0xffff
 CTC_SMALL_ONLY = 0x10000
 CTC_INPUT_PROB = 0x20000
-PHASE_SPEC_SETUP, PHASE_SPEC_MAIN, PHASE_SPEC_NORMALIZE = 1, 2, 4
+PHASE_SPEC_SETUP, PHASE_SPEC_MAIN, PHASE_SPEC_NORMALIZE, PHASE_SPEC_STATS = 1, 2, 4, 8
 PHASE_CTC_PREP, PHASE_CTC_ROWS, PHASE_CTC_LATTICE, PHASE_CTC_GRAD, PHASE_CTC_COLLAPSE = 1, 2, 4, 8, 16
 PHASE_CTC_FUSED = 32
 
@@ -41,6 +41,11 @@ SIGNATURES = {
                                          _sz, _vp, _i]),
     "asrk_ctc_loss_grad_run_phases": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp,
                                            _vp, _ll, _ll, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _i]),
+    "asrk_ctc_loss_grad_zscore_run": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp,
+                                           _vp, _ll, _ll, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _i,
+                                           _vp, _vp, _vp, _vp, _i, _ll, _vp]),
+    "asrk_spectrogram_zscore_handles": (_i, [_vp, _sz, _i, _ll, ctypes.POINTER(ctypes.c_void_p),
+                                             ctypes.POINTER(ctypes.c_void_p)]),
     "asrk_ctc_batch_cost_run": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _vp, _vp,
                                      _sz, _vp, _i]),
     "asrk_ctc_stage_logits_run": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _i, _i, _i, _vp]),

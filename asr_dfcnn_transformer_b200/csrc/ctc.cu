@@ -84,6 +84,17 @@ struct Params {
     int small_only;      // 1: the caller bounded the batch (ASRK_CTC_SMALL_ONLY): no generic kernels follow
     int prob;            // 1: `logits` holds PROBABILITIES p (Keras' softmax output); the op's input is log(p + eps)
     float eps;           //    (K.ctc_batch_cost: eps = 1e-7) and `grad` is the gradient w.r.t. p
+    // co-work of the fused kernel: the z-score pass of the feature path (feat == nullptr: none)
+    struct ZWork {
+        float* feat;                      // rows of 200 float32, un-normalised log-spectrogram on entry
+        const float* stats;               // [Bz][3][200]: mean (hi, lo), 1/std
+        const long long* frame_offsets;   // [Bz + 1]
+        const long long* row_offsets;     // [Bz] first output row of every utterance, or nullptr (= frame_offsets)
+        int* ticket;                      // [1] next chunk (zero on entry)
+        int batch;
+        int rows;                         // feature rows per chunk
+        long long total_frames;
+    } z;
 };
 
 // Utterances whose lattice fits one warp (L <= 31 labels -> 32 state pairs) and whose
@@ -516,9 +527,138 @@ __device__ __forceinline__ float warp_max_redux(float v) {
 #else
 #define ASRK_TICK(i) do { } while (0)
 #endif
+// The z-score pass of the FEATURE path as co-work of this kernel (asrk_ctc_loss_grad_zscore_run).  The transform
+// kernel owns every SM while it runs, so the HBM-bound rest of a step -- 202 MB of z-score traffic, 184 MB of CTC
+// traffic -- runs behind it; as two kernels they overlapped by 18 us of 41 + 57 (the z-score CTAs only get the
+// registers the CTC CTAs leave), and the CTC kernel alone leaves HBM idle in its lattice phase, on the 40 SMs that
+// hold one CTA instead of two, and behind every utterance shorter than the longest.  Here every CTA that has
+// finished its utterance -- and the CTAs launched beyond the batch to fill the free slots -- takes tickets for
+// chunks of `rows` feature rows (newest first: still in L2) and normalises them in place with the arithmetic of
+// spec::normalize_kernel.  What a CTA needs for that is bytes in flight, not threads (a first version with per-thread
+// loads, 16 KB in flight per CTA, took 131 us for the merged kernel): a chunk arrives as ONE TMA bulk copy into the
+// shared memory the utterance no longer needs, the next three tickets' chunks are in flight while this one is
+// normalised (4 x 25.6 KB per CTA for V = 1424; with two buffers a CTA was bound by one bulk copy's latency at
+// 26 GB/s), and the rows leave through plain 16-byte evict-first stores.
+// Thread (r, q) owns column group q (4 bins) of rows r, r + 5, ...: its statistics live in registers per utterance.
+#ifndef ASRK_ZPRE_X100
+#define ASRK_ZPRE_X100 20
+#endif
+constexpr int kZBins = 200;
+constexpr int kZCache = 512;            // utterance starts cached in shared memory (larger batches: global look-ups)
+constexpr int kZBufs = 4;               // chunk buffers per CTA: three bulk copies in flight while one chunk is normalised
+__device__ __forceinline__ void zscore_cowork(const Params::ZWork& z, float* sm, int budget) {
+    __shared__ uint64_t s_zbar[kZBufs];
+    __shared__ int s_tk[kZBufs];
+    const int tid = threadIdx.x;
+    const int rows = z.rows;                                   // rows per chunk (host: what the dynamic smem holds kZBufs times)
+    long long* s_fo = reinterpret_cast<long long*>(sm);        // [kZCache]
+    float4* buf0 = reinterpret_cast<float4*>(s_fo + kZCache);
+    const size_t buf_f4 = (size_t)rows * (kZBins / 4);
+    const bool cached = (z.batch + 1 <= kZCache);
+    const long long* fo = cached ? s_fo : z.frame_offsets;
+    const long long nchunks = (z.total_frames + rows - 1) / rows;
+    const uint64_t drop = l2_policy_evict_first();
+    __syncthreads();                                           // everybody has left the utterance's shared memory
+    if (tid == 0) {
+        for (int j = 0; j < kZBufs; ++j) mbar_init(&s_zbar[j], 1);
+        mbar_fence_init();
+    }
+    if (cached)
+        for (int i = tid; i <= z.batch; i += blockDim.x) s_fo[i] = z.frame_offsets[i];
+    // ticket k of this CTA -> buffer k % kZBufs: chunk c covers frames [total - (c+1) rows, total - c rows)
+    // `budget`: tickets this call may take (< 0: until the queue is empty)
+    auto issue = [&](int k) {
+        const int c = (budget >= 0 && k >= budget) ? 0x7fffffff : atomicAdd(z.ticket, 1);
+        s_tk[k % kZBufs] = c;
+        if (c < nchunks) {
+            const long long f1 = z.total_frames - (long long)c * rows;
+            const long long f0 = f1 > rows ? f1 - rows : 0;
+            tma_load_1d(buf0 + (size_t)(k % kZBufs) * buf_f4, z.feat + (size_t)f0 * kZBins,
+                        (unsigned)(f1 - f0) * kZBins * 4u, &s_zbar[k % kZBufs], drop);
+        }
+    };
+    __syncthreads();
+    if (tid == 0)
+        for (int k = 0; k < kZBufs - 1; ++k) issue(k);
+    __syncthreads();
+    const int q = tid % (kZBins / 4), r0 = tid / (kZBins / 4);      // column group, first row (threads >= 250 idle)
+    for (int k = 0;; ++k) {
+        // (the buffer of ticket k + kZBufs - 1 is the one iteration k - 1 released; s_tk[k] was published at least one
+        // barrier ago)
+        if (tid == 0) issue(k + kZBufs - 1);
+        const int c = s_tk[k % kZBufs];
+        if (c >= nchunks) break;             // (tickets only grow: nothing is in flight for the later ones either)
+        const long long f1 = z.total_frames - (long long)c * rows;
+        const long long f0 = f1 > rows ? f1 - rows : 0;
+        // utterance of the chunk's first frame: largest b with fo[b] <= f0
+        int b = 0;
+        {
+            int lo = 0, hi = z.batch - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (fo[mid] <= f0) lo = mid; else hi = mid - 1;
+            }
+            b = lo;
+        }
+        const float4* src = buf0 + (size_t)(k % kZBufs) * buf_f4;
+        float4* dst = reinterpret_cast<float4*>(z.feat + (size_t)f0 * kZBins);
+        const unsigned parity = (unsigned)(k / kZBufs) & 1u;
+        bool arrived = false;
+        long long cur = f0;
+        while (cur < f1) {
+            const long long next = fo[b + 1];
+            const long long s1 = next < f1 ? next : f1;
+            if (s1 > cur && r0 < 5) {
+                const float* st = z.stats + (size_t)b * 3 * kZBins + 4 * q;
+                const float4 mh = __ldg(reinterpret_cast<const float4*>(st));
+                const float4 ml = __ldg(reinterpret_cast<const float4*>(st + kZBins));
+                const float4 iv = __ldg(reinterpret_cast<const float4*>(st + 2 * kZBins));
+                if (!arrived) { mbar_wait(&s_zbar[k % kZBufs], parity); arrived = true; }
+#pragma unroll 4
+                for (int r = (int)(cur - f0) + r0; r < (int)(s1 - f0); r += 5) {
+                    const float4 v = src[r * (kZBins / 4) + q];
+                    float4 o;
+                    o.x = ((v.x - mh.x) - ml.x) * iv.x;
+                    o.y = ((v.y - mh.y) - ml.y) * iv.y;
+                    o.z = ((v.z - mh.z) - ml.z) * iv.z;
+                    o.w = ((v.w - mh.w) - ml.w) * iv.w;
+                    stg_evict_first(dst + r * (kZBins / 4) + q, o);
+                }
+            }
+            if (s1 > cur) cur = s1;
+            if (cur < f1) ++b;
+        }
+        if (!arrived) mbar_wait(&s_zbar[k % kZBufs], parity);               // (idle threads: the phase must be observed)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // reads of this buffer before its next bulk write
+        __syncthreads();
+    }
+}
+
+template <int NV4, bool PROB>
+__device__ __forceinline__ void fused_small_body(const Params& p, float* sm);
+
 template <int NV4, bool PROB>
 __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     extern __shared__ __align__(16) float sm[];
+    if (blockIdx.x < (unsigned)p.B) {
+        // a CTA whose utterance is shorter than the longest takes some chunks FIRST (0.2 per frame of slack): the CTAs
+        // then reach their HBM-bound row phases at different times instead of all at once (merged kernel 86.6 -> 84.1 us
+        // on a C2 batch; 0.4 per frame: 86.9)
+        if (p.z.feat != nullptr && ASRK_ZPRE_X100 > 0) {
+            int tb = p.input_len[blockIdx.x];
+            tb = tb < 0 ? 0 : (tb > p.T ? p.T : tb);
+            int pre = ((p.T - tb) * ASRK_ZPRE_X100) / 100;
+            pre = pre > 24 ? 24 : pre;
+            if (pre > 0) zscore_cowork(p.z, sm, pre);
+            __syncthreads();
+        }
+        fused_small_body<NV4, PROB>(p, sm);      // (CTAs beyond the batch: co-work only)
+    }
+    if (p.z.feat != nullptr) zscore_cowork(p.z, sm, -1);
+}
+
+template <int NV4, bool PROB>
+__device__ __forceinline__ void fused_small_body(const Params& p, float* sm) {
     __shared__ double s_fin;
 #ifdef ASRK_CTC_TIMING
     __shared__ unsigned long long s_tick[12];
@@ -1407,15 +1547,18 @@ static void launch_rows(const Params& p, int nv4, cudaStream_t stream) {
 
 static void launch_fused(const Params& p, int nv4, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (kSmallSmemFloats + (size_t)kRowWarps * p.V);
+    // with z-score co-work: CTAs beyond the batch fill the resident slots the batch leaves free (two CTAs per SM)
+    int grid = p.B;
+    if (p.z.feat != nullptr && grid < 2 * sm_count()) grid = 2 * sm_count();
     switch (nv4) {
 #define ASRK_FUSED_CASE(N)                                                                                        \
     case N:                                                                                                       \
         if (p.prob) {                                                                                             \
             cudaFuncSetAttribute(fused_small_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            fused_small_kernel<N, true><<<p.B, kRowWarps * 32, smem, stream>>>(p), asrk::note_launch();                                \
+            fused_small_kernel<N, true><<<grid, kRowWarps * 32, smem, stream>>>(p), asrk::note_launch();                                \
         } else {                                                                                                  \
             cudaFuncSetAttribute(fused_small_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            fused_small_kernel<N, false><<<p.B, kRowWarps * 32, smem, stream>>>(p), asrk::note_launch();                               \
+            fused_small_kernel<N, false><<<grid, kRowWarps * 32, smem, stream>>>(p), asrk::note_launch();                               \
         }                                                                                                         \
         break;
         ASRK_FUSED_CASE(4)
@@ -1488,14 +1631,14 @@ static void bind_workspace(Params& p, void* workspace, const WsLayout& l) {
     p.need_generic = reinterpret_cast<int*>(ws + l.flag);
 }
 
-extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stride_t, long long stride_b,
-                                             int T, int B, int V, const int* labels, int label_stride,
-                                             const int* label_len, const int* input_len, int blank,
-                                             int label_mode, const float* grad_scale, float* loss,
-                                             float* grad, long long gstride_t, long long gstride_b,
-                                             int* row_status, int* tokens, int token_stride,
-                                             int* token_len, float* neg_sum_logits, void* workspace,
-                                             size_t workspace_bytes, asrk_stream_t stream_, int phases) {
+static int run_phases_impl(const float* logits, long long stride_t, long long stride_b,
+                           int T, int B, int V, const int* labels, int label_stride,
+                           const int* label_len, const int* input_len, int blank,
+                           int label_mode, const float* grad_scale, float* loss,
+                           float* grad, long long gstride_t, long long gstride_b,
+                           int* row_status, int* tokens, int token_stride,
+                           int* token_len, float* neg_sum_logits, void* workspace,
+                           size_t workspace_bytes, asrk_stream_t stream_, int phases, const Params::ZWork* zwork) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (T < 0 || B < 0 || V < 1 || label_stride < 0) return ASRK_E_BADARG;
     if (B == 0) return ASRK_OK;
@@ -1541,6 +1684,18 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
                     Ls <= kRowWarps * 32) ? 1 : 0;
     // a batch the caller bounded to small lattices needs none of the generic kernels
     p.small_only = (p.fused && (phases & ASRK_CTC_SMALL_ONLY)) ? 1 : 0;
+    if (zwork != nullptr) {
+        // the z-score rides on the fused kernel only: the caller must have bounded the batch to small lattices and
+        // the vector path must apply; nothing has been launched yet, the caller falls back to the two-kernel path
+        if (!p.small_only || !(phases & ASRK_PHASE_CTC_FUSED) || T == 0) return ASRK_E_SHAPE;
+        p.z = *zwork;
+        // kZBufs chunk buffers behind the utterance-start cache in the kernel's dynamic shared memory
+        const size_t smem = sizeof(float) * (kSmallSmemFloats + (size_t)kRowWarps * V);
+        long long rows = ((long long)smem - (long long)sizeof(long long) * kZCache) / kZBufs / (kZBins * 4);
+        rows = rows > 32 ? 32 : rows - rows % 8;
+        if (rows < 8) return ASRK_E_SHAPE;
+        p.z.rows = (int)rows;
+    }
     if (phases & ASRK_PHASE_CTC_PREP) {
         if (!p.small_only && cudaMemsetAsync(p.need_generic, 0, sizeof(int), stream) != cudaSuccess)
             return ASRK_E_CUDA;
@@ -1563,6 +1718,43 @@ extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stri
     if (grad && (phases & ASRK_PHASE_CTC_GRAD)) launch_grad(p, nv4, stream);
     if (tokens && (phases & ASRK_PHASE_CTC_COLLAPSE)) collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p), asrk::note_launch();
     return launch_status();
+}
+
+extern "C" int asrk_ctc_loss_grad_run_phases(const float* logits, long long stride_t, long long stride_b,
+                                             int T, int B, int V, const int* labels, int label_stride,
+                                             const int* label_len, const int* input_len, int blank,
+                                             int label_mode, const float* grad_scale, float* loss,
+                                             float* grad, long long gstride_t, long long gstride_b,
+                                             int* row_status, int* tokens, int token_stride,
+                                             int* token_len, float* neg_sum_logits, void* workspace,
+                                             size_t workspace_bytes, asrk_stream_t stream_, int phases) {
+    return run_phases_impl(logits, stride_t, stride_b, T, B, V, labels, label_stride, label_len, input_len, blank,
+                           label_mode, grad_scale, loss, grad, gstride_t, gstride_b, row_status, tokens, token_stride,
+                           token_len, neg_sum_logits, workspace, workspace_bytes, stream_, phases, nullptr);
+}
+
+extern "C" int asrk_ctc_loss_grad_zscore_run(const float* logits, long long stride_t, long long stride_b,
+                                             int T, int B, int V, const int* labels, int label_stride,
+                                             const int* label_len, const int* input_len, int blank,
+                                             int label_mode, const float* grad_scale, float* loss,
+                                             float* grad, long long gstride_t, long long gstride_b,
+                                             int* row_status, int* tokens, int token_stride,
+                                             int* token_len, float* neg_sum_logits, void* workspace,
+                                             size_t workspace_bytes, asrk_stream_t stream_, int flags,
+                                             float* z_features, const float* z_stats, const long long* z_frame_offsets,
+                                             const long long* z_row_offsets, int z_batch, long long z_total_frames,
+                                             int* z_ticket) {
+    if (!z_features || !z_stats || !z_frame_offsets || !z_ticket || z_batch < 1 || z_total_frames < 0) return ASRK_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(z_features) & 15) != 0) return ASRK_E_ALIGN;
+    if (B < 1) return ASRK_E_SHAPE;              // no CTC kernel to ride on
+    if (z_row_offsets != nullptr) return ASRK_E_SHAPE;   // chunks are bulk copies of consecutive rows: flat layout only
+    Params::ZWork z;
+    z.feat = z_features; z.stats = z_stats; z.frame_offsets = z_frame_offsets; z.row_offsets = z_row_offsets;
+    z.ticket = z_ticket; z.batch = z_batch; z.total_frames = z_total_frames; z.rows = 0;
+    return run_phases_impl(logits, stride_t, stride_b, T, B, V, labels, label_stride, label_len, input_len, blank,
+                           label_mode, grad_scale, loss, grad, gstride_t, gstride_b, row_status, tokens, token_stride,
+                           token_len, neg_sum_logits, workspace, workspace_bytes, stream_,
+                           ASRK_PHASE_ALL | (flags & ~0xffff), &z);
 }
 
 extern "C" int asrk_ctc_loss_grad_run(const float* logits, long long stride_t, long long stride_b,

@@ -600,6 +600,17 @@ extern "C" size_t asrk_spectrogram_workspace_bytes(int batch, long long total_fr
     return ws_layout(batch, total_frames).total;
 }
 
+extern "C" int asrk_spectrogram_zscore_handles(void* workspace, size_t workspace_bytes, int batch, long long total_frames,
+                                               float** stats, int** ticket) {
+    if (!workspace || !stats || !ticket || batch < 1 || total_frames < 0) return ASRK_E_BADARG;
+    const WsLayout l = ws_layout(batch, total_frames);
+    if (workspace_bytes < l.total) return ASRK_E_WORKSPACE;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    *stats = reinterpret_cast<float*>(ws + l.stats);
+    *ticket = reinterpret_cast<int*>(ws + l.counters) + 2;     // zeroed with the tile counter by the MAIN phase
+    return ASRK_OK;
+}
+
 extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype, const float* noise,
                                            const float* gain, const int* snr_db,
                                            const long long* sample_offsets, const long long* sample_counts,
@@ -636,7 +647,7 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         }
         gains = gw;
     }
-    if (!(phases & (ASRK_PHASE_SPEC_MAIN | ASRK_PHASE_SPEC_NORMALIZE))) return launch_status();
+    if (!(phases & (ASRK_PHASE_SPEC_MAIN | ASRK_PHASE_SPEC_NORMALIZE | ASRK_PHASE_SPEC_STATS))) return launch_status();
 
     // the kernel locates tiles through a prefix array in shared memory: at most
     // kMaxBatch utterances per launch, larger batches go in slices
@@ -663,6 +674,10 @@ extern "C" int asrk_spectrogram_run_phases(const void* samples, int sample_dtype
         if (phases & ASRK_PHASE_SPEC_MAIN) {
             if (sample_dtype == ASRK_DTYPE_I16) launch_main<false>(p, grid, stream);
             else launch_main<true>(p, grid, stream);
+        }
+        if (mode == ASRK_SPEC_FBANK && !(phases & ASRK_PHASE_SPEC_NORMALIZE) && (phases & ASRK_PHASE_SPEC_STATS)) {
+            // statistics only: the rows are normalised by the fused CTC kernel's co-work (asrk_ctc_loss_grad_zscore_run)
+            stats_kernel<<<nb, 256, 0, stream>>>(p), asrk::note_launch();
         }
         if (mode == ASRK_SPEC_FBANK && (phases & ASRK_PHASE_SPEC_NORMALIZE)) {
             // (Asking for the largest shared-memory carve-out so that these CTAs can share an SM with the fused CTC

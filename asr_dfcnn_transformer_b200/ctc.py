@@ -53,9 +53,13 @@ def _i32(x, dev, torch):
     return torch.as_tensor(np.asarray(x).reshape(-1).astype(np.int32)).to(dev)
 
 
+class CoWorkNotEligible(RuntimeError):
+    """ctc_loss_grad(zscore=...) on a batch that cannot take the fused kernel; nothing was launched."""
+
+
 def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="by_length",
                   layout="tbv", grad_scale=None, want_grad=True, decode=False, grad_out=None,
-                  stream=None, phases=_lib.PHASE_ALL, outputs=None, bounds=None, input_kind="logits"):
+                  stream=None, phases=_lib.PHASE_ALL, outputs=None, bounds=None, input_kind="logits", zscore=None):
     """Raw op: one fused pass.  logits float32 CUDA tensor ``[T,B,V]`` ('tbv') or
     ``[B,T,V]`` ('btv'); labels int32 ``[B,Lmax]``.  Returns CtcResult of device
     tensors (no synchronisation, statuses are NOT checked here).
@@ -68,7 +72,11 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
 
     ``input_kind="prob"``: ``logits`` holds the softmax output p that Keras hands to ``K.ctc_batch_cost``
     (cnn_ctc.py:149-152); the op's input ``log(p + 1e-7)`` is formed inside the kernel and ``grad`` is the
-    gradient w.r.t. p (no element-wise pass before or after the kernel)."""
+    gradient w.r.t. p (no element-wise pass before or after the kernel).
+
+    ``zscore`` (``features.ZScoreWork``): the z-score pass of the feature path rides on the fused kernel as co-work
+    (one kernel for the step's HBM-bound tail).  Raises ``CoWorkNotEligible`` -- before anything is launched -- when
+    the batch cannot take the fused kernel alone (not bounded to small lattices, vector path not applicable)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     if logits.dtype != torch.float32 or not logits.is_cuda:
@@ -122,6 +130,21 @@ def ctc_loss_grad(logits, labels, label_len, input_len, blank=None, label_mode="
         grad_scale = grad_scale.to(device=dev, dtype=torch.float32).contiguous()
     nbytes = L.asrk_ctc_workspace_bytes(T, B, Ls)
     ws = workspace(nbytes, dev, "ctc", stream)
+    if zscore is not None:
+        if (int(phases) & 0xffff) != _lib.PHASE_ALL or not (int(phases) & _lib.CTC_SMALL_ONLY):
+            raise CoWorkNotEligible("the z-score co-work needs a whole-op call on a batch bounded to small lattices")
+        z = zscore
+        rc = L.asrk_ctc_loss_grad_zscore_run(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(labels), Ls,
+                                             _lib.ptr(label_len), _lib.ptr(input_len), int(blank), mode,
+                                             _lib.ptr(grad_scale), _lib.ptr(loss), _lib.ptr(grad), gt, gb,
+                                             _lib.ptr(status), _lib.ptr(tokens), max(T, 1), _lib.ptr(tlen),
+                                             _lib.ptr(nsl), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(stream),
+                                             int(phases), _lib.ptr(z.features), z.stats, _lib.ptr(z.frame_offsets),
+                                             _lib.ptr(z.row_offsets), z.batch, z.total_frames, z.ticket)
+        if rc == _lib.E_SHAPE:
+            raise CoWorkNotEligible("this batch does not take the fused CTC kernel (nothing was launched)")
+        _lib.check(rc, "asrk_ctc_loss_grad_zscore_run")
+        return CtcResult(loss, grad, status, tokens, tlen, nsl)
     rc = L.asrk_ctc_loss_grad_run_phases(_lib.ptr(logits), st, sb, T, B, V, _lib.ptr(labels), Ls,
                                          _lib.ptr(label_len), _lib.ptr(input_len), int(blank), mode,
                                          _lib.ptr(grad_scale), _lib.ptr(loss), _lib.ptr(grad), gt, gb,

@@ -9,6 +9,7 @@ Host rules copied from the reference (they are control logic, not arithmetic):
     very Python float expression (wav_util.py:61; asrt variant without the +1,
     wav_util.py:96) -- it differs from integer arithmetic for some N.
 """
+import ctypes
 from collections import namedtuple
 
 import numpy as np
@@ -133,6 +134,23 @@ def spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, ba
                                        _lib.stream_ptr(stream), int(phases) | (int(cta_limit) << 16))
     _lib.check(st, "asrk_spectrogram_run")
     return out
+
+
+ZScoreWork = namedtuple("ZScoreWork", "features stats ticket frame_offsets row_offsets batch total_frames")
+
+
+def zscore_work(features, frame_offsets, batch, total_frames, out_row_offsets=None, stream=None):
+    """The z-score pass of a ``spectrogram_device(..., phases=SETUP | MAIN | STATS)`` call on ``stream``, packaged
+    for ``ctc.ctc_loss_grad(zscore=...)``: the fused CTC kernel normalises the rows as co-work
+    (``asrk_ctc_loss_grad_zscore_run``).  ``stats`` / ``ticket`` are addresses inside that call's workspace."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    ws = workspace(L.asrk_spectrogram_workspace_bytes(batch, total_frames), features.device, "spec", stream)
+    stats, ticket = ctypes.c_void_p(), ctypes.c_void_p()
+    rc = L.asrk_spectrogram_zscore_handles(_lib.ptr(ws), ws.numel(), int(batch), int(total_frames),
+                                           ctypes.byref(stats), ctypes.byref(ticket))
+    _lib.check(rc, "asrk_spectrogram_zscore_handles")
+    return ZScoreWork(features, stats, ticket, frame_offsets, out_row_offsets, int(batch), int(total_frames))
 
 
 def compute_features(signals, fs=16000, mode="fbank", noises=None, snr_db=None, gain=None,

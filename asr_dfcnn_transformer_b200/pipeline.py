@@ -43,9 +43,13 @@ def all_reduce_loss(loss_sum_and_count, group=None, stream=None):
 
 
 class HotPathStep:
-    def __init__(self, device=None, feature_ctas=0):
+    def __init__(self, device=None, feature_ctas=0, merged_tail=True):
         torch = _lib.require_cuda()
         self.torch = torch
+        # the step's HBM-bound tail as ONE kernel: the z-score pass rides on the fused CTC kernel as co-work whenever
+        # the batch is bounded to small lattices (``ctc_bounds``); otherwise, or with merged_tail=False, two kernels
+        self.merged_tail = bool(merged_tail)
+        self._ev_feat = torch.cuda.Event()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.feature_ctas = int(feature_ctas)
         self.side = torch.cuda.Stream(device=self.device)
@@ -108,16 +112,43 @@ class HotPathStep:
         self._ev_fork.record(cur)
         self.side.wait_event(self._ev_fork)
         self.hi.wait_event(self._ev_fork)
-        with torch.cuda.stream(self.side):
-            feats = features.spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch,
-                                                total_frames, mode, out=feat_out, cta_limit=self.feature_ctas,
-                                                stream=self.side)
-            self._ev_join.record(self.side)
-        with torch.cuda.stream(self.hi):
-            res = ctc.ctc_loss_grad(logits, labels, label_len, input_len, blank, layout=layout,
-                                    grad_scale=grad_scale, grad_out=grad_out, decode=decode, bounds=ctc_bounds,
-                                    stream=self.hi)
-            self._ev_join2.record(self.hi)
+        res = None
+        if self.merged_tail and mode == "fbank" and ctc_bounds is not None and batch > 0 and total_frames > 0:
+            # transform + statistics on the side stream; the CTC kernel waits for them and normalises the rows itself
+            with torch.cuda.stream(self.side):
+                feats = features.spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch,
+                                                    total_frames, mode, out=feat_out, cta_limit=self.feature_ctas,
+                                                    stream=self.side,
+                                                    phases=_lib.PHASE_SPEC_SETUP | _lib.PHASE_SPEC_MAIN | _lib.PHASE_SPEC_STATS)
+                self._ev_feat.record(self.side)
+            zw = features.zscore_work(feats, frame_offsets, batch, total_frames, stream=self.side)
+            self.hi.wait_event(self._ev_feat)
+            try:
+                with torch.cuda.stream(self.hi):
+                    res = ctc.ctc_loss_grad(logits, labels, label_len, input_len, blank, layout=layout,
+                                            grad_scale=grad_scale, grad_out=grad_out, decode=decode, bounds=ctc_bounds,
+                                            stream=self.hi, zscore=zw)
+                    self._ev_join2.record(self.hi)
+                self._ev_join.record(self.side)
+            except ctc.CoWorkNotEligible:
+                res = None                      # nothing was launched: finish the features the two-kernel way
+                with torch.cuda.stream(self.side):
+                    features.spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch,
+                                                total_frames, mode, out=feats, stream=self.side,
+                                                phases=_lib.PHASE_SPEC_NORMALIZE)
+                    self._ev_join.record(self.side)
+        else:
+            with torch.cuda.stream(self.side):
+                feats = features.spectrogram_device(samples, sample_offsets, sample_counts, frame_offsets, batch,
+                                                    total_frames, mode, out=feat_out, cta_limit=self.feature_ctas,
+                                                    stream=self.side)
+                self._ev_join.record(self.side)
+        if res is None:
+            with torch.cuda.stream(self.hi):
+                res = ctc.ctc_loss_grad(logits, labels, label_len, input_len, blank, layout=layout,
+                                        grad_scale=grad_scale, grad_out=grad_out, decode=decode, bounds=ctc_bounds,
+                                        stream=self.hi)
+                self._ev_join2.record(self.hi)
         cur.wait_event(self._ev_join)
         cur.wait_event(self._ev_join2)
         # (the tensors were allocated / are used on other streams than the caller's: tell the allocator -- not under a

@@ -232,10 +232,14 @@ class DeviceBatch:
 _STEP = {}
 
 
+MERGED_TAIL = True     # --two-kernel-tail: z-score and CTC as separate kernels (round 2's first version)
+
+
 def hot_path(dev):
     from asr_dfcnn_transformer_b200 import pipeline
     if dev not in _STEP:
-        _STEP[dev] = pipeline.HotPathStep(dev, feature_ctas=int(os.environ.get("ASRK_FEATURE_CTAS", "0")))
+        _STEP[dev] = pipeline.HotPathStep(dev, feature_ctas=int(os.environ.get("ASRK_FEATURE_CTAS", "0")),
+                                          merged_tail=MERGED_TAIL)
     return _STEP[dev]
 
 
@@ -253,12 +257,21 @@ def run_step(db, surface="logits"):
         cur = torch.cuda.current_stream(hp.device)
         hp._ev_fork.record(cur)
         hp.side.wait_event(hp._ev_fork)
+        from asr_dfcnn_transformer_b200 import _lib
+        merged = MERGED_TAIL and db.ctc_bounds is not None
         with torch.cuda.stream(hp.side):
             features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat,
-                                        stream=hp.side)
+                                        stream=hp.side,
+                                        phases=(_lib.PHASE_SPEC_SETUP | _lib.PHASE_SPEC_MAIN | _lib.PHASE_SPEC_STATS)
+                                        if merged else _lib.PHASE_ALL)
             hp._ev_join.record(hp.side)
+        zw = None
+        if merged:       # the CTC kernel normalises the feature rows as co-work: it runs behind the transform
+            cur.wait_event(hp._ev_join)
+            zw = features.zscore_work(db.feat, db.fo, db.B, db.total_frames, stream=hp.side)
         r = ctc.ctc_loss_grad(db.probs, db.labels, db.label_len, db.input_len, V - 1, layout="btv",
-                              grad_scale=db.grad_scale, grad_out=db.grad, bounds=db.ctc_bounds, input_kind="prob")
+                              grad_scale=db.grad_scale, grad_out=db.grad, bounds=db.ctc_bounds, input_kind="prob",
+                              zscore=zw)
         cur.wait_event(hp._ev_join)
         return r
     _, r = hot_path(db.samples.device)(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames,
@@ -278,6 +291,19 @@ def run_step_phases(db, ev):
     """the same launches issued phase by phase with CUDA events between them (c4: feature phases only)"""
     from asr_dfcnn_transformer_b200 import _lib, ctc, features
     ev.mark()
+    if MERGED_TAIL and db.workload in ("c2", "c5") and db.ctc_bounds is not None:
+        # the step's three kernels: transform, statistics, fused CTC with the z-score as co-work
+        for ph in (_lib.PHASE_SPEC_SETUP, _lib.PHASE_SPEC_MAIN, _lib.PHASE_SPEC_STATS):
+            features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat,
+                                        phases=ph)
+            ev.mark()
+        ev.mark()                                   # (no separate prep kernel)
+        zw = features.zscore_work(db.feat, db.fo, db.B, db.total_frames)
+        ctc.ctc_loss_grad(db.logits, db.labels, db.label_len, db.input_len, V - 1, grad_scale=db.grad_scale,
+                          grad_out=db.grad, bounds=db.ctc_bounds, decode=(db.workload == "c5"), zscore=zw)
+        for _ in range(4):
+            ev.mark()                               # ctc_fused = the merged kernel; no generic kernels
+        return
     for ph in (_lib.PHASE_SPEC_SETUP, _lib.PHASE_SPEC_MAIN, _lib.PHASE_SPEC_NORMALIZE):
         features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat,
                                     noise=db.noise, snr_db=db.snr_db, phases=ph)
@@ -300,10 +326,11 @@ class PhaseTimer:
         self.cur = None
 
     def begin(self):
-        # plug the stream for ~0.4 ms first: the step's launches and event records are then all enqueued while the GPU
+        # plug the stream for ~2 ms first: the step's launches and event records are then all enqueued while the GPU
         # is busy, so an interval between two events is device time only (without it every interval also holds the
-        # host's enqueue latency of the next launch whenever the GPU has run dry: +20 us on a 125 us kernel)
-        self.torch.cuda._sleep(800000)
+        # host's enqueue latency of the next launch whenever the GPU has run dry: +20 us on a 125 us kernel; with a
+        # 0.4 ms plug the last call of a step -- the Python-heavy CTC entry -- still arrived late)
+        self.torch.cuda._sleep(4000000)
         self.cur = []
 
     def mark(self):
@@ -447,9 +474,13 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--surface", default="logits", choices=["logits", "keras"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--two-kernel-tail", action="store_true",
+                    help="z-score and fused CTC as two kernels instead of one (the z-score as the CTC kernel's co-work)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global MERGED_TAIL
+    MERGED_TAIL = not args.two_kernel_tail
     if args.surface == "keras" and args.workload != "c2":
         ap.error("--surface keras is a variant of the c2 workload")
 
@@ -725,6 +756,8 @@ def main():
                        "utterances_per_gpu": BATCH, "audio_s_per_step_per_gpu": audio_per_step,
                        "all_reduce": "[sum loss, n] accumulated on the device, all-reduced every %d steps" % REDUCE_EVERY,
                        "numa_node_rank0": numa, "cuda_graph": bool(use_graph),
+                       "tail": ("one kernel: fused CTC with the z-score as co-work" if MERGED_TAIL and args.workload in ("c2", "c5")
+                                else "z-score and CTC kernels separate"),
                        "l2": "inputs larger than L2: %d distinct batches rotated, ~%.0f MB touched per step"
                              % (POOL, (step_alg + bc / 2) / 1e6)},
             "roofline": roof,

@@ -286,7 +286,8 @@ int asrk_edit_distance_run(const int* hyp, int hyp_stride, const int* hyp_len,
  * ------------------------------------------------------------------------ */
 #define ASRK_PHASE_SPEC_SETUP 1      /* tables, tile map, (SNR2K gains)            */
 #define ASRK_PHASE_SPEC_MAIN 2       /* framing + window + FFT + log-magnitude     */
-#define ASRK_PHASE_SPEC_NORMALIZE 4  /* per-utterance z-score                      */
+#define ASRK_PHASE_SPEC_NORMALIZE 4  /* per-utterance z-score (statistics + rows)  */
+#define ASRK_PHASE_SPEC_STATS 8      /* without NORMALIZE: the statistics only     */
 #define ASRK_PHASE_CTC_PREP 1        /* label lists, feasibility, repeat chains    */
 #define ASRK_PHASE_CTC_ROWS 2        /* per-frame log-sum-exp / arg-max / gather   */
 #define ASRK_PHASE_CTC_LATTICE 4     /* alpha / beta recursion, loss               */
@@ -306,6 +307,34 @@ int asrk_spectrogram_run_phases(const void* samples, int sample_dtype, const flo
                                 int batch, long long total_frames, int mode, float* out,
                                 void* workspace, size_t workspace_bytes, asrk_stream_t stream,
                                 int phases);
+
+/* The step's tail as ONE kernel: the CTC loss/gradient of a batch bounded to small lattices (flags must carry
+ * ASRK_CTC_SMALL_ONLY, see asrk_ctc_fits_fused; ASRK_CTC_INPUT_PROB allowed) with the z-score pass of the FEATURE
+ * path as co-work -- every CTA that has finished its utterance, and the CTAs launched beyond the batch, normalise
+ * chunks of up to 64 rows of `z_features` in place ((x - mean) / std per utterance and column: wav_util.py:79; the
+ * chunks travel as TMA bulk copies through the kernel's shared memory) from the statistics the spectrogram call left
+ * in its workspace.  Call order on the feature side:
+ *   asrk_spectrogram_run_phases(..., ASRK_PHASE_SPEC_SETUP | ASRK_PHASE_SPEC_MAIN | ASRK_PHASE_SPEC_STATS)
+ *   asrk_spectrogram_zscore_handles(workspace, ...) -> z_stats, z_ticket
+ * then this call, ordered behind it (same stream or an event).  z_frame_offsets / z_batch / z_total_frames are the
+ * spectrogram call's frame_offsets / batch / total_frames; z_row_offsets must be NULL (flat row layout only).
+ * Returns ASRK_E_SHAPE -- before anything is launched -- when the batch cannot take the fused kernel (vector path
+ * not applicable, not bounded): run ASRK_PHASE_SPEC_NORMALIZE and the plain CTC entry instead. */
+int asrk_ctc_loss_grad_zscore_run(const float* logits, long long stride_t, long long stride_b,
+                                  int T, int B, int V, const int* labels, int label_stride,
+                                  const int* label_len, const int* input_len, int blank, int label_mode,
+                                  const float* grad_scale, float* loss, float* grad,
+                                  long long grad_stride_t, long long grad_stride_b, int* row_status,
+                                  int* tokens, int token_stride, int* token_len, float* neg_sum_logits,
+                                  void* workspace, size_t workspace_bytes, asrk_stream_t stream, int flags,
+                                  float* z_features, const float* z_stats, const long long* z_frame_offsets,
+                                  const long long* z_row_offsets, int z_batch, long long z_total_frames,
+                                  int* z_ticket);
+
+/* Where the spectrogram call keeps the per-utterance statistics ([batch][3][200] float32: mean hi, mean lo, 1/std)
+ * and the co-work ticket inside its workspace (same batch / total_frames as the run call). */
+int asrk_spectrogram_zscore_handles(void* workspace, size_t workspace_bytes, int batch, long long total_frames,
+                                    float** stats, int** ticket);
 
 int asrk_ctc_loss_grad_run_phases(const float* logits, long long stride_t, long long stride_b,
                                   int T, int B, int V, const int* labels, int label_stride,

@@ -66,3 +66,59 @@ def _check(rt, s, want, T):
     valid = np.arange(T)[:, None] < il[None, :]
     assert np.array_equal(got[valid], grad[valid])
     assert not got[~valid].any()
+
+
+@pytest.mark.parametrize("B,kind", [(24, "logits"), (301, "logits"), (5, "prob")])
+def test_merged_tail_equals_two_kernel_step(B, kind):
+    """pipeline.HotPathStep with the z-score riding on the fused CTC kernel (one kernel for the step's tail) gives
+    bit-identical features, losses, gradients and tokens to the separate calls: more utterances than resident CTAs
+    (301 > 2 x 148), fewer than the co-work-only CTAs, an utterance without frames, chunk boundaries inside and
+    between utterances, both input kinds; and a batch that cannot take the fused kernel falls back silently."""
+    from oracle import synth
+    from asr_dfcnn_transformer_b200 import _lib, ctc, features, pipeline
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(4200 + B)
+    lens = synth.ragged_lengths(rng, B, 0.3, 2.5)
+    lens[1] = 300                                    # no frame at all (fbank rule: needs 400 samples)
+    pcm = [synth.g2_voiced(rng, int(n)) for n in lens]
+    pk = features.pack_host(pcm, pin=False)
+    il = np.maximum(1, np.array([synth.t_ctc(max(int(f), 1)) for f in pk.n_frames], dtype=np.int32))
+    V = 64
+    x, labels, ll, il = synth.ctc_batch(rng, il, V, 1, 4, lmax=8)
+    if kind == "prob":
+        e = np.exp(x - x.max(-1, keepdims=True))
+        x = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    so = torch.as_tensor(np.asarray(pk.sample_offsets, dtype=np.int64)).to(dev)
+    sc = torch.as_tensor(np.asarray(pk.sample_counts, dtype=np.int64)).to(dev)
+    fo = torch.as_tensor(np.asarray(pk.frame_offsets, dtype=np.int64)).to(dev)
+    samples = pk.samples.to(dev)
+    nf = int(pk.frame_offsets[-1])
+    logits = torch.as_tensor(x).to(dev)
+    dlab = torch.as_tensor(labels.astype(np.int32)).to(dev)
+    dll, dil = torch.as_tensor(ll).to(dev), torch.as_tensor(il).to(dev)
+    bounds = (int(il.max()), int(ll.max()))
+    # separate calls
+    f_ref = features.spectrogram_device(samples, so, sc, fo, B, nf, "fbank")
+    r_ref = ctc.ctc_loss_grad(logits, dlab, dll, dil, V - 1, bounds=bounds, decode=(kind == "logits"), input_kind=kind)
+    torch.cuda.synchronize()
+    n0 = _lib.lib().asrk_launch_count()
+    if kind == "prob":
+        # the step itself speaks logits; the co-work entry is reached through the raw op
+        f = features.spectrogram_device(samples, so, sc, fo, B, nf, "fbank",
+                                        phases=_lib.PHASE_SPEC_SETUP | _lib.PHASE_SPEC_MAIN | _lib.PHASE_SPEC_STATS)
+        zw = features.zscore_work(f, fo, B, nf)
+        r = ctc.ctc_loss_grad(logits, dlab, dll, dil, V - 1, bounds=bounds, input_kind="prob", zscore=zw)
+    else:
+        step = pipeline.HotPathStep(dev)
+        f, r = step(samples, so, sc, fo, B, nf, logits, dlab, dll, dil, V - 1, decode=True, ctc_bounds=bounds)
+    torch.cuda.synchronize()
+    assert _lib.lib().asrk_launch_count() - n0 == 3          # transform, statistics, fused CTC + z-score
+    assert torch.equal(f, f_ref)
+    assert torch.equal(r.loss, r_ref.loss) and torch.equal(r.grad, r_ref.grad) and torch.equal(r.row_status, r_ref.row_status)
+    if kind == "logits":
+        assert torch.equal(r.token_len, r_ref.token_len)
+        assert ctc.tokens_to_lists(r.tokens, r.token_len) == ctc.tokens_to_lists(r_ref.tokens, r_ref.token_len)
+        # a batch whose lattices do not fit the fused kernel: same call, two-kernel tail
+        f2, r2 = step(samples, so, sc, fo, B, nf, logits, dlab, dll, dil, V - 1, decode=True, ctc_bounds=(5000, 600))
+        torch.cuda.synchronize()
+        assert torch.equal(f2, f_ref) and torch.equal(r2.loss, r_ref.loss) and torch.equal(r2.grad, r_ref.grad)
