@@ -90,7 +90,7 @@ struct Params {
         const float* stats;               // [Bz][3][200]: mean (hi, lo), 1/std
         const long long* frame_offsets;   // [Bz + 1]
         const long long* row_offsets;     // [Bz] first output row of every utterance, or nullptr (= frame_offsets)
-        int* ticket;                      // [1] next chunk (zero on entry)
+        int* ticket;                      // [2] next chunk, next utterance (zero on entry)
         int batch;
         int rows;                         // feature rows per chunk
         long long total_frames;
@@ -540,9 +540,6 @@ __device__ __forceinline__ float warp_max_redux(float v) {
 // normalised (4 x 25.6 KB per CTA for V = 1424; with two buffers a CTA was bound by one bulk copy's latency at
 // 26 GB/s), and the rows leave through plain 16-byte evict-first stores.
 // Thread (r, q) owns column group q (4 bins) of rows r, r + 5, ...: its statistics live in registers per utterance.
-#ifndef ASRK_ZPRE_X100
-#define ASRK_ZPRE_X100 20
-#endif
 constexpr int kZBins = 200;
 constexpr int kZCache = 512;            // utterance starts cached in shared memory (larger batches: global look-ups)
 constexpr int kZBufs = 4;               // chunk buffers per CTA: three bulk copies in flight while one chunk is normalised
@@ -635,36 +632,37 @@ __device__ __forceinline__ void zscore_cowork(const Params::ZWork& z, float* sm,
 }
 
 template <int NV4, bool PROB>
-__device__ __forceinline__ void fused_small_body(const Params& p, float* sm);
+__device__ __forceinline__ void fused_small_body(const Params& p, float* sm, int b);
 
 template <int NV4, bool PROB>
 __global__ void __maxnreg__(112) fused_small_kernel(Params p) {
     extern __shared__ __align__(16) float sm[];
-    if (blockIdx.x < (unsigned)p.B) {
-        // a CTA whose utterance is shorter than the longest takes some chunks FIRST (0.2 per frame of slack): the CTAs
-        // then reach their HBM-bound row phases at different times instead of all at once (merged kernel 86.6 -> 84.1 us
-        // on a C2 batch; 0.4 per frame: 86.9)
-        if (p.z.feat != nullptr && ASRK_ZPRE_X100 > 0) {
-            int tb = p.input_len[blockIdx.x];
-            tb = tb < 0 ? 0 : (tb > p.T ? p.T : tb);
-            int pre = ((p.T - tb) * ASRK_ZPRE_X100) / 100;
-            pre = pre > 24 ? 24 : pre;
-            if (pre > 0) zscore_cowork(p.z, sm, pre);
-            __syncthreads();
-        }
-        fused_small_body<NV4, PROB>(p, sm);      // (CTAs beyond the batch: co-work only)
+    if (p.z.feat == nullptr) {
+        fused_small_body<NV4, PROB>(p, sm, (int)blockIdx.x);
+        return;
     }
-    if (p.z.feat != nullptr) zscore_cowork(p.z, sm, -1);
+    // with co-work: utterances are CLAIMED (ticket z.ticket[1]), CTC work first -- a CTA that looped on z-score chunks
+    // while utterances were still waiting for a slot (fewer than two CTAs resident per SM at launch: observed, the
+    // kernel then took 130-230 us instead of 84) would put the z-score in front of the CTC critical path
+    __shared__ int s_utt;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_utt = atomicAdd(p.z.ticket + 1, 1);
+        __syncthreads();
+        const int b = s_utt;
+        if (b >= p.B) break;
+        fused_small_body<NV4, PROB>(p, sm, b);
+    }
+    zscore_cowork(p.z, sm, -1);
 }
 
 template <int NV4, bool PROB>
-__device__ __forceinline__ void fused_small_body(const Params& p, float* sm) {
+__device__ __forceinline__ void fused_small_body(const Params& p, float* sm, const int b) {
     __shared__ double s_fin;
 #ifdef ASRK_CTC_TIMING
     __shared__ unsigned long long s_tick[12];
 #endif
     ASRK_TICK(0);
-    const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int T = p.input_len[b];

@@ -607,7 +607,7 @@ extern "C" int asrk_spectrogram_zscore_handles(void* workspace, size_t workspace
     if (workspace_bytes < l.total) return ASRK_E_WORKSPACE;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     *stats = reinterpret_cast<float*>(ws + l.stats);
-    *ticket = reinterpret_cast<int*>(ws + l.counters) + 2;     // zeroed with the tile counter by the MAIN phase
+    *ticket = reinterpret_cast<int*>(ws + l.counters) + 2;     // two ints, zeroed with the tile counter by the MAIN phase
     return ASRK_OK;
 }
 

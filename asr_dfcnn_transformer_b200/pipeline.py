@@ -43,11 +43,12 @@ def all_reduce_loss(loss_sum_and_count, group=None, stream=None):
 
 
 class HotPathStep:
-    def __init__(self, device=None, feature_ctas=0, merged_tail=True):
+    def __init__(self, device=None, feature_ctas=0, merged_tail=False):
         torch = _lib.require_cuda()
         self.torch = torch
-        # the step's HBM-bound tail as ONE kernel: the z-score pass rides on the fused CTC kernel as co-work whenever
-        # the batch is bounded to small lattices (``ctc_bounds``); otherwise, or with merged_tail=False, two kernels
+        # merged_tail=True: the step's HBM-bound tail as ONE kernel -- the z-score pass rides on the fused CTC kernel as
+        # co-work whenever the batch is bounded to small lattices (``ctc_bounds``).  Bit-identical and one launch fewer,
+        # but measured no faster than the two overlapping kernels (profiles/r2_tail.md), so it is not the default
         self.merged_tail = bool(merged_tail)
         self._ev_feat = torch.cuda.Event()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

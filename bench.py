@@ -232,7 +232,7 @@ class DeviceBatch:
 _STEP = {}
 
 
-MERGED_TAIL = True     # --two-kernel-tail: z-score and CTC as separate kernels (round 2's first version)
+MERGED_TAIL = False    # --merged-tail: the z-score as co-work of the fused CTC kernel (one kernel for the step's tail)
 
 
 def hot_path(dev):
@@ -474,13 +474,14 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--surface", default="logits", choices=["logits", "keras"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--two-kernel-tail", action="store_true",
-                    help="z-score and fused CTC as two kernels instead of one (the z-score as the CTC kernel's co-work)")
+    ap.add_argument("--merged-tail", action="store_true",
+                    help="one kernel for the step's tail: the z-score pass as co-work of the fused CTC kernel "
+                         "(bit-identical, measured no faster: profiles/r2_tail.md)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global MERGED_TAIL
-    MERGED_TAIL = not args.two_kernel_tail
+    MERGED_TAIL = bool(args.merged_tail)
     if args.surface == "keras" and args.workload != "c2":
         ap.error("--surface keras is a variant of the c2 workload")
 

@@ -109,7 +109,7 @@ def test_merged_tail_equals_two_kernel_step(B, kind):
         zw = features.zscore_work(f, fo, B, nf)
         r = ctc.ctc_loss_grad(logits, dlab, dll, dil, V - 1, bounds=bounds, input_kind="prob", zscore=zw)
     else:
-        step = pipeline.HotPathStep(dev)
+        step = pipeline.HotPathStep(dev, merged_tail=True)
         f, r = step(samples, so, sc, fo, B, nf, logits, dlab, dll, dil, V - 1, decode=True, ctc_bounds=bounds)
     torch.cuda.synchronize()
     assert _lib.lib().asrk_launch_count() - n0 == 3          # transform, statistics, fused CTC + z-score
