@@ -16,10 +16,12 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
 WORKLOADS = [("c2", "C2 (256 utterances, 3-7 s; logits surface)"), ("c2keras", "C2, Keras surface (probabilities in)"),
+             ("c2merged", "C2 with the merged tail (--merged-tail: z-score as co-work of the fused CTC kernel)"),
              ("c3", "C3 (64 utterances of 20 s, T = 1998, L ~ 300: generic CTC kernels)"),
              ("c4", "C4 (512 float32 utterances + noise, SNR2K + fused mix, features only)")]
 OURS = ("spec::", "ctc::", "noise::")
-REPS = [("prof_step_r2", "c2"), ("prof_keras_r2", "c2keras"), ("prof_c3_r2", "c3"), ("prof_c4_r2", "c4")]
+REPS = [("prof_step_r2", "c2"), ("prof_keras_r2", "c2keras"), ("prof_merged_r2", "c2merged"), ("prof_c3_r2", "c3"),
+        ("prof_c4_r2", "c4")]
 KEYS = {"spectrogram_kernel<0>": "spec_main", "spectrogram_kernel<1>": "spec_main_f32", "fused_small_kernel": "ctc_fused",
         "normalize_kernel": "spec_normalize", "stats_kernel": "spec_stats", "rows_kernel": "ctc_rows",
         "lattice_kernel": "ctc_lattice", "grad_kernel": "ctc_grad", "snr2k_kernel": "snr2k"}

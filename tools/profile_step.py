@@ -1,5 +1,5 @@
 """Small driver for ncu: builds one C2 batch and runs a few steps of the hot path.
-    python tools/profile_step.py [steps] [batch]
+    python tools/profile_step.py [steps] [workload] [surface] [merged]
 """
 import os
 import sys
@@ -12,6 +12,7 @@ import bench  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 workload = sys.argv[2] if len(sys.argv) > 2 else "c2"
 surface = sys.argv[3] if len(sys.argv) > 3 else "logits"
+bench.MERGED_TAIL = len(sys.argv) > 4 and sys.argv[4] == "merged"      # the z-score as co-work of the fused CTC kernel
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 w = bench.WORKLOADS[workload]
