@@ -1693,6 +1693,9 @@ static int run_phases_impl(const float* logits, long long stride_t, long long st
         rows = rows > 32 ? 32 : rows - rows % 8;
         if (rows < 8) return ASRK_E_SHAPE;
         p.z.rows = (int)rows;
+        // fresh tickets for THIS launch (a second call behind the same spectrogram call must not find them spent:
+        // no utterance would be claimed and the outputs would silently keep their old contents)
+        if (cudaMemsetAsync(p.z.ticket, 0, 2 * sizeof(int), stream) != cudaSuccess) return ASRK_E_CUDA;
     }
     if (phases & ASRK_PHASE_CTC_PREP) {
         if (!p.small_only && cudaMemsetAsync(p.need_generic, 0, sizeof(int), stream) != cudaSuccess)

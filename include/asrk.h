@@ -332,8 +332,8 @@ int asrk_ctc_loss_grad_zscore_run(const float* logits, long long stride_t, long 
                                   int* z_ticket);
 
 /* Where the spectrogram call keeps the per-utterance statistics ([batch][3][200] float32: mean hi, mean lo, 1/std)
- * and the co-work tickets (two ints: next chunk, next utterance; zeroed by ASRK_PHASE_SPEC_MAIN) inside its
- * workspace (same batch / total_frames as the run call). */
+ * and the co-work tickets (two ints: next chunk, next utterance; asrk_ctc_loss_grad_zscore_run zeroes them on its
+ * stream before it launches) inside its workspace (same batch / total_frames as the run call). */
 int asrk_spectrogram_zscore_handles(void* workspace, size_t workspace_bytes, int batch, long long total_frames,
                                     float** stats, int** ticket);
 
