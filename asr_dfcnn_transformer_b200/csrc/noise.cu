@@ -12,12 +12,15 @@
 // combined along the recursion n -> (n/2 rounded down to a multiple of 8, rest)),
 // then float32 divide / sqrt / multiply.
 //
-// One CTA per utterance.  TWO lanes own one leaf block: lane h holds accumulators 4h .. 4h+3 of numpy's eight and
-// reads its half of every 32-byte group with one 16-byte load (all of a leaf's <= 16 loads are issued before the
-// first add: 8 KB in flight per warp).  A warp folds its 16 leaves through four levels of the recursion tree with
-// shuffles (siblings are neighbours); what is left of the tree lives in a small shared-memory heap, folded bottom-up.
+// One CTA per utterance.  A warp takes sixteen consecutive leaf blocks (<= 2048 samples) per pass: it copies that
+// range of both arrays into shared memory with coalesced 16-byte cp.async (16 KB in flight per warp), then TWO lanes
+// own one leaf -- lane h holds accumulators 4h .. 4h+3 of numpy's eight -- and the warp folds its 16 leaf sums
+// through four levels of the recursion tree with shuffles (siblings are neighbours); what is left of the tree lives
+// in a small shared-memory heap, folded bottom-up.
 // (Round 1 gave a leaf to eight lanes with 4-byte loads in a dependent loop and kept the whole tree in 144 KB of
-// shared memory: one 1024-thread CTA per SM, 1.7 waves, 1.8 TB/s.)
+// shared memory: one 1024-thread CTA per SM, 1.7 waves, 1.8 TB/s = 181 us per C4 batch.  Round 2's first version
+// read the leaves straight from global memory, 16 bytes per lane: every load instruction touched 16 cache lines
+// (leaves are ~312 bytes apart) and the kernel was bound by L1 tag look-ups: 116 us.)
 #include <math.h>
 
 #include "asrk_common.cuh"
@@ -30,32 +33,25 @@ constexpr int kMaxDepth = 15;                 // up to 128 * 2^15 = 4,194,304 sa
 constexpr int kWarpLevels = 4;                // 16 leaves per warp and pass
 constexpr int kHeap = 1 << (kMaxDepth - kWarpLevels + 1);   // heap slots above the warps' sub-trees (index 1 = root)
 constexpr int kBlock = 128;                   // numpy PW_BLOCKSIZE
+constexpr int kStage = 16 * kBlock;           // floats per warp and array: its sixteen leaves
 
 // sum of squares of a[0 .. len) in numpy's leaf order (len <= 128), for the lane pair (h = 0 / 1) that owns the leaf;
-// the result is valid in lane h == 0.  `vec`: a is 16-byte aligned.
-__device__ __forceinline__ float leaf_sum(const float* a, int len, int h, bool vec) {
+// the result is valid in lane h == 0.  `a` points into the warp's staged copy of its sixteen leaves (shared memory).
+__device__ __forceinline__ float leaf_sum(const float* a, int len, int h) {
     const int ngrp = len >> 3;                 // full groups of eight (<= 16); none: numpy's plain loop from 0
     float r = 0.f;
     if (ngrp > 0) {
-        float4 v[16];
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-            if (g < ngrp) {
-                const float* q = a + 8 * g + 4 * h;
-                if (vec) v[g] = __ldcs(reinterpret_cast<const float4*>(q));
-                else v[g] = make_float4(__ldcs(q), __ldcs(q + 1), __ldcs(q + 2), __ldcs(q + 3));
-            }
-        }
-        float r0 = __fmul_rn(v[0].x, v[0].x), r1 = __fmul_rn(v[0].y, v[0].y);
-        float r2 = __fmul_rn(v[0].z, v[0].z), r3 = __fmul_rn(v[0].w, v[0].w);
-#pragma unroll
-        for (int g = 1; g < 16; ++g) {
-            if (g < ngrp) {
-                r0 = __fadd_rn(r0, __fmul_rn(v[g].x, v[g].x));
-                r1 = __fadd_rn(r1, __fmul_rn(v[g].y, v[g].y));
-                r2 = __fadd_rn(r2, __fmul_rn(v[g].z, v[g].z));
-                r3 = __fadd_rn(r3, __fmul_rn(v[g].w, v[g].w));
-            }
+        // (leaf starts are multiples of 8 samples from the staged range's start: 16-byte aligned)
+        const float4* a4 = reinterpret_cast<const float4*>(a) + h;
+        float4 v = a4[0];
+        float r0 = __fmul_rn(v.x, v.x), r1 = __fmul_rn(v.y, v.y), r2 = __fmul_rn(v.z, v.z), r3 = __fmul_rn(v.w, v.w);
+#pragma unroll 4
+        for (int g = 1; g < ngrp; ++g) {
+            v = a4[2 * g];
+            r0 = __fadd_rn(r0, __fmul_rn(v.x, v.x));
+            r1 = __fadd_rn(r1, __fmul_rn(v.y, v.y));
+            r2 = __fadd_rn(r2, __fmul_rn(v.z, v.z));
+            r3 = __fadd_rn(r3, __fmul_rn(v.w, v.w));
         }
         r = __fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3));
     }
@@ -102,6 +98,9 @@ __global__ void __launch_bounds__(kThreads, 4) snr2k_kernel(const float* signal,
     const float* noi = noise + s0;
     const bool vec = ((reinterpret_cast<uintptr_t>(sig) | reinterpret_cast<uintptr_t>(noi)) & 15) == 0;
     const int lane = tid & 31;
+    extern __shared__ __align__(16) float stage_all[];                        // [warps][2][kStage]
+    float* st_s = stage_all + (size_t)(tid >> 5) * 2 * kStage;
+    float* st_n = st_s + kStage;
     const int q = lane >> 1, h = lane & 1;      // leaf of the warp, half of the leaf
     const int n_slots = 1 << D;
     for (int base = 0; base < n_slots; base += kThreads / 2) {
@@ -123,8 +122,42 @@ __global__ void __launch_bounds__(kThreads, 4) snr2k_kernel(const float* signal,
         }
         // both lanes of a pair share `valid`; pairs of one warp may differ, so keep the shuffles converged by running
         // the leaf for everyone (an invalid pair reads nothing: len 0)
-        float es = leaf_sum(sig + (valid ? start : 0), valid ? (int)len : 0, h, vec);
-        float en = leaf_sum(noi + (valid ? start : 0), valid ? (int)len : 0, h, vec);
+        // the warp's valid leaves are consecutive in memory: one coalesced copy of [first start, last end) of both
+        // arrays into the warp's staging rows (16-byte cp.async; 4-byte when the utterance start is not aligned)
+        const long long lo = valid ? start : 0x7fffffffffffffffLL, hi = valid ? start + len : -1;
+        long long w0 = lo, w1 = hi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long a0 = __shfl_xor_sync(0xffffffffu, w0, o), a1 = __shfl_xor_sync(0xffffffffu, w1, o);
+            w0 = a0 < w0 ? a0 : w0;
+            w1 = a1 > w1 ? a1 : w1;
+        }
+        if (w1 > w0) {
+            const int cnt = (int)(w1 - w0);                                  // <= 16 * 128 floats
+            if (vec) {
+                const int n4 = cnt >> 2;                                     // (starts and w0 are multiples of 8)
+                for (int i = lane; i < n4; i += 32) {
+                    cp_async16(st_s + 4 * i, sig + w0 + 4 * i, 16);
+                    cp_async16(st_n + 4 * i, noi + w0 + 4 * i, 16);
+                }
+                for (int i = (n4 << 2) + lane; i < cnt; i += 32) {
+                    cp_async4(st_s + i, sig + w0 + i, 4);
+                    cp_async4(st_n + i, noi + w0 + i, 4);
+                }
+            } else {
+                for (int i = lane; i < cnt; i += 32) {
+                    cp_async4(st_s + i, sig + w0 + i, 4);
+                    cp_async4(st_n + i, noi + w0 + i, 4);
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        const int off = valid ? (int)(start - w0) : 0;
+        float es = leaf_sum(st_s + off, valid ? (int)len : 0, h);
+        float en = leaf_sum(st_n + off, valid ? (int)len : 0, h);
+        __syncwarp();                                                        // the staging rows are free again
         // fold the warp's 16 leaves: the left sibling takes left + right when the right one exists (a leaf above the
         // bottom level sits in the leftmost slot of its sub-tree, the other slots are absent)
         bool here = valid;
@@ -179,7 +212,9 @@ extern "C" int asrk_snr2k_run(const float* signal, const float* noise, const lon
     if (batch == 0) return ASRK_OK;
     if (!signal || !noise || !sample_offsets || !sample_counts || !snr_db || !gain_out)
         return ASRK_E_BADARG;
-    snr2k_kernel<<<batch, kThreads, 0, stream>>>(signal, noise, sample_offsets, sample_counts,
-                                                    snr_db, gain_out), asrk::note_launch();
+    const size_t smem = sizeof(float) * 2 * kStage * (kThreads / 32);
+    cudaFuncSetAttribute(snr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    snr2k_kernel<<<batch, kThreads, smem, stream>>>(signal, noise, sample_offsets, sample_counts,
+                                                       snr_db, gain_out), asrk::note_launch();
     return asrk::launch_status();
 }
