@@ -15,22 +15,28 @@
 //   fused   : one CTA per utterance whose lattice fits a warp and 60 KB of shared memory
 //             (every AISHELL-shaped utterance): rows streamed through per-warp buffers filled
 //             by TMA bulk copies on per-warp mbarriers (max / first arg-max / log-sum-exp /
-//             gather), alpha and beta on two warps concurrently in the fp32 log2 domain
-//             relative to levels kept in double, greedy collapse on a third, then the rows
-//             again from L2 for softmax minus occupancy, written once.  Logits cross HBM once
-//             in, the gradient once out.  A caller that bounds the batch (ASRK_CTC_SMALL_ONLY)
-//             gets exactly this one launch.
+//             gather), alpha and beta on two warps concurrently in the LINEAR domain in fp64
+//             with an exact power-of-two rescaling per column, greedy collapse on a third, then
+//             the rows again from L2 for softmax minus occupancy, written once.  Logits cross
+//             HBM once in, the gradient once out.  A caller that bounds the batch
+//             (ASRK_CTC_SMALL_ONLY) gets exactly this one launch.  With ASRK_CTC_INPUT_PROB the
+//             input is Keras' softmax output p: log(p + eps) and the gradient w.r.t. p are formed
+//             inside.  Optionally (asrk_ctc_loss_grad_zscore_run) the kernel also carries the
+//             z-score pass of the feature path as co-work: TMA-fed chunks through the shared
+//             memory of CTAs that have finished their utterances.
 //   generic path for long lattices (T in the thousands, hundreds of labels), skipped by a
 //   device flag when every utterance was fused:
 //   rows    : one WARP per (t,b) row, grid-stride -- max, first arg-max, log-sum-exp and the
 //             gather of the log-probabilities the lattice needs.  HBM-bound.
-//   lattice : one CTA per utterance -- log-space alpha / beta, one (blank,label) state pair
-//             per thread so a step needs ONE neighbour value; running values in fp64 with
-//             fp32 transcendentals and periodic max-renormalisation of the stored alpha.
-//   grad    : one WARP per row -- softmax from the (L2-resident) row and the stored
-//             log-sum-exp, minus the lattice occupancies, written once with 16-byte stores;
-//             zero rows for t >= len.  Repeated labels are summed along precomputed chains
-//             in a fixed order (no atomics): results are bit-reproducible.
+//   lattice : grid (B, 2): the alpha sweep and the beta sweep of an utterance run in two CTAs
+//             at the same time; log2 domain, one (blank,label) state pair per thread so a step
+//             needs ONE neighbour value; running values in fp64 with fp32 transcendentals on the
+//             differences, columns stored as float32 relative to a per-column level in double.
+//   grad    : one CTA per (utterance, 64 frames), a warp per row -- softmax from the row and the
+//             stored log-sum-exp, minus the lattice occupancies 2^(ahat + bhat + levels - log2 p)
+//             scattered per class into a shared-memory row first, so that the gradient row is
+//             written once with 16-byte stores; zero rows for t >= len.  Repeated labels are
+//             summed along precomputed chains in a fixed order (no atomics): bit-reproducible.
 //   collapse: greedy decode from the stored arg-max path (warp ballot + prefix count).
 #include <math.h>
 
@@ -40,7 +46,6 @@ namespace asrk {
 namespace ctc {
 
 constexpr int kRowWarps = 8;                 // warps per CTA in the row kernels
-constexpr int kRenorm = 8;                   // lattice renormalisation period (steps)
 constexpr float kNegInf = -INFINITY;
 
 struct Params {
