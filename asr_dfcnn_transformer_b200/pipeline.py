@@ -43,7 +43,7 @@ def all_reduce_loss(loss_sum_and_count, group=None, stream=None):
 
 
 class HotPathStep:
-    def __init__(self, device=None, feature_ctas=0, merged_tail=False):
+    def __init__(self, device=None, feature_ctas=0, merged_tail=False, feature_priority=0):
         torch = _lib.require_cuda()
         self.torch = torch
         # merged_tail=True: the step's HBM-bound tail as ONE kernel -- the z-score pass rides on the fused CTC kernel as
@@ -53,7 +53,9 @@ class HotPathStep:
         self._ev_feat = torch.cuda.Event()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.feature_ctas = int(feature_ctas)
-        self.side = torch.cuda.Stream(device=self.device)
+        # (feature_priority < 0: the persistent transform on a high-priority stream -- only matters when several
+        # steps are in flight on different HotPathStep instances, see tools/time_overlap.py)
+        self.side = torch.cuda.Stream(device=self.device, priority=int(feature_priority))
         # the CTC kernels go on a second stream of their own (fixed streams keep the scratch buffers' addresses fixed
         # for graph capture).  Measured and dropped: a HIGH-priority stream for the CTC kernel, gated behind the
         # transform kernel, so that its CTAs are dispatched before the z-score CTAs -- the two HBM-bound kernels
@@ -71,12 +73,12 @@ class HotPathStep:
         features.workspace(L.asrk_spectrogram_workspace_bytes(int(batch), int(total_frames)), self.device, "spec", self.side)
         features.workspace(L.asrk_ctc_workspace_bytes(int(T), int(batch), int(label_stride)), self.device, "ctc", self.hi)
 
-    def capture(self, *args, loss_acc=None, **kw):
+    def capture(self, *args, loss_acc=None, loss_out=None, **kw):
         """Capture one step on fixed device buffers (same arguments as ``__call__``; pass ``feat_out`` / ``grad_out``)
         into a CUDA graph: the steady state of a training loop replays it without any host-side enqueue between
         its kernels.  ``loss_acc`` (float64 [2] device tensor): the per-step [sum loss, n] is ADDED to it inside the
-        graph (``ctc.loss_sum(..., accumulate=True)``).  Returns (graph, features, CtcResult); ``graph.replay()``
-        runs the step on the current stream."""
+        graph (``ctc.loss_sum(..., accumulate=True)``); ``loss_out``: the step's own [sum loss, n] is WRITTEN to it.
+        Returns (graph, features, CtcResult); ``graph.replay()`` runs the step on the current stream."""
         torch = self.torch
         # workspaces, function attributes and the streams' pools exist before the capture starts
         self(*args, **kw)
@@ -87,6 +89,8 @@ class HotPathStep:
             feats, res = self(*args, **kw)
             if loss_acc is not None:
                 ctc.loss_sum(res.loss, res.row_status, out=loss_acc, accumulate=True)
+            if loss_out is not None:
+                ctc.loss_sum(res.loss, res.row_status, out=loss_out)
         return g, feats, res
 
     def from_host(self, h_samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames,
@@ -159,6 +163,86 @@ class HotPathStep:
                 if t is not None:
                     t.record_stream(cur)
         return feats, res
+
+
+class StepsInFlight:
+    """Device-resident steps of DIFFERENT batches in flight at the same time.
+
+    Inside one step the persistent transform (fp64 pipe and shared memory: HBM nearly idle, every SM taken) is
+    followed by the HBM-bound tail (z-score, CTC), whose CTAs retire at different times: a step alone leaves SMs
+    empty while the last CTC CTAs finish, and the memory system idle while the transform runs.  The steps of
+    consecutive batches are independent (the loader of the reference runs ahead of the training step in its own
+    thread, ``train.py:40-42``), so each resident batch gets its own ``HotPathStep`` (own streams, own scratch
+    buffers), its step is captured into a CUDA graph, and the graphs are replayed round-robin on ``lanes`` streams:
+    the next batch's transform -- limited to ``feature_ctas`` CTAs so that it never needs the whole chip -- starts on
+    the SMs the previous batch's tail has left, and that tail runs next to it.  Results are bit-identical to the
+    serial step (``tests/test_gpu_roundtrip.py``); measured on a C2 batch: 219 -> 191 us per step with two lanes,
+    flat for ``feature_ctas`` between 72 and 112 (``tools/time_overlap.py``, ``profiles/r2_overlap.md``).
+
+    ``add`` captures a batch (same arguments as ``HotPathStep.__call__``) and returns its slot: ``slot.features``,
+    ``slot.result`` and ``slot.loss_sum`` (float64 [2]: the step's own [sum loss, n], rewritten by every replay).
+    ``launch(slot)`` replays it on the next lane and returns that lane's stream; ``slot.done`` is recorded behind
+    it.  A consumer that reads ``slot.loss_sum`` on another stream hands ``launch`` an event through
+    ``slot.reusable`` (recorded after its read) so that the next replay of the slot waits for it.  ``join`` makes
+    the current stream wait for everything launched so far."""
+
+    class Slot:
+        pass
+
+    def __init__(self, device=None, lanes=2, feature_ctas=104, merged_tail=False):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(int(lanes))]
+        self.feature_ctas, self.merged_tail = int(feature_ctas), bool(merged_tail)
+        self.slots = []
+        self._k = 0
+        self._ev_start = torch.cuda.Event()
+
+    def add(self, samples, sample_offsets, sample_counts, frame_offsets, batch, total_frames, logits, labels,
+            label_len, input_len, blank=None, **kw):
+        torch = self.torch
+        s = StepsInFlight.Slot()
+        s.step = HotPathStep(self.device, feature_ctas=self.feature_ctas, merged_tail=self.merged_tail)
+        # the scratch buffers are keyed on the launch streams: steps in flight must not share one (torch hands out
+        # streams from a pool of 32 per device and priority)
+        used = {h for sl in self.slots for h in (sl.step.side.cuda_stream, sl.step.hi.cuda_stream)}
+        if {s.step.side.cuda_stream, s.step.hi.cuda_stream} & used or s.step.side.cuda_stream == s.step.hi.cuda_stream:
+            raise RuntimeError("StepsInFlight: torch's stream pool handed out a stream twice (too many resident batches)")
+        s.step.reserve(batch, total_frames, logits.shape[0] if kw.get("layout", "tbv") == "tbv" else logits.shape[1],
+                       labels.shape[1])
+        s.loss_sum = torch.zeros(2, dtype=torch.float64, device=self.device)
+        s.graph, s.features, s.result = s.step.capture(samples, sample_offsets, sample_counts, frame_offsets, batch,
+                                                       total_frames, logits, labels, label_len, input_len, blank,
+                                                       loss_out=s.loss_sum, **kw)
+        # the graph holds raw addresses: the slot keeps every tensor of the batch alive
+        s.inputs = (samples, sample_offsets, sample_counts, frame_offsets, logits, labels, label_len, input_len, kw)
+        s.done = torch.cuda.Event()
+        s.reusable = None
+        self.slots.append(s)
+        return s
+
+    def launch(self, slot):
+        torch = self.torch
+        lane = self.lanes[self._k % len(self.lanes)]
+        self._k += 1
+        # the lane starts behind whatever the caller has enqueued so far (inputs written on the current stream)
+        self._ev_start.record(torch.cuda.current_stream(self.device))
+        lane.wait_event(self._ev_start)
+        if slot.reusable is not None:
+            lane.wait_event(slot.reusable)
+            slot.reusable = None
+        with torch.cuda.stream(lane):
+            slot.graph.replay()
+            slot.done.record(lane)
+        return lane
+
+    def join(self, stream=None):
+        cur = self.torch.cuda.current_stream(self.device) if stream is None else stream
+        for lane in self.lanes:
+            cur.wait_stream(lane)
 
 
 class HostRoundTrip:

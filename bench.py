@@ -17,7 +17,9 @@ quoted on; C1 is the reference's own CPU-runnable case and a parity-test case on
       the device, mix fused into the frame load
   c5  the sweep shape: C2 batches from a larger rotating pool, greedy decode fused into the CTC pass and the
       label error (device edit distance) computed per step
-One step = the whole batch through the path.  Utterances are sharded by batch across ranks (weak scaling:
+One step = the whole batch through the path.  For c2 / c5 two steps (of different resident batches) are in flight
+at a time (pipeline.StepsInFlight, --steps-in-flight 1 for strictly serial steps): the next batch's transform runs
+next to the previous batch's HBM-bound z-score and CTC kernels; every step's work lies inside the timed region.  Utterances are sharded by batch across ranks (weak scaling:
 every rank owns its own batch); the only collective is the all-reduce of [sum loss, n], issued every second
 step on the accumulated sums (the reference prints its mean loss every second step, train.py:71-73).
 """
@@ -487,6 +489,11 @@ def main():
                     help="one kernel for the step's tail: the z-score pass as co-work of the fused CTC kernel "
                          "(bit-identical, measured no faster: profiles/r2_tail.md)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--steps-in-flight", type=int, default=None,
+                    help="device-resident steps of different batches in flight at once (pipeline.StepsInFlight); "
+                         "default 2 for c2 / c5 with graphs, 1 (strictly serial steps) otherwise")
+    ap.add_argument("--feature-ctas", type=int, default=None,
+                    help="CTAs of the persistent transform kernel (default: 104 with several steps in flight, else one per SM)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global MERGED_TAIL
@@ -516,6 +523,15 @@ def main():
         return
     wl = WORKLOADS[args.workload]
     BATCH, POOL = wl["batch"], wl["pool"]
+    graphable = (not args.no_graph) and args.surface == "logits" and args.workload in ("c2", "c3", "c5")
+    in_flight = args.steps_in_flight
+    if in_flight is None:
+        in_flight = 2 if (graphable and args.workload in ("c2", "c5")) else 1
+    if in_flight > 1 and not graphable:
+        ap.error("--steps-in-flight > 1 needs the graph path (c2 / c3 / c5, logits surface, no --no-graph)")
+    if in_flight > 1 and POOL % in_flight:
+        POOL += in_flight - POOL % in_flight          # every resident batch keeps its lane
+    feature_ctas = args.feature_ctas if args.feature_ctas is not None else (104 if in_flight > 1 else 0)
 
     # ---- (0) CPU baseline on rank 0 (N = 1 only), BEFORE CUDA is initialised so that the
     # worker processes can be forked safely ---------------------------------------------
@@ -580,9 +596,21 @@ def main():
 
     # steady state: one CUDA graph per resident batch (the step's launches, stream forks and joins replayed without
     # any host-side enqueue); c4 (one call) and the keras surface stay on the plain path
-    use_graph = (not args.no_graph) and args.surface == "logits" and args.workload in ("c2", "c3", "c5")
+    use_graph = graphable
     launches_per_step = None
-    if use_graph:
+    flight = None
+    if in_flight > 1:
+        # several steps in flight: one HotPathStep + graph per resident batch, replayed round-robin on `in_flight`
+        # lane streams; every replay writes its own [sum loss, n], summed over REDUCE_EVERY steps on the side stream
+        flight = pipeline.StepsInFlight(dev, lanes=in_flight, feature_ctas=feature_ctas, merged_tail=MERGED_TAIL)
+        for db in pool:
+            n0 = L.asrk_launch_count()
+            db.slot = flight.add(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, db.logits, db.labels,
+                                 db.label_len, db.input_len, V - 1, feat_out=db.feat, grad_out=db.grad,
+                                 grad_scale=db.grad_scale, ctc_bounds=db.ctc_bounds, decode=(args.workload == "c5"))
+            db.res = db.slot.result
+            launches_per_step = int(L.asrk_launch_count() - n0) // 2
+    elif use_graph:
         hot_path(dev).reserve(BATCH, max(d.total_frames for d in pool), max(d.logits.shape[0] for d in pool),
                               pool[0].labels.shape[1])
         for db in pool:
@@ -594,8 +622,36 @@ def main():
             launches_per_step = int(L.asrk_launch_count() - n0) // 2      # (capture() runs the step once before capturing)
         acc.zero_()
 
+    pending = []
+
+    def step_in_flight(db):
+        lane = flight.launch(db.slot)
+        if args.workload == "c5":
+            from asr_dfcnn_transformer_b200 import utils
+            with torch.cuda.stream(lane):
+                db.label_err = utils.edit_distance(db.res.tokens, db.res.token_len, db.labels, db.label_len)
+                db.slot.done.record(lane)
+        pending.append(db.slot)
+        step_no[0] += 1
+        if step_no[0] % REDUCE_EVERY == 0:
+            for sl in pending:
+                side.wait_event(sl.done)
+            with torch.cuda.stream(side):
+                red.copy_(pending[0].loss_sum)
+                for sl in pending[1:]:
+                    red.add_(sl.loss_sum)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for sl in pending:
+                    sl.reusable = ev              # the slot's next replay overwrites loss_sum: behind this read
+                if world > 1:
+                    dist.all_reduce(red, op=dist.ReduceOp.SUM)
+            pending.clear()
+
     def step(db):
-        if use_graph:
+        if flight is not None:
+            step_in_flight(db)
+        elif use_graph:
             db.graph.replay()
             if args.workload == "c5":
                 from asr_dfcnn_transformer_b200 import utils
@@ -615,6 +671,7 @@ def main():
     barrier()
     acc.zero_()
     step_no[0] = 0
+    pending.clear()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -627,7 +684,9 @@ def main():
         db = pool[i % POOL]
         step(db)
         audio += db.audio_s
-    if world > 1:
+    if flight is not None:
+        flight.join()
+    if world > 1 or flight is not None:
         torch.cuda.current_stream().wait_stream(side)
     e1.record()
     barrier()
@@ -650,6 +709,7 @@ def main():
 
     # ---- (2) per-kernel durations, live, same launches ----------------------
     kms = None
+    narrow_ms = None
     if args.surface == "logits":
         pt = PhaseTimer(torch)
         for i in range(args.steps):
@@ -658,6 +718,23 @@ def main():
             pt.end()
         torch.cuda.synchronize()
         kms = pt.summary()
+        if flight is not None and feature_ctas:
+            # the transform as the in-flight step launches it (fewer CTAs than SMs), alone, behind the same plug
+            from asr_dfcnn_transformer_b200 import features as _features
+            tot = 0.0
+            for i in range(min(args.steps, 12)):
+                db = pool[i % POOL]
+                torch.cuda._sleep(4000000)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                _features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat,
+                                             phases=_lib.PHASE_SPEC_SETUP)
+                a0.record()
+                _features.spectrogram_device(db.samples, db.so, db.sc, db.fo, db.B, db.total_frames, "fbank", out=db.feat,
+                                             phases=_lib.PHASE_SPEC_MAIN, cta_limit=feature_ctas)
+                a1.record()
+                torch.cuda.synchronize()
+                tot += a0.elapsed_time(a1)
+            narrow_ms = tot / min(args.steps, 12)
         if args.workload != "c4":
             # a noise-free batch launches no kernel in the setup phase (one small memset): what the events
             # bracket there is the host's enqueue latency, not device work
@@ -760,6 +837,12 @@ def main():
                     "step_frac": (step_alg / (ms / args.steps * 1e-3) / 1e9) / peak}
             if note:
                 roof["note"] = note
+            if flight is not None:
+                roof["in_step"] = {
+                    "transform_ctas": feature_ctas or None, "transform_alone_ms": narrow_ms,
+                    "note": "kernel_ms and frac are each kernel ALONE on the whole chip; in the timed step the transform "
+                            "runs on transform_ctas SMs next to the previous batch's z-score and CTC kernels "
+                            "(steps_in_flight), which is what step_frac measures"}
         line = {
             "metric": METRIC, "value": value, "unit": "audio-sec/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -769,6 +852,8 @@ def main():
                        "utterances_per_gpu": BATCH, "audio_s_per_step_per_gpu": audio_per_step,
                        "all_reduce": "[sum loss, n] accumulated on the device, all-reduced every %d steps" % REDUCE_EVERY,
                        "numa_node_rank0": numa, "cuda_graph": bool(use_graph),
+                       "steps_in_flight": in_flight,
+                       "feature_ctas": feature_ctas or "one per SM",
                        "tail": ("one kernel: fused CTC with the z-score as co-work" if MERGED_TAIL and args.workload in ("c2", "c5")
                                 else "z-score and CTC kernels separate"),
                        "l2": "inputs larger than L2: %d distinct batches rotated, ~%.0f MB touched per step"

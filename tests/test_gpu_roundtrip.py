@@ -122,3 +122,52 @@ def test_merged_tail_equals_two_kernel_step(B, kind):
         f2, r2 = step(samples, so, sc, fo, B, nf, logits, dlab, dll, dil, V - 1, decode=True, ctc_bounds=(5000, 600))
         torch.cuda.synchronize()
         assert torch.equal(f2, f_ref) and torch.equal(r2.loss, r_ref.loss) and torch.equal(r2.grad, r_ref.grad)
+
+
+@pytest.mark.parametrize("lanes,feature_ctas,merged,generic", [(2, 104, False, False), (3, 40, False, False),
+                                                               (2, 104, True, False), (2, 104, False, True)])
+def test_steps_in_flight_equal_serial_steps(lanes, feature_ctas, merged, generic):
+    """pipeline.StepsInFlight: the captured steps of different batches replayed round-robin on several lane streams
+    (the next batch's transform next to the previous batch's HBM-bound tail) return bit for bit what the serial step
+    returns -- features, loss, gradient, tokens, [sum loss, n] -- over several rounds with poisoned output buffers;
+    with the fused CTC kernel, the merged tail and the generic long-lattice kernels."""
+    from asr_dfcnn_transformer_b200 import ctc, features, pipeline
+    dev = torch.device("cuda", 0)
+    n_batches = 2 * lanes
+    serial = pipeline.HotPathStep(dev)
+    flight = pipeline.StepsInFlight(dev, lanes=lanes, feature_ctas=feature_ctas, merged_tail=merged)
+    want, slots, outs = [], [], []
+    for i in range(n_batches):
+        pcm, x, labels, ll, il = _batch(1300 + i, B=40 + 9 * i)
+        B, V = x.shape[1:]
+        pk = features.pack_host(pcm, pin=False)
+        so = torch.as_tensor(np.asarray(pk.sample_offsets, dtype=np.int64)).to(dev)
+        sc = torch.as_tensor(np.asarray(pk.sample_counts, dtype=np.int64)).to(dev)
+        fo = torch.as_tensor(np.asarray(pk.frame_offsets, dtype=np.int64)).to(dev)
+        nf = int(pk.frame_offsets[-1])
+        a = (pk.samples.to(dev), so, sc, fo, B, nf, torch.as_tensor(x).to(dev), torch.as_tensor(labels.astype(np.int32)).to(dev),
+             torch.as_tensor(ll).to(dev), torch.as_tensor(il).to(dev), V - 1)
+        # generic: bounds beyond the fused kernel's lattices -> rows / lattice / grad / collapse kernels (the C3 path)
+        bounds = (5000, 600) if generic else (int(il.max()), int(ll.max()))
+        f, r = serial(*a, decode=True, ctc_bounds=bounds)
+        torch.cuda.synchronize()
+        want.append((f.clone(), r.loss.clone(), r.grad.clone(), ctc.tokens_to_lists(r.tokens, r.token_len),
+                     ctc.loss_sum(r.loss, r.row_status).clone()))
+        feat = torch.empty((nf, 200), dtype=torch.float32, device=dev)
+        grad = torch.empty_like(a[6])
+        outs.append((feat, grad))
+        slots.append(flight.add(*a, feat_out=feat, grad_out=grad, decode=True, ctc_bounds=bounds))
+    for rnd in range(3):
+        for feat, grad in outs:
+            feat.fill_(float("nan"))
+            grad.fill_(float("nan"))
+        torch.cuda.synchronize()
+        for s in slots:
+            flight.launch(s)
+        flight.join()
+        torch.cuda.synchronize()
+        for s, (f, loss, grad, toks, lsum) in zip(slots, want):
+            assert torch.equal(s.features, f), rnd
+            assert torch.equal(s.result.loss, loss) and torch.equal(s.result.grad, grad), rnd
+            assert ctc.tokens_to_lists(s.result.tokens, s.result.token_len) == toks
+            assert torch.equal(s.loss_sum, lsum)
