@@ -88,6 +88,9 @@ def pack_host(signals, fs=16000, mode="fbank", noises=None, pin=True):
         offs[i] = pos
         nfr[i] = _check_frames(n_frames_for(n, fs, mode), n)
         pos += (n + align - 1) // align * align
+    if noises is not None and counts.max() > (1 << 22):
+        # asrk_snr2k_run's summation tree (include/asrk.h): a longer utterance would get a NaN gain
+        raise ValueError("noise mix: utterances of more than 2**22 samples are not supported (device SNR2K tree)")
     total = max(pos, align)
     pin = pin and torch.cuda.is_available()
     buf = torch.zeros(total, dtype=tdtype, pin_memory=pin)

@@ -56,9 +56,17 @@ def _pack_pair(signal, noise, dev, torch):
     return s, n
 
 
+SNR2K_MAX_SAMPLES = 1 << 22
+
+
 def SNR2K(signal, noise, dB):
     """noise.py:48-52 -> numpy float32 scalar (the dtype numpy 2.x gives for
-    float32 inputs), computed on the device with numpy's summation order."""
+    float32 inputs), computed on the device with numpy's summation order.
+    One limit the reference does not have: the device tree of numpy's pairwise
+    sum holds up to 2**22 samples (262 s at 16 kHz); longer inputs raise."""
+    if np.size(signal) > SNR2K_MAX_SAMPLES:
+        raise ValueError("SNR2K: %d samples; the device summation tree holds up to 2**22 (include/asrk.h, "
+                         "asrk_snr2k_run)" % np.size(signal))
     torch = _lib.require_cuda()
     L = _lib.lib()
     dev = torch.device("cuda", torch.cuda.current_device())

@@ -48,6 +48,15 @@ def test_no_cpu_fallback():
         ctc.greedy_decode(torch.zeros(3, 1, 4), [3])
 
 
+def test_snr2k_length_limit_is_loud():
+    """the one limit the reference's SNR2K does not have (device summation tree: 2**22 samples) raises at the
+    Python surface instead of returning the C ABI's NaN gain"""
+    from asr_dfcnn_transformer_b200 import noise
+    big = np.zeros(noise.SNR2K_MAX_SAMPLES + 1, np.float32)
+    with pytest.raises(ValueError, match="2\\*\\*22"):
+        noise.SNR2K(big, big, 5)
+
+
 def test_bench_workload_shapes():
     import bench
     hb = bench.make_batch(2000, batch=8)
