@@ -46,6 +46,11 @@ def test_no_cpu_fallback():
         features.compute_features([np.zeros(16000, np.int16)])
     with pytest.raises(RuntimeError):
         ctc.greedy_decode(torch.zeros(3, 1, 4), [3])
+    from asr_dfcnn_transformer_b200 import pipeline
+    with pytest.raises(RuntimeError):
+        pipeline.HotPathStep()
+    with pytest.raises(RuntimeError):
+        pipeline.StepsInFlight(lanes=2)
 
 
 def test_snr2k_length_limit_is_loud():
