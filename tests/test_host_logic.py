@@ -109,3 +109,15 @@ def test_loader_rules(tmp_path):
         symbol_list = pd.read_table(ref, header=None).iloc[:, 0].tolist()
         symbol_list.append("_")
         assert dict([p, i] for i, p in enumerate(symbol_list)) == s2i
+
+
+def test_bench_rejects_steps_in_flight_without_the_graph_path():
+    """several steps in flight are replayed CUDA graphs: workloads / surfaces that stay on the plain path refuse the
+    flag before any work is done (argparse error, exit status 2)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in (["--workload", "c4"], ["--surface", "keras"], ["--no-graph"]):
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps-in-flight", "2"] + extra,
+                             capture_output=True, text=True, timeout=120)
+        assert out.returncode == 2 and "steps-in-flight" in out.stderr, (extra, out.stderr[-500:])
